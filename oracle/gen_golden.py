@@ -1,0 +1,235 @@
+"""Generate tests/golden/*.npz by running the REAL reference (legacy generation) in the build container.
+
+    python oracle/gen_golden.py            # needs /root/reference; writes tests/golden/
+
+The reference (/root/reference/src/solvers-legacy/{full_solver,rtm_solver}.py and
+/root/reference/src/field_generator/gaussian3D.py) is imported unmodified with the two zero-source-change
+shims of SURVEY.md section 8c:
+  1. ``full_solver.omega_pe = full_solver.ScalarDomain.omega_pe``  (module global missing -> NameError at
+     full_solver.py:273 whenever phaseshift=True)
+  2. empty ``matplotlib`` / ``matplotlib.pyplot`` modules registered before ``import rtm_solver``
+     (rtm_solver.py:8-9 import them at top level; unused by the code paths exercised).
+The fixtures travel to the GPU box; /root/reference does not.  Inputs are stored next to outputs so the
+tests never need to regenerate anything with a RNG.
+"""
+import contextlib
+import io
+import os
+import sys
+import types
+
+import numpy as np
+
+REF = "/root/reference/src"
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def import_reference():
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    sys.path.insert(0, os.path.join(REF, "solvers-legacy"))
+    sys.path.insert(0, os.path.join(REF, "field_generator"))
+    import full_solver as fs
+    import rtm_solver as rtm
+    import gaussian3D as g3
+    fs.omega_pe = fs.ScalarDomain.omega_pe
+    return fs, rtm, g3
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def axes(lengths, dims):
+    return [np.linspace(-L / 2, L / 2, n) for L, n in zip(lengths, dims)]
+
+
+def gaussian_column(x, y, z, ne0=1e24, LR=1e-3):
+    """Formula of minimal_solver.test_lens (minimal_solver.py:192-201), loaded via external_ne."""
+    XX, YY, _ = np.meshgrid(x, y, z, indexing="ij")
+    return ne0 * np.exp(-(XX ** 2 + YY ** 2) / LR ** 2)
+
+
+def probe_states(rng, n, lengths, frac_out=0.15):
+    """Random 9-vectors incl. out-of-box, on-face and exact-node positions."""
+    from scipy.constants import c
+    half = np.array(lengths)[:, None] / 2
+    pos = (rng.random((3, n)) * 2 - 1) * half
+    k = int(frac_out * n)
+    pos[:, :k] *= 1.0 + 0.2 * rng.random((3, k))            # some outside
+    v = rng.standard_normal((3, n)) * 0.05 * c
+    v[2] += c
+    s = np.zeros((9, n))
+    s[:3], s[3:6] = pos, v
+    s[6] = 1.0 + 0.1 * rng.random(n)
+    s[7] = rng.random(n)
+    return s
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    fs, rtm, g3 = import_reference()
+    lwl = 1064e-9
+
+    # ---------------------------------------------------------------- G1: RHS (L0) on a non-cubic grid
+    lengths, dims, extent = (10e-3, 8e-3, 20e-3), (24, 20, 28), 10e-3
+    x, y, z = axes(lengths, dims)
+    ne = gaussian_column(x, y, z) * (1 + 0.3 * np.cos(2 * np.pi * z / 7e-3))[None, None, :]
+    rng = np.random.default_rng(11)
+    s = probe_states(rng, 4096, lengths)
+    # exact nodes / faces / the rounded-float32 end points
+    xf, yf, zf = np.float32(x), np.float32(y), np.float32(z)
+    s[0, -8:] = np.float64(xf[[0, -1, 3, 3, 0, -1, 5, 7]])
+    s[1, -8:] = np.float64(yf[[0, -1, 4, 0, -1, 2, 0, 19]])
+    s[2, -8:] = np.float64(zf[[0, -1, 5, 27, 0, 13, 27, 27]])
+    s[2, -16:-8] = -extent                                   # the beam's start plane (outside f32 z[0]?)
+    out = {}
+    for ph in (False, True):
+        dom = fs.ScalarDomain(x, y, z, extent, phaseshift=ph)
+        dom.external_ne(ne)
+        dom.calc_dndr(lwl)
+        out["dsdt_phase%d" % ph] = fs.dsdt(0.0, s.ravel().copy(), dom).reshape(9, -1)
+    np.savez_compressed(os.path.join(OUT, "g1_rhs.npz"), x=x, y=y, z=z, ne=ne, extent=extent, lwl=lwl, s=s,
+                        gradx=dom.dndx, grady=dom.dndy, gradz=dom.dndz, **out)
+
+    # ---------------------------------------------------------------- G2: shipped joint RK45, exp-cos
+    lengths, dims, extent = (10e-3, 10e-3, 20e-3), (40, 36, 48), 10e-3
+    x, y, z = axes(lengths, dims)
+    dom = fs.ScalarDomain(x, y, z, extent, phaseshift=True)
+    dom.test_exponential_cos(n_e0=2e23, Ly=1e-3, s=-4e-3)     # evaluation/test_CoherentRefractogram.ipynb cell 2
+    dom.calc_dndr(lwl)
+    np.random.seed(0)
+    s0 = fs.init_beam(384, 4e-3, 5e-5, extent, "circular", "z")
+    rf, Jf = quiet(dom.solve, s0.copy(), return_E=True)
+    g2 = dict(x=x, y=y, z=z, extent=extent, lwl=lwl, ne=dom.ne, s0=s0, sf=dom.sf, rf=rf, Jf=Jf)
+
+    # per-ray adaptive (== ScalarDomain.solve with Np=1 per ray), default and tight tolerances
+    from scipy.integrate import solve_ivp
+    sub = s0[:, :32]
+    for tag, (rtol, atol) in {"def": (1e-3, 1e-6), "tight": (1e-7, 1e-9)}.items():
+        sf1 = np.empty((9, sub.shape[1]))
+        nfev = np.empty(sub.shape[1], dtype=np.int64)
+        tt = np.linspace(0.0, np.sqrt(8.0) * extent / fs.c, 2)
+        for i in range(sub.shape[1]):
+            sol = solve_ivp(lambda t, yy: fs.dsdt(t, yy, dom), [0, tt[-1]], sub[:, i].copy(), t_eval=tt,
+                            rtol=rtol, atol=atol)
+            sf1[:, i], nfev[i] = sol.y[:, -1], sol.nfev
+        g2["perray_sf_" + tag], g2["perray_nfev_" + tag] = sf1, nfev
+
+    # fixed-step RK4 whose RHS is the reference dsdt
+    def rk4(dom, s0, n_steps):
+        h = np.sqrt(8.0) * dom.extent / fs.c / n_steps
+        yv = s0.ravel().copy()
+        f = lambda v: fs.dsdt(0.0, v, dom)
+        for _ in range(n_steps):
+            k1 = f(yv); k2 = f(yv + (0.5 * h) * k1); k3 = f(yv + (0.5 * h) * k2); k4 = f(yv + h * k3)
+            yv = yv + (h / 6.0) * (k1 + 2.0 * k2 + 2.0 * k3 + k4)
+        return yv.reshape(9, -1)
+    g2["rk4_nsteps"] = 160
+    g2["rk4_sf"] = rk4(dom, s0[:, :128], 160)
+    g2["rk4_rf"], g2["rk4_Jf"] = fs.ray_to_Jonesvector(g2["rk4_sf"], extent, probing_direction="z")
+    np.savez_compressed(os.path.join(OUT, "g2_expcos.npz"), **g2)
+
+    # ---------------------------------------------------------------- G3: turbulent field_generator grid
+    np.random.seed(1)
+    gen = g3.gaussian3D(lambda k: k ** (-11 / 3))
+    f = gen.domain_fft(l_max=1, l_min=0.01, extent=5, res=16, factor=1)      # 32^3, examples turb_gen.py:36-50
+    ne = 1e25 + 9e24 * f
+    lengths, extent = (10e-3, 10e-3, 20e-3), 10e-3
+    x, y, z = axes(lengths, ne.shape)
+    dom = fs.ScalarDomain(x, y, z, extent)
+    dom.external_ne(ne)
+    dom.calc_dndr(lwl)
+    np.random.seed(2)
+    s0 = fs.init_beam(256, 4.5e-3, 5e-5, extent, "circular", "z")
+    rf = quiet(dom.solve, s0.copy())
+    g3d = dict(x=x, y=y, z=z, extent=extent, lwl=lwl, ne=ne, s0=s0, sf=dom.sf, rf=rf,
+               rk4_nsteps=200, rk4_sf=rk4(dom, s0[:, :128], 200))
+    # other probing directions (legacy conventions, full_solver.py:574-610,856-881)
+    for pd in ("x", "y"):
+        lengths_p = {"x": (20e-3, 10e-3, 10e-3), "y": (10e-3, 20e-3, 10e-3)}[pd]
+        xp, yp, zp = axes(lengths_p, ne.shape)
+        dp = fs.ScalarDomain(xp, yp, zp, extent, probing_direction=pd)
+        dp.external_ne(ne)
+        dp.calc_dndr(lwl)
+        np.random.seed(3)
+        s0p = fs.init_beam(64, 4e-3, 5e-5, extent, "circular", pd)
+        sfp = rk4(dp, s0p, 120)
+        rfp, _ = fs.ray_to_Jonesvector(sfp, extent, probing_direction=pd)
+        g3d.update({f"{pd}_x": xp, f"{pd}_y": yp, f"{pd}_z": zp, f"{pd}_s0": s0p, f"{pd}_sf": sfp, f"{pd}_rf": rfp})
+    np.savez_compressed(os.path.join(OUT, "g3_turb.npz"), **g3d)
+
+    # ---------------------------------------------------------------- G4: optics + detector
+    rng = np.random.default_rng(5)
+    n = 5000
+    r0 = np.zeros((4, n))
+    r0[0], r0[2] = rng.normal(0, 3e-3, n), rng.normal(0, 3e-3, n)          # metres
+    r0[1], r0[3] = rng.normal(0, 2.5e-2, n), rng.normal(0, 2.5e-2, n)      # rad: many rays hit the stops
+    r0[1, :1500] *= 0.02; r0[3, :1500] *= 0.02                             # ... and many pass DF/LF stops
+    g4 = dict(r0=r0)
+    def run(cls, meth, **kw):
+        o = cls(r0.copy(), L=400, R=25)
+        getattr(o, meth)(**kw)
+        return o
+    for tag, cls, meth, kw in [("shadow_single", rtm.Shadowgraphy, "single_lens_solve", {}),
+                               ("shadow_two", rtm.Shadowgraphy, "two_lens_solve", {}),
+                               ("schlieren_DF", rtm.Schlieren, "DF_solve", {"R": 1}),
+                               ("schlieren_LF", rtm.Schlieren, "LF_solve", {"R": 1}),
+                               ("refracto_incoherent", rtm.Refractometry, "incoherent_solve", {})]:
+        o = run(cls, meth, **kw)
+        g4[tag + "_rf"] = o.rf
+        for bs in (25, 8):
+            o.histogram(bin_scale=bs)
+            g4[f"{tag}_H{bs}"] = o.H
+    # element functions one by one (incl. knife edge and rect aperture AND-quirk)
+    rmm = rtm.m_to_mm(r0[:, 1000:2000])
+    g4["el_distance"] = rtm.distance(rmm.copy(), 123.0)
+    g4["el_lens"] = rtm.lens(rmm.copy(), 200.0, 133.0)
+    g4["el_circ_ap"] = rtm.circular_aperture(rmm.copy(), 4.0)
+    g4["el_circ_stop"] = rtm.circular_stop(rmm.copy(), 4.0)
+    g4["el_rect_ap"] = rtm.rect_aperture(rmm.copy(), 3.0, 2.0)
+    g4["el_knife_y"] = rtm.knife_edge(rmm.copy(), 0.5, "y", 1)
+    g4["el_knife_x"] = rtm.knife_edge(rmm.copy(), -0.5, "x", -1)
+    # coherent chains: E from the G2 solve (phase accumulated), 384 rays, synthetic E on 2000 rays
+    E = np.zeros((2, 2000), dtype=complex)
+    ph = rng.random(2000) * 40
+    E[1] = np.cos(ph) + 1j * np.sin(ph)
+    E[0] = 0.1 * E[1] * np.exp(0.3j)
+    rc = r0[:, :2000].copy(); rc[1] *= 0.02; rc[3] *= 0.02
+    it = rtm.Interferometry(rc.copy(), E=E.copy(), L=400, R=25)
+    it.two_lens_solve(wl=lwl)
+    it.interferogram(bin_scale=40)
+    g4.update(coh_r0=rc, coh_E=E, interf_rf=it.rf, interf_rE=it.rE, interf_H40=it.H)
+    rfm = rtm.Refractometry(rc.copy(), E=E.copy(), L=400, R=25)
+    rfm.coherent_solve(wl=lwl)
+    g4.update(refr_coh_rf=rfm.rf, refr_coh_rE=rfm.rE)
+    np.savez_compressed(os.path.join(OUT, "g4_optics.npz"), **g4)
+
+    # ---------------------------------------------------------------- G5: docstring KATs + field fixture
+    # SLAB test of full_solver.py:56-82 at reduced resolution (65^3) and NULL test (full_solver.py:12-54)
+    N_V = 32; M_V = 2 * N_V + 1; ext = 5.0e-3
+    a = np.linspace(-ext, ext, M_V)
+    kat = {}
+    for name in ("null", "slab"):
+        dom = fs.ScalarDomain(a, a, a, ext)
+        dom.test_null() if name == "null" else dom.test_slab(s=10, n_e0=1e25)
+        dom.calc_dndr()                                       # default lwl 1053e-9
+        np.random.seed(4)
+        s0 = fs.init_beam(200, 5e-3, 0.5e-3, ext, "circular", "z")
+        rf = quiet(dom.solve, s0.copy())
+        kat[name + "_s0"], kat[name + "_rf"], kat[name + "_sf"] = s0, rf, dom.sf
+    # field-generator fixture in the spirit of evaluation/sergio_testing/integratedPy.npy (reduced grid)
+    xs, ys, zs = np.linspace(-5e-3, 5e-3, 20), np.linspace(-5e-3, 5e-3, 200), np.linspace(-5e-3, 5e-3, 20)
+    dom = fs.ScalarDomain(xs, ys, zs, 5e-3)
+    dom.test_linear_cos(s1=-1, s2=1, n_e0=1e26, Ly=5e-3)
+    kat["linear_cos_integrated"] = dom.ne.sum(axis=2)
+    np.savez_compressed(os.path.join(OUT, "g5_kat.npz"), axis=a, extent=ext, **kat)
+
+    for fn in sorted(os.listdir(OUT)):
+        print(fn, os.path.getsize(os.path.join(OUT, fn)) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,131 @@
+"""Pins oracle/synthpy_oracle.py to vectors produced by the REAL reference (oracle/gen_golden.py)."""
+import numpy as np
+
+from conftest import rel_err
+from oracle import synthpy_oracle as O
+
+
+def _dom(g, phaseshift=False, pd="z", pre=""):
+    d = O.Domain(g[pre + "x"], g[pre + "y"], g[pre + "z"], float(g["extent"]), phaseshift=phaseshift,
+                 probing_direction=pd)
+    d.external_ne(g["ne"])
+    d.calc_dndr(float(g["lwl"]))
+    return d
+
+
+def test_rhs_bit_exact(golden):
+    g = golden("g1_rhs")
+    for ph in (False, True):
+        d = _dom(g, phaseshift=ph)
+        out = d.dsdt(0.0, g["s"].ravel().copy()).reshape(9, -1)
+        assert np.array_equal(out, g["dsdt_phase%d" % ph])
+    for a, k in enumerate(("gradx", "grady", "gradz")):
+        assert d.grads[a].dtype == np.float32 and np.array_equal(d.grads[a], g[k])
+
+
+def test_joint_rk45_as_shipped(golden):
+    g = golden("g2_expcos")
+    d = _dom(g, phaseshift=True)
+    sf = d.solve_joint(g["s0"])
+    assert np.array_equal(sf, g["sf"])
+    rf, Jf = O.ray_to_jones(sf, float(g["extent"]))
+    assert np.array_equal(rf, g["rf"]) and np.array_equal(Jf, g["Jf"])
+
+
+def test_per_ray_and_rk4(golden):
+    g = golden("g2_expcos")
+    d = _dom(g, phaseshift=True)
+    sf, nfev = d.solve_per_ray(g["s0"][:, :8])
+    assert np.array_equal(sf, g["perray_sf_def"][:, :8]) and np.array_equal(nfev, g["perray_nfev_def"][:8])
+    sf, steps = d.solve_rk4(g["s0"][:, :128], int(g["rk4_nsteps"]))
+    assert np.array_equal(sf, g["rk4_sf"]) and (steps == int(g["rk4_nsteps"])).all()
+    rf, Jf = O.ray_to_jones(sf, float(g["extent"]))
+    assert np.array_equal(rf, g["rk4_rf"]) and np.array_equal(Jf, g["rk4_Jf"])
+
+
+def test_rk4_early_exit_is_same_line(golden):
+    g = golden("g3_turb")
+    d = _dom(g)
+    n = int(g["rk4_nsteps"])
+    sf, steps = d.solve_rk4(g["s0"][:, :64], n, early_exit=True)
+    assert steps.max() < n                                  # every ray left the box before t_end
+    rf, _ = O.ray_to_jones(sf, float(g["extent"]))
+    rf_full, _ = O.ray_to_jones(g["rk4_sf"][:, :64], float(g["extent"]))
+    assert rel_err(rf, rf_full, floor=1e-6) < 1e-11
+
+
+def test_turbulent_and_probing_directions(golden):
+    g = golden("g3_turb")
+    d = _dom(g)
+    assert np.array_equal(d.solve_joint(g["s0"]), g["sf"])
+    assert np.array_equal(d.solve_rk4(g["s0"][:, :128], int(g["rk4_nsteps"]))[0], g["rk4_sf"])
+    for pd in ("x", "y"):
+        dp = _dom(g, pd=pd, pre=pd + "_")
+        sf, _ = dp.solve_rk4(g[pd + "_s0"], 120)
+        assert np.array_equal(sf, g[pd + "_sf"])
+        assert np.array_equal(O.ray_to_jones(sf, float(g["extent"]), pd)[0], g[pd + "_rf"])
+
+
+def test_init_beam_stream(golden):
+    g = golden("g2_expcos")
+    np.random.seed(0)
+    s0 = O.init_beam(384, 4e-3, 5e-5, float(g["extent"]), "circular", "z")
+    assert np.array_equal(s0, g["s0"])
+    g3 = golden("g3_turb")
+    for pd in ("x", "y"):
+        np.random.seed(3)
+        assert np.array_equal(O.init_beam(64, 4e-3, 5e-5, float(g3["extent"]), "circular", pd), g3[pd + "_s0"])
+
+
+def test_optics_chains_and_histograms(golden):
+    g = golden("g4_optics")
+    for tag in ("shadow_single", "shadow_two", "schlieren_DF", "schlieren_LF", "refracto_incoherent"):
+        r = O.run_chain(g["r0"], O.chain(tag))
+        assert np.array_equal(r, g[tag + "_rf"], equal_nan=True), tag
+        for bs in (25, 8):
+            H = O.histogram(r, bin_scale=bs)
+            assert np.array_equal(H, g[f"{tag}_H{bs}"]), (tag, bs)
+    rmm = O.m_to_mm(g["r0"][:, 1000:2000])
+    for key, op in [("el_distance", ("travel", 123.0)), ("el_lens", ("lens", 200.0, 133.0)),
+                    ("el_circ_ap", ("circ_ap", 4.0)), ("el_circ_stop", ("circ_stop", 4.0)),
+                    ("el_rect_ap", ("rect_ap", 3.0, 2.0)), ("el_knife_y", ("knife", 0.5, 2, 1)),
+                    ("el_knife_x", ("knife", -0.5, 0, -1))]:
+        assert np.array_equal(O.apply_op(rmm, op), g[key], equal_nan=True), key
+
+
+def test_coherent_chains_and_interferogram(golden):
+    g = golden("g4_optics")
+    lwl = 1064e-9
+    r, E = O.run_chain(g["coh_r0"], O.chain("interf_two"), E=g["coh_E"], wl=lwl)
+    assert np.array_equal(r, g["interf_rf"], equal_nan=True)
+    assert np.array_equal(E, g["interf_rE"], equal_nan=True)
+    H = O.interferogram(r, E, bin_scale=40)
+    assert H.shape == g["interf_H40"].shape
+    assert rel_err(H, g["interf_H40"], floor=1e-9) < 1e-12          # unordered FP64 sums
+    r, E = O.run_chain(g["coh_r0"], O.chain("refracto_coherent"), E=g["coh_E"], wl=lwl)
+    assert np.array_equal(r, g["refr_coh_rf"], equal_nan=True)
+    assert np.array_equal(E, g["refr_coh_rE"], equal_nan=True)
+
+
+def test_docstring_kats(golden):
+    g = golden("g5_kat")
+    a, ext = g["axis"], float(g["extent"])
+    for name in ("null", "slab"):
+        d = O.Domain(a, a, a, ext)
+        d.test_null() if name == "null" else d.test_slab(s=10, n_e0=1e25)
+        d.calc_dndr()
+        sf = d.solve_joint(g[name + "_s0"])
+        rf, _ = O.ray_to_jones(sf, ext)
+        assert np.array_equal(rf, g[name + "_rf"])
+    # NULL test (full_solver.py:12-54): no deflection at all
+    s0 = g["null_s0"]
+    assert np.array_equal(g["null_rf"][1], np.arctan(s0[3] / s0[5]))
+    # SLAB test (full_solver.py:56-82): uniform deflection in -x.  Analytic: dvx/c = -(L/2nc) dne/dx = -0.0994;
+    # the shipped solver crosses the box in ~6 joint steps at rtol 1e-3, so it only lands within ~10 % of that
+    #  -- what the KAT really pins is uniformity and sign.
+    th = g["slab_rf"][1] - np.arctan(g["slab_s0"][3] / g["slab_s0"][5])
+    assert abs(th.mean() + 0.0991) < 0.015 and th.std() < 1e-4
+    xs, ys, zs = np.linspace(-5e-3, 5e-3, 20), np.linspace(-5e-3, 5e-3, 200), np.linspace(-5e-3, 5e-3, 20)
+    d = O.Domain(xs, ys, zs, 5e-3)
+    d.test_linear_cos(s1=-1, s2=1, n_e0=1e26, Ly=5e-3)
+    assert np.array_equal(d.ne.sum(axis=2), g["linear_cos_integrated"])
