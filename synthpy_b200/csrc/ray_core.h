@@ -1,0 +1,577 @@
+// Per-ray math of the synthpy_b200 hot path: trilinear field lookup, RHS, RK4 / Dormand-Prince steps,
+// exit-plane projection, ray-transfer-matrix optics and detector bin search.
+//
+// Everything here is `SP_HD` (host + device) and free of CUDA runtime calls so that the very same source
+// is (a) inlined into the sm_100a kernels in kernels.cu and (b) compiled by g++ into the CPU-side
+// self-test harness (tests/host_harness.cpp) -- the build container has no GPU, so (b) is how the
+// arithmetic is exercised before a gpurun call.  (b) is a test build, not a product path.
+//
+// Reference semantics restated here (paths relative to the reference repo root):
+//   locate()/trilinear : scipy RegularGridInterpolator linear, bounds_error=False, fill 0
+//                        (src/solvers-legacy/full_solver.py:232-234,317-332; JAX copy src/simulator/utils.py:124-214)
+//   rhs()              : dsdt, full_solver.py:516-544 (propagator.py:94-175)
+//   dp5_*              : scipy.integrate RK45 as driven by solve_ivp at full_solver.py:391
+//   exit_project()     : ray_to_Jonesvector, full_solver.py:838-894 (propagator.py:178-298)
+//   optic ops / bins   : src/solvers-legacy/rtm_solver.py:48-178,424-453 (src/simulator/diagnostics.py:122-379)
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define SP_HD __host__ __device__ __forceinline__
+#else
+#define SP_HD inline
+#endif
+
+namespace sp {
+
+struct alignas(16) f4 { float x, y, z, w; };
+struct alignas(16) d2 { double x, y; };
+struct alignas(8) f2 { float x, y; };
+
+template <typename T> struct Pair;
+template <> struct Pair<double> { typedef d2 type; };
+template <> struct Pair<float> { typedef f2 type; };
+
+// ---- small portability layer -------------------------------------------------------------------------
+SP_HD double sp_fma(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    return __fma_rn(a, b, c);
+#else
+    return a * b + c;
+#endif
+}
+SP_HD float sp_fma(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return a * b + c;
+#endif
+}
+// exactly-rounded, never-contracted multiply/add: used where the reference's value feeds an index decision
+SP_HD double mul_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b; return r;
+#endif
+}
+SP_HD double add_rn(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b; return r;
+#endif
+}
+SP_HD int floor_to_int(double x) {
+#if defined(__CUDA_ARCH__)
+    return __double2int_rd(x);
+#else
+    if (!(x == x)) return 0;
+    if (x >= 2147483000.0) return 2147483000;
+    if (x <= -2147483000.0) return -2147483000;
+    return (int)floor(x);
+#endif
+}
+SP_HD int floor_to_int(float x) {
+#if defined(__CUDA_ARCH__)
+    return __float2int_rd(x);
+#else
+    return floor_to_int((double)x);
+#endif
+}
+SP_HD double ldg(const double* p) {
+#if defined(__CUDA_ARCH__)
+    return __ldg(p);
+#else
+    return *p;
+#endif
+}
+SP_HD f4 ldg(const f4* p) {
+#if defined(__CUDA_ARCH__)
+    const float4 v = __ldg(reinterpret_cast<const float4*>(p));
+    f4 r; r.x = v.x; r.y = v.y; r.z = v.z; r.w = v.w; return r;
+#else
+    return *p;
+#endif
+}
+SP_HD d2 ldg(const d2* p) {
+#if defined(__CUDA_ARCH__)
+    const double2 v = __ldg(reinterpret_cast<const double2*>(p));
+    d2 r; r.x = v.x; r.y = v.y; return r;
+#else
+    return *p;
+#endif
+}
+SP_HD f2 ldg(const f2* p) {
+#if defined(__CUDA_ARCH__)
+    const float2 v = __ldg(reinterpret_cast<const float2*>(p));
+    f2 r; r.x = v.x; r.y = v.y; return r;
+#else
+    return *p;
+#endif
+}
+
+// ---- field view --------------------------------------------------------------------------------------
+// Kernel frame: axes (u, v, w) = (m+1, m+2, m) mod 3 of the caller's (x, y, z), m = march (probing) axis;
+// w is the fastest-varying axis of the packed grid, so the two corners a ray needs along its direction of
+// travel are one 32-byte read and a 128-byte line holds 8 consecutive cells of one (u, v) column.
+template <typename T> struct AxisTab {
+    const typename Pair<T>::type* tab;  // [n] {g[i], 1/(g[i+1]-g[i])}; entry n-1 = {g[n-1], 0}
+    T g0, inv_d;                        // uniform first guess  i ~ floor((x - g0) * inv_d)
+    T lo, hi;                           // g[0], g[n-1]: the reference's out-of-bounds test
+    int n;
+};
+
+template <typename T> struct FieldView {
+    const f4* data;       // [nu][nv][nw] {g_u, g_v, g_w, aux}
+    const double* aux64;  // [nu][nv][nw] n-1 in float64, or nullptr
+    AxisTab<T> ax[3];
+    long long su;         // element stride of u  (= nv*nw)
+    int sv;               // element stride of v  (= nw)
+};
+
+// Cell index i with g[i] <= x < g[i+1] (clipped to [0, n-2]; x == g[n-1] -> n-2) and normalised distance
+// (x - g[i]) / (g[i+1] - g[i]); false when x is outside [g[0], g[n-1]] (fill value applies).  NaN is "in
+// bounds" with a NaN weight, as in scipy (_rgi.py: find_indices + _find_out_of_bounds).
+// The weights come from the real (float32-rounded) coordinate table, not from an ideal uniform grid.
+template <typename T> SP_HD bool locate(const AxisTab<T>& A, T x, int& i, T& w) {
+    if (x < A.lo || x > A.hi) return false;
+    int k = floor_to_int((x - A.g0) * A.inv_d);
+    k = k < 0 ? 0 : (k > A.n - 2 ? A.n - 2 : k);
+    typename Pair<T>::type e = ldg(A.tab + k);
+    T d = x - e.x;
+    T ww = d * e.y;
+    if (!(d >= (T)0) || !(ww < (T)0.999999)) {
+        if (x == x) {  // exact walk against the table (rare: first guess off by one, or x within 1e-6 of a node)
+            while (k > 0 && x < ldg(A.tab + k).x) --k;
+            while (k < A.n - 2 && x >= ldg(A.tab + k + 1).x) ++k;
+            e = ldg(A.tab + k);
+            ww = (x - e.x) * e.y;
+        }
+    }
+    i = k; w = ww;
+    return true;
+}
+
+// Acceleration a = interp(grad) and, optionally, n-1 at (pu, pv, pw).  Returns false (and zeros) when
+// the point is outside the grid: no memory is touched then.
+// Corner / product order follows scipy's _evaluate_linear: weight = ((1*wu)*wv)*ww, corners in
+// itertools.product order, value accumulated left to right (fused multiply-adds differ by <= 1 ulp).
+template <typename T, bool PHASE, bool AUX64>
+SP_HD bool rhs(const FieldView<T>& F, T pu, T pv, T pw, T& au, T& av, T& aw, T& nm1) {
+    int iu, iv, iw; T wu, wv, ww;
+    au = av = aw = nm1 = (T)0;
+    if (!locate(F.ax[0], pu, iu, wu)) return false;
+    if (!locate(F.ax[1], pv, iv, wv)) return false;
+    if (!locate(F.ax[2], pw, iw, ww)) return false;
+    const long long base = (long long)iu * F.su + (long long)iv * F.sv + iw;
+    const f4* p = F.data + base;
+    const f4 c000 = ldg(p), c001 = ldg(p + 1);
+    const f4 c010 = ldg(p + F.sv), c011 = ldg(p + F.sv + 1);
+    const f4 c100 = ldg(p + F.su), c101 = ldg(p + F.su + 1);
+    const f4 c110 = ldg(p + F.su + F.sv), c111 = ldg(p + F.su + F.sv + 1);
+    const T mu = (T)1 - wu, mv = (T)1 - wv, mw = (T)1 - ww;
+    const T w00 = mu * mv, w01 = mu * wv, w10 = wu * mv, w11 = wu * wv;
+    const T k000 = w00 * mw, k001 = w00 * ww, k010 = w01 * mw, k011 = w01 * ww;
+    const T k100 = w10 * mw, k101 = w10 * ww, k110 = w11 * mw, k111 = w11 * ww;
+#define SP_ACC(comp)                                                                                     \
+    sp_fma((T)c111.comp, k111, sp_fma((T)c110.comp, k110, sp_fma((T)c101.comp, k101,                      \
+    sp_fma((T)c100.comp, k100, sp_fma((T)c011.comp, k011, sp_fma((T)c010.comp, k010,                      \
+    sp_fma((T)c001.comp, k001, (T)c000.comp * k000)))))))
+    au = SP_ACC(x); av = SP_ACC(y); aw = SP_ACC(z);
+    if (PHASE) {
+        if (AUX64) {
+            const double* q = F.aux64 + base;
+            const double a000 = ldg(q), a001 = ldg(q + 1), a010 = ldg(q + F.sv), a011 = ldg(q + F.sv + 1);
+            const double a100 = ldg(q + F.su), a101 = ldg(q + F.su + 1);
+            const double a110 = ldg(q + F.su + F.sv), a111 = ldg(q + F.su + F.sv + 1);
+            nm1 = sp_fma((T)a111, k111, sp_fma((T)a110, k110, sp_fma((T)a101, k101, sp_fma((T)a100, k100,
+                  sp_fma((T)a011, k011, sp_fma((T)a010, k010, sp_fma((T)a001, k001, (T)a000 * k000)))))));
+        } else {
+            nm1 = SP_ACC(w);
+        }
+    }
+#undef SP_ACC
+    return true;
+}
+
+// ---- ray state ---------------------------------------------------------------------------------------
+template <typename T> struct Ray {
+    T p[3];   // position, kernel frame
+    T v[3];   // velocity
+    T ph;     // accumulated phase (state row 7)
+};
+
+// True when the ray is outside the grid on some axis and not moving back towards it: its RHS is zero for
+// ever, so integration can stop (exit_project puts it on the same straight line).
+template <typename T> SP_HD bool escaped(const FieldView<T>& F, const Ray<T>& r) {
+    bool e = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        e = e || (r.p[k] > F.ax[k].hi && r.v[k] >= (T)0) || (r.p[k] < F.ax[k].lo && r.v[k] <= (T)0);
+    return e;
+}
+
+// Classical RK4 step of  p' = v, v' = a(p), ph' = omega (n(p) - 1).  Returns how many of the four RHS
+// evaluations touched the field.  Combination order is y + (h/6)(((k1 + 2k2) + 2k3) + k4).
+template <typename T, bool PHASE, bool AUX64>
+SP_HD int rk4_step(const FieldView<T>& F, T h, T omega, Ray<T>& r) {
+    const T hh = (T)0.5 * h, h6 = h / (T)6;
+    T a1[3], a2[3], a3[3], a4[3], n1, n2, n3, n4;
+    T v2[3], v3[3], v4[3];
+    int touched = 0;
+    touched += rhs<T, PHASE, AUX64>(F, r.p[0], r.p[1], r.p[2], a1[0], a1[1], a1[2], n1);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v2[k] = sp_fma(hh, a1[k], r.v[k]);
+    touched += rhs<T, PHASE, AUX64>(F, sp_fma(hh, r.v[0], r.p[0]), sp_fma(hh, r.v[1], r.p[1]),
+                                    sp_fma(hh, r.v[2], r.p[2]), a2[0], a2[1], a2[2], n2);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v3[k] = sp_fma(hh, a2[k], r.v[k]);
+    touched += rhs<T, PHASE, AUX64>(F, sp_fma(hh, v2[0], r.p[0]), sp_fma(hh, v2[1], r.p[1]),
+                                    sp_fma(hh, v2[2], r.p[2]), a3[0], a3[1], a3[2], n3);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) v4[k] = sp_fma(h, a3[k], r.v[k]);
+    touched += rhs<T, PHASE, AUX64>(F, sp_fma(h, v3[0], r.p[0]), sp_fma(h, v3[1], r.p[1]),
+                                    sp_fma(h, v3[2], r.p[2]), a4[0], a4[1], a4[2], n4);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const T sp_ = ((r.v[k] + (T)2 * v2[k]) + (T)2 * v3[k]) + v4[k];
+        const T sv_ = ((a1[k] + (T)2 * a2[k]) + (T)2 * a3[k]) + a4[k];
+        r.p[k] = sp_fma(h6, sp_, r.p[k]);
+        r.v[k] = sp_fma(h6, sv_, r.v[k]);
+    }
+    if (PHASE) {
+        const T sn = ((n1 + (T)2 * n2) + (T)2 * n3) + n4;
+        r.ph = sp_fma(h6, omega * sn, r.ph);
+    }
+    return touched;
+}
+
+// ---- Dormand-Prince 5(4) with SciPy's controller -------------------------------------------------------
+// Tableau of scipy/integrate/_ivp/rk.py::RK45 (Dormand & Prince 1980).
+struct DP {
+    static constexpr double c2 = 1.0 / 5, c3 = 3.0 / 10, c4 = 4.0 / 5, c5 = 8.0 / 9;
+    static constexpr double a21 = 1.0 / 5;
+    static constexpr double a31 = 3.0 / 40, a32 = 9.0 / 40;
+    static constexpr double a41 = 44.0 / 45, a42 = -56.0 / 15, a43 = 32.0 / 9;
+    static constexpr double a51 = 19372.0 / 6561, a52 = -25360.0 / 2187, a53 = 64448.0 / 6561, a54 = -212.0 / 729;
+    static constexpr double a61 = 9017.0 / 3168, a62 = -355.0 / 33, a63 = 46732.0 / 5247, a64 = 49.0 / 176,
+                            a65 = -5103.0 / 18656;
+    static constexpr double b1 = 35.0 / 384, b3 = 500.0 / 1113, b4 = 125.0 / 192, b5 = -2187.0 / 6784, b6 = 11.0 / 84;
+    static constexpr double e1 = -71.0 / 57600, e3 = 71.0 / 16695, e4 = -71.0 / 1920, e5 = 17253.0 / 339200,
+                            e6 = -22.0 / 525, e7 = 1.0 / 40;
+    static constexpr double SAFETY = 0.9, MIN_FACTOR = 0.2, MAX_FACTOR = 10.0;
+};
+
+// Derivative of the 7 live components (p, v, ph) at a state; amp and pol have zero derivative.
+template <typename T> struct Deriv { T dp[3]; T dv[3]; T dph; };
+
+template <typename T, bool PHASE, bool AUX64>
+SP_HD int deriv(const FieldView<T>& F, T omega, const T* p, const T* v, Deriv<T>& k) {
+    T nm1;
+    int t = rhs<T, PHASE, AUX64>(F, p[0], p[1], p[2], k.dv[0], k.dv[1], k.dv[2], nm1);
+    k.dp[0] = v[0]; k.dp[1] = v[1]; k.dp[2] = v[2];
+    k.dph = PHASE ? omega * nm1 : (T)0;
+    return t;
+}
+
+// One attempted DP5 step of size h from (r, k1 = f(r)).  Outputs the 5th-order state, f(new state) (FSAL)
+// and sum over the live components of (err_i / scale_i)^2 with scale = atol + rtol max(|y|, |y_new|)
+// (rk.py:_step_impl).  amp (|y| = amp0) and pol contribute zero error.
+template <typename T, bool PHASE, bool AUX64>
+SP_HD int dp5_attempt(const FieldView<T>& F, T omega, T h, T rtol, T atol, const Ray<T>& r, const Deriv<T>& k1,
+                      Ray<T>& rn, Deriv<T>& k7, T& err_sq) {
+    Deriv<T> k2, k3, k4, k5, k6;
+    T p[3], v[3];
+    int touched = 0;
+    // stage states: y + (K[:s].T @ a[:s]) * h     (rk.py: rk_step)
+#define SP_STAGE(expr_p, expr_v)                          \
+    _Pragma("unroll") for (int c = 0; c < 3; ++c) {       \
+        p[c] = r.p[c] + (expr_p) * h;                     \
+        v[c] = r.v[c] + (expr_v) * h;                     \
+    }
+    SP_STAGE((T)DP::a21 * k1.dp[c], (T)DP::a21 * k1.dv[c]);
+    touched += deriv<T, PHASE, AUX64>(F, omega, p, v, k2);
+    SP_STAGE((T)DP::a31 * k1.dp[c] + (T)DP::a32 * k2.dp[c], (T)DP::a31 * k1.dv[c] + (T)DP::a32 * k2.dv[c]);
+    touched += deriv<T, PHASE, AUX64>(F, omega, p, v, k3);
+    SP_STAGE((T)DP::a41 * k1.dp[c] + (T)DP::a42 * k2.dp[c] + (T)DP::a43 * k3.dp[c],
+             (T)DP::a41 * k1.dv[c] + (T)DP::a42 * k2.dv[c] + (T)DP::a43 * k3.dv[c]);
+    touched += deriv<T, PHASE, AUX64>(F, omega, p, v, k4);
+    SP_STAGE((T)DP::a51 * k1.dp[c] + (T)DP::a52 * k2.dp[c] + (T)DP::a53 * k3.dp[c] + (T)DP::a54 * k4.dp[c],
+             (T)DP::a51 * k1.dv[c] + (T)DP::a52 * k2.dv[c] + (T)DP::a53 * k3.dv[c] + (T)DP::a54 * k4.dv[c]);
+    touched += deriv<T, PHASE, AUX64>(F, omega, p, v, k5);
+    SP_STAGE((T)DP::a61 * k1.dp[c] + (T)DP::a62 * k2.dp[c] + (T)DP::a63 * k3.dp[c] + (T)DP::a64 * k4.dp[c] +
+                 (T)DP::a65 * k5.dp[c],
+             (T)DP::a61 * k1.dv[c] + (T)DP::a62 * k2.dv[c] + (T)DP::a63 * k3.dv[c] + (T)DP::a64 * k4.dv[c] +
+                 (T)DP::a65 * k5.dv[c]);
+    touched += deriv<T, PHASE, AUX64>(F, omega, p, v, k6);
+#undef SP_STAGE
+    // y_new = y + h * (K[:-1].T @ B)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        rn.p[c] = r.p[c] + h * ((T)DP::b1 * k1.dp[c] + (T)DP::b3 * k3.dp[c] + (T)DP::b4 * k4.dp[c] +
+                                (T)DP::b5 * k5.dp[c] + (T)DP::b6 * k6.dp[c]);
+        rn.v[c] = r.v[c] + h * ((T)DP::b1 * k1.dv[c] + (T)DP::b3 * k3.dv[c] + (T)DP::b4 * k4.dv[c] +
+                                (T)DP::b5 * k5.dv[c] + (T)DP::b6 * k6.dv[c]);
+    }
+    rn.ph = r.ph;
+    if (PHASE)
+        rn.ph = r.ph + h * ((T)DP::b1 * k1.dph + (T)DP::b3 * k3.dph + (T)DP::b4 * k4.dph + (T)DP::b5 * k5.dph +
+                            (T)DP::b6 * k6.dph);
+    touched += deriv<T, PHASE, AUX64>(F, omega, rn.p, rn.v, k7);
+    // error estimate  (K.T @ E) * h / scale
+    T acc = (T)0;
+#define SP_ERR(y0, y1, K1, K3, K4, K5, K6, K7)                                                           \
+    {                                                                                                    \
+        const T e = ((T)DP::e1 * (K1) + (T)DP::e3 * (K3) + (T)DP::e4 * (K4) + (T)DP::e5 * (K5) +         \
+                     (T)DP::e6 * (K6) + (T)DP::e7 * (K7)) * h;                                            \
+        const T a0 = fabs(y0), a1_ = fabs(y1);                                                           \
+        const T q = e / (atol + (a0 > a1_ ? a0 : a1_) * rtol);                                           \
+        acc += q * q;                                                                                    \
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        SP_ERR(r.p[c], rn.p[c], k1.dp[c], k3.dp[c], k4.dp[c], k5.dp[c], k6.dp[c], k7.dp[c]);
+        SP_ERR(r.v[c], rn.v[c], k1.dv[c], k3.dv[c], k4.dv[c], k5.dv[c], k6.dv[c], k7.dv[c]);
+    }
+    if (PHASE) SP_ERR(r.ph, rn.ph, k1.dph, k3.dph, k4.dph, k5.dph, k6.dph, k7.dph);
+#undef SP_ERR
+    err_sq = acc;
+    return touched;
+}
+
+// Step-size factor after an attempt with RMS error norm `en` (rk.py:_step_impl).
+template <typename T> SP_HD T dp5_factor(T en, bool accepted, bool rejected_before) {
+    if (accepted) {
+        T f = (en == (T)0) ? (T)DP::MAX_FACTOR : fmin((T)DP::MAX_FACTOR, (T)DP::SAFETY * pow(en, (T)-0.2));
+        if (rejected_before) f = fmin((T)1, f);
+        return f;
+    }
+    return fmax((T)DP::MIN_FACTOR, (T)DP::SAFETY * pow(en, (T)-0.2));
+}
+
+// Hairer's initial step as coded in scipy/integrate/_ivp/common.py::select_initial_step (order = 4), with
+// the RMS norms taken over the ray's own n_state components (amp contributes (amp/scale)^2 to d0 only).
+template <typename T, bool PHASE, bool AUX64>
+SP_HD T dp5_initial_step(const FieldView<T>& F, T omega, T t_end, T rtol, T atol, int n_state, T amp, T pol,
+                         const Ray<T>& r, const Deriv<T>& f0, int& touched) {
+    if (t_end == (T)0) return (T)0;
+    const T inv_n = (T)1 / (T)n_state;
+    T s0 = (T)0, s1 = (T)0;
+    T sc_p[3], sc_v[3], sc_ph;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        sc_p[c] = atol + fabs(r.p[c]) * rtol;
+        sc_v[c] = atol + fabs(r.v[c]) * rtol;
+        T q = r.p[c] / sc_p[c]; s0 += q * q;
+        q = r.v[c] / sc_v[c]; s0 += q * q;
+        q = f0.dp[c] / sc_p[c]; s1 += q * q;
+        q = f0.dv[c] / sc_v[c]; s1 += q * q;
+    }
+    sc_ph = atol + fabs(r.ph) * rtol;
+    { T q = r.ph / sc_ph; s0 += q * q; q = f0.dph / sc_ph; s1 += q * q; }
+    if (n_state > 6) {
+        T q = amp / (atol + fabs(amp) * rtol); s0 += q * q;
+        q = pol / (atol + fabs(pol) * rtol); s0 += q * q;
+    }
+    const T d0 = sqrt(s0 * inv_n), d1 = sqrt(s1 * inv_n);
+    T h0 = (d0 < (T)1e-5 || d1 < (T)1e-5) ? (T)1e-6 : (T)0.01 * d0 / d1;
+    h0 = fmin(h0, t_end);
+    T p1[3], v1[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { p1[c] = r.p[c] + h0 * f0.dp[c]; v1[c] = r.v[c] + h0 * f0.dv[c]; }
+    Deriv<T> f1;
+    touched += deriv<T, PHASE, AUX64>(F, omega, p1, v1, f1);
+    T s2 = (T)0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        T q = (f1.dp[c] - f0.dp[c]) / sc_p[c]; s2 += q * q;
+        q = (f1.dv[c] - f0.dv[c]) / sc_v[c]; s2 += q * q;
+    }
+    { T q = (f1.dph - f0.dph) / sc_ph; s2 += q * q; }
+    const T d2 = sqrt(s2 * inv_n) / h0;
+    T h1;
+    if (d1 <= (T)1e-15 && d2 <= (T)1e-15) h1 = fmax((T)1e-6, h0 * (T)1e-3);
+    else h1 = pow((T)0.01 / fmax(d1, d2), (T)0.2);
+    return fmin(fmin((T)100 * h0, h1), t_end);
+}
+
+// ---- exit plane ------------------------------------------------------------------------------------------
+// ray_to_Jonesvector (full_solver.py:838-894): back-project to the plane coord[p] = extent; angles atan(v_a/v_p).
+// kp/ka/kb are kernel-frame indices of the probing axis and of the axes that land in rf rows (0,1) / (2,3).
+template <typename T>
+SP_HD void exit_project(const Ray<T>& r, int kp, int ka, int kb, T extent, T& xa, T& tha, T& xb, T& thb) {
+    const T tbp = (r.p[kp] - extent) / r.v[kp];
+    xa = r.p[ka] - r.v[ka] * tbp;
+    xb = r.p[kb] - r.v[kb] * tbp;
+    tha = atan(r.v[ka] / r.v[kp]);
+    thb = atan(r.v[kb] / r.v[kp]);
+}
+
+// ---- optics ------------------------------------------------------------------------------------------------
+struct OpticOp { int kind; int pad; double p0, p1, p2; };
+enum { OP_TRAVEL = 0, OP_TRAVEL_NOE = 1, OP_LENS = 2, OP_CIRC_AP = 3, OP_CIRC_STOP = 4, OP_RECT_AP = 5,
+       OP_KNIFE = 6, OP_REF_BEAM = 7 };
+
+struct DetRay {
+    double x, th, y, ph;      // mm, rad
+    double ex_re, ex_im, ey_re, ey_im;
+    bool alive;
+};
+
+SP_HD void sp_sincos(double a, double* s, double* c) {
+#if defined(__CUDA_ARCH__)
+    sincos(a, s, c);
+#else
+    *s = sin(a); *c = cos(a);
+#endif
+}
+
+SP_HD void cmul_phase(double& re, double& im, double arg) {
+    double s, c; sp_sincos(arg, &s, &c);
+    const double r = re * c - im * s, i = re * s + im * c;   // (re + i im)(c + i s), numpy's complex product
+    re = r; im = i;
+}
+
+// Applies the optical train to one ray.  rf (metres) -> m_to_mm -> ops.  Matrix elements are applied as the
+// reference's np.matmul of a block-diagonal 4x4 does: x' = 1*x + d*th (products then sum).  Rejected rays
+// are flagged dead (the reference sets the column to NaN; every later element keeps it NaN).
+// E advances by exp(i k sqrt(dx^2 + dy^2)) across TRAVEL (k = 2 pi / wavelength, positions in mm: the
+// reference's own unit mix, diagnostics.py:315-321).  Across a lens dx = dy = 0 so the factor is exactly 1.
+SP_HD void run_optics(DetRay& d, double x_m, double y_m, const OpticOp* ops, int n_ops, bool with_E, double kwave) {
+    for (int i = 0; i < n_ops && d.alive; ++i) {
+        const OpticOp op = ops[i];
+        switch (op.kind) {
+            case OP_TRAVEL:
+            case OP_TRAVEL_NOE: {
+                const double nx = add_rn(d.x, mul_rn(op.p0, d.th));
+                const double ny = add_rn(d.y, mul_rn(op.p0, d.ph));
+                if (with_E && op.kind == OP_TRAVEL) {
+                    const double dx = nx - d.x, dy = ny - d.y;
+                    const double arg = mul_rn(kwave, sqrt(add_rn(mul_rn(dx, dx), mul_rn(dy, dy))));
+                    cmul_phase(d.ex_re, d.ex_im, arg);
+                    cmul_phase(d.ey_re, d.ey_im, arg);
+                }
+                d.x = nx; d.y = ny;
+            } break;
+            case OP_LENS:
+                d.th = add_rn(mul_rn(-1.0 / op.p0, d.x), d.th);
+                d.ph = add_rn(mul_rn(-1.0 / op.p1, d.y), d.ph);
+                break;
+            case OP_CIRC_AP:
+                if (add_rn(mul_rn(d.x, d.x), mul_rn(d.y, d.y)) > op.p0 * op.p0) d.alive = false;
+                break;
+            case OP_CIRC_STOP:
+                if (add_rn(mul_rn(d.x, d.x), mul_rn(d.y, d.y)) < op.p0 * op.p0) d.alive = false;
+                break;
+            case OP_RECT_AP:   // only rays outside BOTH half-widths are rejected (rtm_solver.py:114-117)
+                if (d.x * d.x > op.p0 * op.p0 && d.y * d.y > op.p1 * op.p1) d.alive = false;
+                break;
+            case OP_KNIFE: {
+                const double c = (op.p1 < 1.0) ? d.x : d.y;
+                if (op.p2 > 0 ? (c > op.p0) : (c < op.p0)) d.alive = false;
+            } break;
+            case OP_REF_BEAM: {   // diagnostics.py:559-581 (uses exit positions in METRES)
+                double deg = op.p1;
+                if (deg >= 45.0) deg = -fabs(deg - 90.0);
+                const double rad = deg * 3.14159265358979323846 / 180.0;
+                const double yw = atan(rad), xw = sqrt(1.0 - yw * yw);
+                double s, c; sp_sincos(2.0 * op.p0 / 3.0 * (xw * x_m + yw * y_m), &s, &c);
+                d.ey_re += c; d.ey_im += s;
+            } break;
+            default: break;
+        }
+        // NaN positions: comparisons above are false, as in NumPy; the ray stays "alive" but can never be
+        // binned (bin search fails on NaN), matching the reference's isnan filter.
+    }
+}
+
+// ---- detector bins ---------------------------------------------------------------------------------------
+// np.linspace(lo, hi, nb+1)[i] = i * step + lo with step = (hi - lo) / nb, last edge forced to hi.
+SP_HD double lin_edge(double lo, double hi, double step, int nb, int i) {
+    return (i >= nb) ? hi : add_rn(mul_rn((double)i, step), lo);
+}
+
+// histogram mode: index of the bin with edge[i] <= v < edge[i+1], v == hi -> nb-1  (np.histogram2d);
+// digitize mode : np.digitize(v, edges) - 1 must be in [0, nb-1], so v == hi is OUT (rtm_solver.py:439-444).
+// Returns -1 when the value is not binned (outside, NaN).
+SP_HD int bin_index(double v, double lo, double hi, int nb, bool right_inclusive) {
+    if (!(v >= lo) || !(v <= hi)) return -1;
+    if (v == hi) return right_inclusive ? nb - 1 : -1;
+    const double step = (hi - lo) / (double)nb;
+    int i = floor_to_int((v - lo) / step);
+    i = i < 0 ? 0 : (i > nb - 1 ? nb - 1 : i);
+    while (i > 0 && v < lin_edge(lo, hi, step, nb, i)) --i;
+    while (i < nb - 1 && v >= lin_edge(lo, hi, step, nb, i + 1)) ++i;
+    return i;
+}
+
+// ---- Philox4x32-10 beam generator ---------------------------------------------------------------------------
+struct Philox {
+    uint32_t k0, k1;
+    SP_HD static void mulhilo(uint32_t a, uint32_t b, uint32_t& hi, uint32_t& lo) {
+        const uint64_t p = (uint64_t)a * b;
+        hi = (uint32_t)(p >> 32); lo = (uint32_t)p;
+    }
+    SP_HD void block(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t out[4]) const {
+        uint32_t a = k0, b = k1;
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t h0, l0, h1, l1;
+            mulhilo(0xD2511F53u, c0, h0, l0);
+            mulhilo(0xCD9E8D57u, c2, h1, l1);
+            const uint32_t n0 = h1 ^ c1 ^ a, n2 = h0 ^ c3 ^ b;
+            c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+            a += 0x9E3779B9u; b += 0xBB67AE85u;
+        }
+        out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+    }
+};
+
+SP_HD double u53(uint32_t hi, uint32_t lo) {   // uniform in [0,1) with 53 random bits, like NumPy's random_sample
+    return (double)((((uint64_t)hi << 32) | lo) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+struct BeamSpec { int beam_type, probing_axis; double size_a, size_b, divergence, start; uint64_t seed; };
+enum { BEAM_CIRC_FOLD = 0, BEAM_CIRC_POW2 = 1, BEAM_SQUARE = 2, BEAM_RECT = 3, BEAM_LINEAR = 4 };
+
+// Initial state of global ray `idx` in the CALLER's frame: s[0..5] = x,y,z,vx,vy,vz; amp = 1, phase = pol = 0.
+// Distributions follow init_beam (full_solver.py:547-835) / Beam.init_beam (beam.py:35-303).
+SP_HD void beam_ray(const BeamSpec& B, uint64_t idx, double s[6]) {
+    const double C = 299792458.0, PI = 3.14159265358979323846;
+    Philox ph; ph.k0 = (uint32_t)B.seed; ph.k1 = (uint32_t)(B.seed >> 32);
+    uint32_t r0[4], r1[4], r2[4];
+    ph.block((uint32_t)idx, (uint32_t)(idx >> 32), 0u, 0x5eedu, r0);
+    ph.block((uint32_t)idx, (uint32_t)(idx >> 32), 1u, 0x5eedu, r1);
+    ph.block((uint32_t)idx, (uint32_t)(idx >> 32), 2u, 0x5eedu, r2);
+    const double U0 = u53(r0[0], r0[1]), U1 = u53(r0[2], r0[3]), U2 = u53(r1[0], r1[1]);
+    const double U3 = u53(r1[2], r1[3]), U4 = u53(r2[0], r2[1]), U5 = u53(r2[2], r2[3]);
+    // chi ~ divergence * N(0,1)  (Box-Muller);  phi ~ U[0, pi)
+    const double chi = B.divergence * sqrt(-2.0 * log(1.0 - U4)) * cos(2.0 * PI * U5);
+    const double phi = PI * U3;
+    double a, b;
+    double vpar = C * cos(chi), v1 = C * sin(chi) * cos(phi), v2 = C * sin(chi) * sin(phi);
+    switch (B.beam_type) {
+        case BEAM_CIRC_FOLD: {
+            const double t = 2.0 * PI * U0;
+            double u = U1 + U2; if (u > 1.0) u = 2.0 - u;
+            a = B.size_a * u * cos(t); b = B.size_a * u * sin(t);
+        } break;
+        case BEAM_CIRC_POW2: {
+            const double t = 2.0 * PI * U0, u = sqrt(U1);
+            a = B.size_a * u * cos(t); b = B.size_a * u * sin(t);
+        } break;
+        case BEAM_SQUARE: a = B.size_a * (2.0 * U1 - 1.0); b = B.size_a * (2.0 * U0 - 1.0); break;
+        case BEAM_RECT: a = B.size_a * (2.0 * U1 - 1.0); b = B.size_b * (2.0 * U0 - 1.0); break;
+        default: /* BEAM_LINEAR: x-z plane only (full_solver.py:707-720) */
+            s[0] = B.size_a * (2.0 * U0 - 1.0); s[1] = 0.0; s[2] = B.start;
+            s[3] = C * sin(chi); s[4] = 0.0; s[5] = C * cos(chi);
+            return;
+    }
+    if (B.probing_axis == 0) { s[0] = B.start; s[1] = a; s[2] = b; s[3] = vpar; s[4] = v1; s[5] = v2; }
+    else if (B.probing_axis == 2) { s[0] = a; s[1] = b; s[2] = B.start; s[3] = v1; s[4] = v2; s[5] = vpar; }
+    else { s[0] = a; s[1] = B.start; s[2] = b; s[3] = v1; s[4] = vpar; s[5] = v2; }
+}
+
+}  // namespace sp

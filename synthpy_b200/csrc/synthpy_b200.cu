@@ -1,0 +1,1124 @@
+// synthpy_b200 -- sm_100a kernels and the C ABI of include/synthpy_b200.h.
+//
+// Kernels (all hand-written for sm_100a; no library calls on the data path):
+//   k_normalise_ne / k_pack_from_ne / k_pack_from_grads : field preparation (float32 stencil == np.gradient)
+//   k_sort_keys / k_scan / k_sort_scatter               : counting sort of rays into coherent bundles
+//   k_propagate<T, METHOD, PHASE, AUX64>                 : persistent ray integrator + fused optics/binning
+//   k_joint_*                                           : the reference's joint-step RK45 (one h for all rays)
+//   k_optics_image / k_finalize / k_rhs / k_beam        : stand-alone entry points
+//
+// Per-ray arithmetic lives in ray_core.h (shared with the CPU self-test build).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/synthpy_b200.h"
+#include "ray_core.h"
+#include "field_prep.h"
+
+using namespace sp;
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static std::atomic<uint64_t> g_launches{0};
+
+static int fail(int code, const std::string& msg) { g_err = msg; return code; }
+#define CU(x)                                                                                            \
+    do {                                                                                                 \
+        cudaError_t e_ = (x);                                                                            \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(SP_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_));                      \
+    } while (0)
+#define LAUNCH_CHECK()                                                                                   \
+    do {                                                                                                 \
+        g_launches.fetch_add(1);                                                                         \
+        CU(cudaGetLastError());                                                                          \
+    } while (0)
+
+extern "C" int sp_version(void) { return SP_ABI_VERSION; }
+extern "C" const char* sp_last_error(void) { return g_err.c_str(); }
+extern "C" uint64_t sp_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------------------- field
+struct sp_field {
+    int n[3];          // caller-frame dims nx, ny, nz
+    int perm[3];       // kernel axis k -> caller axis
+    int nk[3];         // kernel-frame dims nu, nv, nw
+    f4* data = nullptr;
+    double* aux64 = nullptr;
+    d2* tab64[3] = {nullptr, nullptr, nullptr};   // kernel-frame axis tables
+    f2* tab32[3] = {nullptr, nullptr, nullptr};
+    double g0[3], inv_d[3], lo[3], hi[3];         // kernel frame
+    int device = 0;
+    uint64_t bytes = 0;
+};
+
+template <typename T> static FieldView<T> make_view(const sp_field* f);
+template <> FieldView<double> make_view<double>(const sp_field* f) {
+    FieldView<double> V;
+    V.data = f->data; V.aux64 = f->aux64;
+    for (int k = 0; k < 3; ++k) {
+        V.ax[k].tab = f->tab64[k]; V.ax[k].g0 = f->g0[k]; V.ax[k].inv_d = f->inv_d[k];
+        V.ax[k].lo = f->lo[k]; V.ax[k].hi = f->hi[k]; V.ax[k].n = f->nk[k];
+    }
+    V.su = (long long)f->nk[1] * f->nk[2]; V.sv = f->nk[2];
+    return V;
+}
+template <> FieldView<float> make_view<float>(const sp_field* f) {
+    FieldView<float> V;
+    V.data = f->data; V.aux64 = f->aux64;
+    for (int k = 0; k < 3; ++k) {
+        V.ax[k].tab = f->tab32[k]; V.ax[k].g0 = (float)f->g0[k]; V.ax[k].inv_d = (float)f->inv_d[k];
+        V.ax[k].lo = (float)f->lo[k]; V.ax[k].hi = (float)f->hi[k]; V.ax[k].n = f->nk[k];
+    }
+    V.su = (long long)f->nk[1] * f->nk[2]; V.sv = f->nk[2];
+    return V;
+}
+
+template <typename NE>
+__global__ void k_normalise_ne(const NE* __restrict__ ne, float* __restrict__ out, long long total, double nc) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < total; i += stride) out[i] = normalise_ne(ne[i], nc);
+}
+
+// One thread per packed cell; neighbouring threads are neighbours along w (coalesced float4 stores).
+template <typename NE>
+__global__ void k_pack_from_ne(const float* __restrict__ ne_nc, const NE* __restrict__ ne, f4* __restrict__ out,
+                               double* __restrict__ aux64, PackArgs P) {
+    const long long total = (long long)P.nk[0] * P.nk[1] * P.nk[2];
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    for (; t < total; t += gstride) {
+        double nm1;
+        out[t] = pack_cell(t, ne_nc, ne, P, nm1);
+        if (aux64) aux64[t] = nm1;
+    }
+}
+
+__global__ void k_pack_from_grads(const float* __restrict__ gx, const float* __restrict__ gy,
+                                  const float* __restrict__ gz, const float* __restrict__ aux32,
+                                  const double* __restrict__ aux64_in, f4* __restrict__ out,
+                                  double* __restrict__ aux64, PackArgs P) {
+    const long long total = (long long)P.nk[0] * P.nk[1] * P.nk[2];
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    for (; t < total; t += gstride) {
+        int ic[3];
+        const long long idx = unpack_index(t, P, ic);
+        const float g[3] = {gx[idx], gy[idx], gz[idx]};
+        f4 v; v.x = g[P.perm[0]]; v.y = g[P.perm[1]]; v.z = g[P.perm[2]];
+        v.w = aux32 ? aux32[idx] : (aux64_in ? (float)aux64_in[idx] : 0.f);
+        if (aux64 && aux64_in) aux64[t] = aux64_in[idx];
+        out[t] = v;
+    }
+}
+
+__global__ void k_export_grads(const f4* __restrict__ in, float* gx, float* gy, float* gz, float* aux, PackArgs P) {
+    const long long total = (long long)P.nk[0] * P.nk[1] * P.nk[2];
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    for (; t < total; t += gstride) {
+        int ic[3];
+        const long long idx = unpack_index(t, P, ic);
+        const f4 v = in[t];
+        float g[3];
+        g[P.perm[0]] = v.x; g[P.perm[1]] = v.y; g[P.perm[2]] = v.z;
+        if (gx) gx[idx] = g[0];
+        if (gy) gy[idx] = g[1];
+        if (gz) gz[idx] = g[2];
+        if (aux) aux[idx] = v.w;
+    }
+}
+
+static int field_common(sp_field* f, const float* axh[3], int nx, int ny, int nz, int march_axis, cudaStream_t st) {
+    if (nx < 2 || ny < 2 || nz < 2) return fail(SP_EINVAL, "grid needs at least 2 nodes per axis");
+    if (march_axis < 0 || march_axis > 2) return fail(SP_EINVAL, "march_axis must be 0, 1 or 2");
+    f->n[0] = nx; f->n[1] = ny; f->n[2] = nz;
+    f->perm[0] = (march_axis + 1) % 3; f->perm[1] = (march_axis + 2) % 3; f->perm[2] = march_axis;
+    CU(cudaGetDevice(&f->device));
+    for (int k = 0; k < 3; ++k) {
+        const int ca = f->perm[k], n = f->n[ca];
+        AxisTables T;
+        if (!build_axis_tables(axh[ca], n, T)) return fail(SP_EINVAL, "axes must be strictly ascending");
+        f->nk[k] = n;
+        std::vector<d2>& t64 = T.t64; std::vector<f2>& t32 = T.t32;
+        f->g0[k] = T.g0; f->lo[k] = T.lo; f->hi[k] = T.hi; f->inv_d[k] = T.inv_d;
+        CU(cudaMalloc(&f->tab64[k], n * sizeof(d2)));
+        CU(cudaMalloc(&f->tab32[k], n * sizeof(f2)));
+        CU(cudaMemcpyAsync(f->tab64[k], t64.data(), n * sizeof(d2), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(f->tab32[k], t32.data(), n * sizeof(f2), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));   // host vectors go out of scope
+        f->bytes += n * (sizeof(d2) + sizeof(f2));
+    }
+    const size_t cells = (size_t)nx * ny * nz;
+    CU(cudaMalloc(&f->data, cells * sizeof(f4)));
+    f->bytes += cells * sizeof(f4);
+    return SP_OK;
+}
+
+static PackArgs pack_args(const sp_field* f) {
+    PackArgs P; memset(&P, 0, sizeof(P));
+    for (int k = 0; k < 3; ++k) { P.n[k] = f->n[k]; P.perm[k] = f->perm[k]; P.nk[k] = f->nk[k]; }
+    return P;
+}
+
+static int pack_grid(long long total) {
+    long long b = (total + 255) / 256;
+    return (int)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b));
+}
+
+extern "C" int sp_field_destroy(sp_field* f) {
+    if (!f) return SP_OK;
+    cudaFree(f->data); cudaFree(f->aux64);
+    for (int k = 0; k < 3; ++k) { cudaFree(f->tab64[k]); cudaFree(f->tab32[k]); }
+    delete f;
+    return SP_OK;
+}
+
+extern "C" uint64_t sp_field_bytes(const sp_field* f) { return f ? f->bytes : 0; }
+
+extern "C" int sp_field_create(sp_field** out, const void* ne_dev, int ne_is_f64, const float* ax_x_host,
+                               const float* ax_y_host, const float* ax_z_host, int nx, int ny, int nz,
+                               double omega, int march_axis, int flags, void* stream) {
+    if (!out || !ne_dev || !ax_x_host || !ax_y_host || !ax_z_host) return fail(SP_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    sp_field* f = new sp_field();
+    const float* axh[3] = {ax_x_host, ax_y_host, ax_z_host};
+    int rc = field_common(f, axh, nx, ny, nz, march_axis, st);
+    if (rc) { sp_field_destroy(f); return rc; }
+    const long long cells = (long long)nx * ny * nz;
+    float* ne_nc = nullptr;
+    float* coef = nullptr;
+    auto cleanup = [&]() { cudaFree(ne_nc); cudaFree(coef); };
+    PackArgs P = pack_args(f);
+    // coefficient tables
+    size_t ncoef = 3 * (size_t)(nx + ny + nz);
+    std::vector<float> hc(ncoef);
+    size_t off = 0;
+    AxisCoef C[3];
+    size_t offs[3];
+    for (int a = 0; a < 3; ++a) {
+        C[a] = axis_coef(axh[a], f->n[a]);
+        offs[a] = off;
+        for (int i = 0; i < f->n[a]; ++i) { hc[off + i] = C[a].a[i]; hc[off + f->n[a] + i] = C[a].b[i]; hc[off + 2 * f->n[a] + i] = C[a].c[i]; }
+        off += 3 * (size_t)f->n[a];
+    }
+#define CUF(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { cleanup(); sp_field_destroy(f); return fail(SP_ECUDA, std::string(#x) + ": " + cudaGetErrorString(e_)); } } while (0)
+    CUF(cudaMalloc(&ne_nc, cells * sizeof(float)));
+    CUF(cudaMalloc(&coef, ncoef * sizeof(float)));
+    CUF(cudaMemcpyAsync(coef, hc.data(), ncoef * sizeof(float), cudaMemcpyHostToDevice, st));
+    for (int a = 0; a < 3; ++a) {
+        P.st[a].a = coef + offs[a]; P.st[a].b = coef + offs[a] + f->n[a]; P.st[a].c = coef + offs[a] + 2 * f->n[a];
+        P.st[a].two_dx = C[a].two_dx; P.st[a].dx0 = C[a].dx0; P.st[a].dxn = C[a].dxn;
+        P.st[a].uniform = C[a].uniform; P.st[a].n = f->n[a];
+    }
+    const double c = 299792458.0;
+    P.k32 = (float)(-0.5 * c * c);
+    P.omega = omega; P.flags = flags;
+    const double nc = 3.14207787e-4 * omega * omega;
+    if (flags & SP_FIELD_PHASE_F64) {
+        CUF(cudaMalloc(&f->aux64, cells * sizeof(double)));
+        f->bytes += cells * sizeof(double);
+    }
+    const int grid = pack_grid(cells);
+    if (ne_is_f64) {
+        k_normalise_ne<double><<<grid, 256, 0, st>>>((const double*)ne_dev, ne_nc, cells, nc);
+        g_launches++; CUF(cudaGetLastError());
+        k_pack_from_ne<double><<<grid, 256, 0, st>>>(ne_nc, (const double*)ne_dev, f->data, f->aux64, P);
+    } else {
+        k_normalise_ne<float><<<grid, 256, 0, st>>>((const float*)ne_dev, ne_nc, cells, nc);
+        g_launches++; CUF(cudaGetLastError());
+        k_pack_from_ne<float><<<grid, 256, 0, st>>>(ne_nc, (const float*)ne_dev, f->data, f->aux64, P);
+    }
+    g_launches++; CUF(cudaGetLastError());
+    CUF(cudaStreamSynchronize(st));   // temporaries are freed below; creation is a one-off
+#undef CUF
+    cleanup();
+    *out = f;
+    return SP_OK;
+}
+
+extern "C" int sp_field_create_from_gradients(sp_field** out, const float* gx_dev, const float* gy_dev,
+                                              const float* gz_dev, const float* aux_f32_dev,
+                                              const double* aux_f64_dev, const float* ax_x_host,
+                                              const float* ax_y_host, const float* ax_z_host, int nx, int ny,
+                                              int nz, int march_axis, void* stream) {
+    if (!out || !gx_dev || !gy_dev || !gz_dev || !ax_x_host || !ax_y_host || !ax_z_host)
+        return fail(SP_EINVAL, "null argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    sp_field* f = new sp_field();
+    const float* axh[3] = {ax_x_host, ax_y_host, ax_z_host};
+    int rc = field_common(f, axh, nx, ny, nz, march_axis, st);
+    if (rc) { sp_field_destroy(f); return rc; }
+    const long long cells = (long long)nx * ny * nz;
+    if (aux_f64_dev) {
+        if (cudaMalloc(&f->aux64, cells * sizeof(double)) != cudaSuccess) { sp_field_destroy(f); return fail(SP_ENOMEM, "aux64"); }
+        f->bytes += cells * sizeof(double);
+    }
+    PackArgs P = pack_args(f);
+    k_pack_from_grads<<<pack_grid(cells), 256, 0, st>>>(gx_dev, gy_dev, gz_dev, aux_f32_dev, aux_f64_dev, f->data,
+                                                        f->aux64, P);
+    g_launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) { sp_field_destroy(f); return fail(SP_ECUDA, cudaGetErrorString(e)); }
+    *out = f;
+    return SP_OK;
+}
+
+extern "C" int sp_field_export_gradients(const sp_field* f, float* gx_dev, float* gy_dev, float* gz_dev,
+                                         float* aux_dev, void* stream) {
+    if (!f) return fail(SP_EINVAL, "null field");
+    PackArgs P = pack_args(f);
+    const long long cells = (long long)f->n[0] * f->n[1] * f->n[2];
+    k_export_grads<<<pack_grid(cells), 256, 0, (cudaStream_t)stream>>>(f->data, gx_dev, gy_dev, gz_dev, aux_dev, P);
+    LAUNCH_CHECK();
+    return SP_OK;
+}
+
+// -------------------------------------------------------------------------------------- detector channels
+#define SP_MAX_OPS 16
+#define SP_MAX_CHANNELS 4
+
+struct ChannelDev {
+    OpticOp ops[SP_MAX_OPS];
+    int n_ops, kind, nx, ny, with_E, input_mm;
+    double kwave, x_lo, x_hi, y_lo, y_hi;
+    unsigned long long* counts;
+    double* planes;
+};
+
+static int channel_to_dev(const sp_channel* c, ChannelDev& d) {
+    if (c->n_ops < 0 || c->n_ops > SP_MAX_OPS) return fail(SP_EINVAL, "too many optic ops (max 16)");
+    memset(&d, 0, sizeof(d));
+    for (int i = 0; i < c->n_ops; ++i) {
+        d.ops[i].kind = c->ops_host[i].kind;
+        d.ops[i].p0 = c->ops_host[i].p0; d.ops[i].p1 = c->ops_host[i].p1; d.ops[i].p2 = c->ops_host[i].p2;
+        if (d.ops[i].kind < 0 || d.ops[i].kind > SP_OP_REF_BEAM) return fail(SP_EINVAL, "unknown optic op");
+    }
+    d.n_ops = c->n_ops; d.input_mm = c->input_mm;
+    d.kind = c->image.kind; d.nx = c->image.nx; d.ny = c->image.ny;
+    d.x_lo = c->image.x_lo; d.x_hi = c->image.x_hi; d.y_lo = c->image.y_lo; d.y_hi = c->image.y_hi;
+    d.counts = (unsigned long long*)c->image.counts_dev; d.planes = c->image.planes_dev;
+    d.with_E = (c->image.kind == SP_IMG_INTERFEROGRAM);
+    d.kwave = c->wavelength > 0 ? 2.0 * 3.14159265358979323846 / c->wavelength : 0.0;
+    if (d.kind == SP_IMG_HISTOGRAM && !d.counts && d.nx > 0) return fail(SP_EINVAL, "histogram channel without counts buffer");
+    if (d.kind == SP_IMG_INTERFEROGRAM && !d.planes && d.nx > 0) return fail(SP_EINVAL, "interferogram channel without planes buffer");
+    return SP_OK;
+}
+
+// Detector binning of one ray.  Histogram counts are warp-aggregated: lanes that hit the same pixel elect
+// one leader which issues a single 64-bit atomic with the lane count (rays are bundled coherently, so
+// neighbouring lanes land in neighbouring pixels).  Returns 1 if binned.
+__device__ __forceinline__ int bin_ray(const ChannelDev& ch, const DetRay& d, bool active) {
+    int pix = -1;
+    if (active && d.alive && ch.nx > 0) {
+        const bool hist = (ch.kind == SP_IMG_HISTOGRAM);
+        const int ix = bin_index(d.x, ch.x_lo, ch.x_hi, ch.nx, hist);
+        const int iy = bin_index(d.y, ch.y_lo, ch.y_hi, ch.ny, hist);
+        if (ix >= 0 && iy >= 0) pix = iy * ch.nx + ix;
+    }
+    if (ch.kind == SP_IMG_HISTOGRAM) {
+        const unsigned peers = __match_any_sync(__activemask(), pix);
+        if (pix >= 0 && (__ffs(peers) - 1) == (int)(threadIdx.x & 31))
+            atomicAdd(ch.counts + pix, (unsigned long long)__popc(peers));
+    } else if (pix >= 0) {
+        const size_t plane = (size_t)ch.nx * ch.ny;
+        atomicAdd(ch.planes + pix, d.ex_re);
+        atomicAdd(ch.planes + plane + pix, d.ex_im);
+        atomicAdd(ch.planes + 2 * plane + pix, d.ey_re);
+        atomicAdd(ch.planes + 3 * plane + pix, d.ey_im);
+    }
+    return pix >= 0;
+}
+
+struct Epilogue {
+    double* sf; double* rf; double* jf; uint32_t* steps;
+    int n_channels;
+    ChannelDev ch[SP_MAX_CHANNELS];
+};
+
+// --------------------------------------------------------------------------------------------- ray sorting
+struct SortArgs {
+    const double* s0; uint64_t n_total;        // caller arrays hold n_total rays (row stride)
+    uint64_t chunk_off; uint32_t chunk_n;      // this chunk = rays [chunk_off, chunk_off + chunk_n)
+    BeamSpec beam; int use_beam; uint64_t ray_offset;
+    int perm[3];
+    double g0u, inv_du, g0v, inv_dv; int nu, nv;
+    int key_shift; uint32_t n_keys;
+};
+
+__device__ __forceinline__ uint32_t part1by1(uint32_t x) {
+    x &= 0x0000ffffu; x = (x | (x << 8)) & 0x00ff00ffu; x = (x | (x << 4)) & 0x0f0f0f0fu;
+    x = (x | (x << 2)) & 0x33333333u; x = (x | (x << 1)) & 0x55555555u;
+    return x;
+}
+
+__device__ __forceinline__ void load_ray_caller(const double* s0, uint64_t n_total, uint64_t gi, const BeamSpec& B,
+                                                int use_beam, uint64_t ray_offset, double s[6]) {
+    if (use_beam) beam_ray(B, ray_offset + gi, s);
+    else {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) s[k] = s0[(uint64_t)k * n_total + gi];
+    }
+}
+
+// Key = Morton code of the (u, v) cell column the ray starts in: rays of one warp then walk the same few
+// 128-byte lines of the field for their whole flight.
+__global__ void k_sort_keys(SortArgs A, uint32_t* __restrict__ keys, uint32_t* __restrict__ hist) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.chunk_n) return;
+    double s[6];
+    load_ray_caller(A.s0, A.n_total, A.chunk_off + i, A.beam, A.use_beam, A.ray_offset, s);
+    const double pu = s[A.perm[0]], pv = s[A.perm[1]];
+    int iu = floor_to_int((pu - A.g0u) * A.inv_du), iv = floor_to_int((pv - A.g0v) * A.inv_dv);
+    iu = min(max(iu, 0), A.nu - 1); iv = min(max(iv, 0), A.nv - 1);
+    uint32_t key = (part1by1((uint32_t)iu) | (part1by1((uint32_t)iv) << 1)) >> A.key_shift;
+    key = min(key, A.n_keys - 1);
+    keys[i] = key;
+    atomicAdd(hist + key, 1u);
+}
+
+// Single-block exclusive scan (n_keys <= 4 Mi): each thread owns a contiguous slice.
+__global__ void k_scan(uint32_t* __restrict__ hist, uint32_t n) {
+    __shared__ uint32_t part[1024];
+    const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
+    const uint32_t b = threadIdx.x * per, e = min(b + per, n);
+    uint32_t s = 0;
+    for (uint32_t i = b; i < e; ++i) s += hist[i];
+    part[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t run = 0;
+        for (uint32_t i = 0; i < blockDim.x; ++i) { uint32_t v = part[i]; part[i] = run; run += v; }
+    }
+    __syncthreads();
+    uint32_t run = part[threadIdx.x];
+    for (uint32_t i = b; i < e; ++i) { uint32_t v = hist[i]; hist[i] = run; run += v; }
+}
+
+__global__ void k_sort_scatter(const uint32_t* __restrict__ keys, uint32_t* __restrict__ cursor,
+                               uint32_t* __restrict__ order, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    order[atomicAdd(cursor + keys[i], 1u)] = i;
+}
+
+// ---------------------------------------------------------------------------------------------- propagate
+template <typename T> struct PropArgs {
+    FieldView<T> F;
+    const double* s0; uint64_t n_total;
+    uint64_t chunk_off; uint32_t chunk_n;
+    const uint32_t* order;                    // sorted slot -> ray index within the chunk, or nullptr
+    unsigned long long* cursor;               // bundle dispenser
+    BeamSpec beam; int use_beam; uint64_t ray_offset;
+    int perm[3];                              // kernel axis -> caller axis
+    int kp, ka, kb;                           // kernel-frame indices: probing axis, rf rows (0,1), rf rows (2,3)
+    int method, flags, n_steps, n_state;
+    T h, t_end, rtol, atol, omega, extent;
+    sp_stats* stats;
+};
+
+struct LaneStats { unsigned long long steps, acc, capped, binned, rejected, evals; };
+
+__device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+template <typename T, int METHOD, bool PHASE, bool AUX64>
+__global__ void __launch_bounds__(128) k_propagate(const PropArgs<T> A, const Epilogue E) {
+    const int lane = threadIdx.x & 31;
+    LaneStats ls = {0, 0, 0, 0, 0, 0};
+    const bool early = (A.flags & SP_FLAG_EARLY_EXIT) != 0;
+    for (;;) {
+        unsigned long long slot0 = 0;
+        if (lane == 0) slot0 = atomicAdd(A.cursor, 32ull);
+        slot0 = __shfl_sync(0xffffffffu, slot0, 0);
+        if (slot0 >= A.chunk_n) break;
+        const unsigned long long slot = slot0 + lane;
+        const bool valid = slot < A.chunk_n;
+        const uint64_t li = valid ? (A.order ? (uint64_t)A.order[slot] : slot) : 0;
+        const uint64_t gi = A.chunk_off + li;         // index into the caller's arrays
+        double s[6];
+        double amp = 1.0, ph0 = 0.0, pol = 0.0;
+        if (valid) {
+            load_ray_caller(A.s0, A.n_total, gi, A.beam, A.use_beam, A.ray_offset, s);
+            if (!A.use_beam) { amp = A.s0[6 * A.n_total + gi]; ph0 = A.s0[7 * A.n_total + gi]; pol = A.s0[8 * A.n_total + gi]; }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) s[k] = 0.0;
+        }
+        Ray<T> r;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { r.p[k] = (T)s[A.perm[k]]; r.v[k] = (T)s[3 + A.perm[k]]; }
+        r.ph = (T)ph0;
+        unsigned n_att = 0;
+        if (valid) {
+            if (METHOD == SP_METHOD_RK4) {
+                const T h = A.h;
+                for (int it = 0; it < A.n_steps; ++it) {
+                    if (early && escaped(A.F, r)) break;
+                    ls.evals += rk4_step<T, PHASE, AUX64>(A.F, h, A.omega, r);
+                    ++n_att;
+                }
+                ls.acc += n_att;
+            } else {
+                // SciPy RK45 driven as solve_ivp does (rk.py:_step_impl), one controller per ray
+                Deriv<T> f; int touched = 0;
+                touched += deriv<T, PHASE, AUX64>(A.F, A.omega, r.p, r.v, f);
+                T h_abs = dp5_initial_step<T, PHASE, AUX64>(A.F, A.omega, A.t_end, A.rtol, A.atol, A.n_state, (T)amp,
+                                                            (T)pol, r, f, touched);
+                T t = (T)0;
+                const unsigned cap = A.n_steps > 0 ? (unsigned)A.n_steps : (1u << 30);
+                const T inv_n = (T)1 / (T)A.n_state;
+                bool failed = false;
+                while (t < A.t_end && !failed) {
+                    if (early && escaped(A.F, r)) break;
+                    const T min_step = (T)10 * (nextafter(t, (T)INFINITY) - t);
+                    if (h_abs < min_step) h_abs = min_step;
+                    bool rejected = false;
+                    for (;;) {
+                        if (n_att >= cap) { failed = true; ls.capped += 1; break; }
+                        if (h_abs < min_step) { failed = true; ls.capped += 1; break; }
+                        T t_new = t + h_abs;
+                        if (t_new - A.t_end > (T)0) t_new = A.t_end;
+                        const T h = t_new - t;
+                        h_abs = fabs(h);
+                        Ray<T> rn; Deriv<T> fn; T esq;
+                        touched += dp5_attempt<T, PHASE, AUX64>(A.F, A.omega, h, A.rtol, A.atol, r, f, rn, fn, esq);
+                        ++n_att;
+                        const T en = sqrt(esq * inv_n);
+                        if (en < (T)1) {
+                            h_abs *= dp5_factor<T>(en, true, rejected);
+                            t = t_new; r = rn; f = fn; ls.acc += 1;
+                            break;
+                        }
+                        h_abs *= dp5_factor<T>(en, false, rejected);
+                        rejected = true;
+                    }
+                }
+                ls.evals += touched;
+            }
+            ls.steps += n_att;
+        }
+        // ---- epilogue: exit plane, outputs, fused optics + binning ----
+        T xa = 0, tha = 0, xb = 0, thb = 0;
+        if (valid) exit_project<T>(r, A.kp, A.ka, A.kb, A.extent, xa, tha, xb, thb);
+        const uint64_t N = A.n_total;
+        if (valid) {
+            if (E.sf) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    E.sf[(uint64_t)A.perm[k] * N + gi] = (double)r.p[k];
+                    E.sf[(uint64_t)(3 + A.perm[k]) * N + gi] = (double)r.v[k];
+                }
+                E.sf[6 * N + gi] = amp; E.sf[7 * N + gi] = (double)r.ph; E.sf[8 * N + gi] = pol;
+            }
+            if (E.rf) {
+                E.rf[gi] = (double)xa; E.rf[N + gi] = (double)tha; E.rf[2 * N + gi] = (double)xb; E.rf[3 * N + gi] = (double)thb;
+            }
+            if (E.steps) E.steps[gi] = n_att;
+        }
+        if (E.jf || E.n_channels > 0) {
+            // Jones vector (full_solver.py:883-890): amp e^{i phase} R(pol) (0, 1)^T
+            double sp_, cp_, ss, cs;
+            sp_sincos((double)r.ph, &sp_, &cp_);
+            sp_sincos(pol, &ss, &cs);
+            const double rr = amp * cp_, ri = amp * sp_;
+            const double ex_re = rr * (-ss), ex_im = ri * (-ss), ey_re = rr * cs, ey_im = ri * cs;
+            if (valid && E.jf) {
+                E.jf[2 * gi] = ex_re; E.jf[2 * gi + 1] = ex_im;
+                E.jf[2 * (N + gi)] = ey_re; E.jf[2 * (N + gi) + 1] = ey_im;
+            }
+            for (int c = 0; c < E.n_channels; ++c) {
+                const ChannelDev& ch = E.ch[c];
+                DetRay d;
+                d.x = (double)xa * 1e3; d.th = (double)tha; d.y = (double)xb * 1e3; d.ph = (double)thb;   // m_to_mm
+                d.ex_re = ex_re; d.ex_im = ex_im; d.ey_re = ey_re; d.ey_im = ey_im; d.alive = valid;
+                if (valid) run_optics(d, (double)xa, (double)xb, ch.ops, ch.n_ops, ch.with_E != 0, ch.kwave);
+                const int b = bin_ray(ch, d, valid);
+                ls.binned += b;
+                ls.rejected += (valid && !d.alive) ? 1 : 0;
+            }
+        }
+    }
+    if (A.stats) {
+        const unsigned long long a = warp_sum(ls.steps), b = warp_sum(ls.acc), c = warp_sum(ls.capped),
+                                 d = warp_sum(ls.binned), e = warp_sum(ls.rejected), f = warp_sum(ls.evals);
+        if (lane == 0) {
+            if (a) atomicAdd((unsigned long long*)&A.stats->ray_steps, a);
+            if (b) atomicAdd((unsigned long long*)&A.stats->ray_steps_acc, b);
+            if (c) atomicAdd((unsigned long long*)&A.stats->rays_capped, c);
+            if (d) atomicAdd((unsigned long long*)&A.stats->rays_binned, d);
+            if (e) atomicAdd((unsigned long long*)&A.stats->rays_rejected, e);
+            if (f) atomicAdd((unsigned long long*)&A.stats->rhs_evals, f);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------- joint RK45
+// The reference as shipped integrates ALL rays as one 9N-dimensional system: one step size, accepted or
+// rejected from the RMS error norm over every component of every ray (full_solver.py:391 -> scipy RK45).
+// State lives in HBM between attempts; the controller runs on the host exactly like SciPy's Python loop.
+struct JointBuf {               // SoA over rays, kernel frame
+    double *p[3], *v[3], *ph;   // current state
+    double *fv[3], *fph;        // f = derivative at current state (dv and dphase; dp = v)
+    double *pn[3], *vn[3], *phn, *fvn[3], *fphn;   // candidate
+    double* amp; double* pol;
+    double* partial;            // per-block partial sums
+};
+
+template <bool PHASE, bool AUX64>
+__global__ void k_joint_init(FieldView<double> F, JointBuf B, const double* s0, uint64_t n, int p0, int p1, int p2,
+                             double omega, double rtol, double atol, int pass, double h0) {
+    // pass 0: load state, f0 = f(y0); partial sums of (y0/scale)^2 and (f0/scale)^2
+    // pass 1: f1 = f(y0 + h0 f0); partial sums of ((f1 - f0)/scale)^2
+    __shared__ double sh0[128], sh1[128];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double s_a = 0.0, s_b = 0.0;
+    if (i < n) {
+        const int perm[3] = {p0, p1, p2};
+        Ray<double> r; Deriv<double> f;
+        if (pass == 0) {
+            for (int k = 0; k < 3; ++k) { r.p[k] = s0[(uint64_t)perm[k] * n + i]; r.v[k] = s0[(uint64_t)(3 + perm[k]) * n + i]; }
+            r.ph = s0[7 * n + i];
+            B.amp[i] = s0[6 * n + i]; B.pol[i] = s0[8 * n + i];
+            deriv<double, PHASE, AUX64>(F, omega, r.p, r.v, f);
+            for (int k = 0; k < 3; ++k) { B.p[k][i] = r.p[k]; B.v[k][i] = r.v[k]; B.fv[k][i] = f.dv[k]; }
+            B.ph[i] = r.ph; B.fph[i] = f.dph;
+            for (int k = 0; k < 3; ++k) {
+                const double sp_ = atol + fabs(r.p[k]) * rtol, sv_ = atol + fabs(r.v[k]) * rtol;
+                double q = r.p[k] / sp_; s_a += q * q; q = r.v[k] / sv_; s_a += q * q;
+                q = f.dp[k] / sp_; s_b += q * q; q = f.dv[k] / sv_; s_b += q * q;
+            }
+            const double sph = atol + fabs(r.ph) * rtol;
+            double q = r.ph / sph; s_a += q * q; q = f.dph / sph; s_b += q * q;
+            q = B.amp[i] / (atol + fabs(B.amp[i]) * rtol); s_a += q * q;
+            q = B.pol[i] / (atol + fabs(B.pol[i]) * rtol); s_a += q * q;
+        } else {
+            double p1_[3], v1_[3];
+            for (int k = 0; k < 3; ++k) {
+                r.p[k] = B.p[k][i]; r.v[k] = B.v[k][i];
+                p1_[k] = r.p[k] + h0 * r.v[k]; v1_[k] = r.v[k] + h0 * B.fv[k][i];
+            }
+            deriv<double, PHASE, AUX64>(F, omega, p1_, v1_, f);
+            for (int k = 0; k < 3; ++k) {
+                const double sp_ = atol + fabs(r.p[k]) * rtol, sv_ = atol + fabs(r.v[k]) * rtol;
+                double q = (f.dp[k] - r.v[k]) / sp_; s_a += q * q;
+                q = (f.dv[k] - B.fv[k][i]) / sv_; s_a += q * q;
+            }
+            const double sph = atol + fabs(B.ph[i]) * rtol;
+            const double q = (f.dph - B.fph[i]) / sph; s_a += q * q;
+        }
+    }
+    sh0[threadIdx.x] = s_a; sh1[threadIdx.x] = s_b;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { sh0[threadIdx.x] += sh0[threadIdx.x + o]; sh1[threadIdx.x] += sh1[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { B.partial[2 * blockIdx.x] = sh0[0]; B.partial[2 * blockIdx.x + 1] = sh1[0]; }
+}
+
+template <bool PHASE, bool AUX64>
+__global__ void k_joint_attempt(FieldView<double> F, JointBuf B, uint64_t n, double omega, double h, double rtol,
+                                double atol) {
+    __shared__ double sh0[128];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double esq = 0.0;
+    if (i < n) {
+        Ray<double> r, rn; Deriv<double> f, fn;
+        for (int k = 0; k < 3; ++k) { r.p[k] = B.p[k][i]; r.v[k] = B.v[k][i]; f.dp[k] = r.v[k]; f.dv[k] = B.fv[k][i]; }
+        r.ph = B.ph[i]; f.dph = B.fph[i];
+        dp5_attempt<double, PHASE, AUX64>(F, omega, h, rtol, atol, r, f, rn, fn, esq);
+        for (int k = 0; k < 3; ++k) { B.pn[k][i] = rn.p[k]; B.vn[k][i] = rn.v[k]; B.fvn[k][i] = fn.dv[k]; }
+        B.phn[i] = rn.ph; B.fphn[i] = fn.dph;
+    }
+    sh0[threadIdx.x] = esq;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh0[threadIdx.x] += sh0[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) B.partial[2 * blockIdx.x] = sh0[0];
+}
+
+// Deterministic (fixed-order) final reduction of the per-block partials -> out[0], out[1] (mapped host memory).
+__global__ void k_joint_reduce(const double* __restrict__ partial, int nblocks, double* __restrict__ out) {
+    __shared__ double sh0[256], sh1[256];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += blockDim.x) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+    sh0[threadIdx.x] = a; sh1[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { sh0[threadIdx.x] += sh0[threadIdx.x + o]; sh1[threadIdx.x] += sh1[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { out[0] = sh0[0]; out[1] = sh1[0]; }
+}
+
+// Exit projection + outputs + optics/binning for rays whose state sits in a JointBuf (used after the joint solve).
+__global__ void k_joint_finish(JointBuf B, uint64_t n, int use_new, int p0, int p1, int p2, int kp, int ka, int kb,
+                               double extent, const Epilogue E, sp_stats* stats) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool valid = i < n;
+    const int perm[3] = {p0, p1, p2};
+    Ray<double> r; double amp = 1.0, pol = 0.0;
+    for (int k = 0; k < 3; ++k) { r.p[k] = 0; r.v[k] = 1; }
+    r.ph = 0;
+    if (valid) {
+        for (int k = 0; k < 3; ++k) { r.p[k] = (use_new ? B.pn : B.p)[k][i]; r.v[k] = (use_new ? B.vn : B.v)[k][i]; }
+        r.ph = (use_new ? B.phn : B.ph)[i]; amp = B.amp[i]; pol = B.pol[i];
+    }
+    double xa = 0, tha = 0, xb = 0, thb = 0;
+    if (valid) exit_project<double>(r, kp, ka, kb, extent, xa, tha, xb, thb);
+    if (valid) {
+        if (E.sf) {
+            for (int k = 0; k < 3; ++k) { E.sf[(uint64_t)perm[k] * n + i] = r.p[k]; E.sf[(uint64_t)(3 + perm[k]) * n + i] = r.v[k]; }
+            E.sf[6 * n + i] = amp; E.sf[7 * n + i] = r.ph; E.sf[8 * n + i] = pol;
+        }
+        if (E.rf) { E.rf[i] = xa; E.rf[n + i] = tha; E.rf[2 * n + i] = xb; E.rf[3 * n + i] = thb; }
+    }
+    unsigned long long binned = 0, rejected = 0;
+    if (E.jf || E.n_channels > 0) {
+        double sp_, cp_, ss, cs;
+        sp_sincos(r.ph, &sp_, &cp_); sp_sincos(pol, &ss, &cs);
+        const double rr = amp * cp_, ri = amp * sp_;
+        const double ex_re = rr * (-ss), ex_im = ri * (-ss), ey_re = rr * cs, ey_im = ri * cs;
+        if (valid && E.jf) {
+            E.jf[2 * i] = ex_re; E.jf[2 * i + 1] = ex_im; E.jf[2 * (n + i)] = ey_re; E.jf[2 * (n + i) + 1] = ey_im;
+        }
+        for (int c = 0; c < E.n_channels; ++c) {
+            const ChannelDev& ch = E.ch[c];
+            DetRay d;
+            d.x = xa * 1e3; d.th = tha; d.y = xb * 1e3; d.ph = thb;
+            d.ex_re = ex_re; d.ex_im = ex_im; d.ey_re = ey_re; d.ey_im = ey_im; d.alive = valid;
+            if (valid) run_optics(d, xa, xb, ch.ops, ch.n_ops, ch.with_E != 0, ch.kwave);
+            binned += bin_ray(ch, d, valid);
+            rejected += (valid && !d.alive) ? 1 : 0;
+        }
+    }
+    if (stats) {
+        binned = warp_sum(binned); rejected = warp_sum(rejected);
+        if ((threadIdx.x & 31) == 0) {
+            if (binned) atomicAdd((unsigned long long*)&stats->rays_binned, binned);
+            if (rejected) atomicAdd((unsigned long long*)&stats->rays_rejected, rejected);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------ stand-alone kernels
+__global__ void k_optics_image(const double* __restrict__ rf, const double* __restrict__ jf, uint64_t n,
+                               const ChannelDev ch, double* __restrict__ rf_out, double* __restrict__ jf_out) {
+    const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    const uint64_t n_round = (n + 31) / 32 * 32;      // keep warps converged for __match_any_sync
+    for (uint64_t i = i0; i < n_round; i += stride) {
+        const bool valid = i < n;
+        DetRay d;
+        d.alive = valid; d.x = d.th = d.y = d.ph = 0.0;
+        d.ex_re = d.ex_im = d.ey_re = d.ey_im = 0.0;
+        double xm = 0.0, ym = 0.0;
+        if (valid) {
+            xm = rf[i]; ym = rf[2 * n + i];
+            const double unit = ch.input_mm ? 1.0 : 1e3;      // m_to_mm (diagnostics.py:122-127)
+            d.x = xm * unit; d.th = rf[n + i]; d.y = ym * unit; d.ph = rf[3 * n + i];
+            if (jf) { d.ex_re = jf[2 * i]; d.ex_im = jf[2 * i + 1]; d.ey_re = jf[2 * (n + i)]; d.ey_im = jf[2 * (n + i) + 1]; }
+            run_optics(d, xm, ym, ch.ops, ch.n_ops, jf != nullptr, ch.kwave);
+        }
+        if (valid && rf_out) {
+            const double nanv = __longlong_as_double(0x7ff8000000000000ULL);
+            rf_out[i] = d.alive ? d.x : nanv; rf_out[n + i] = d.alive ? d.th : nanv;
+            rf_out[2 * n + i] = d.alive ? d.y : nanv; rf_out[3 * n + i] = d.alive ? d.ph : nanv;
+            if (jf_out) {
+                jf_out[2 * i] = d.alive ? d.ex_re : nanv; jf_out[2 * i + 1] = d.alive ? d.ex_im : nanv;
+                jf_out[2 * (n + i)] = d.alive ? d.ey_re : nanv; jf_out[2 * (n + i) + 1] = d.alive ? d.ey_im : nanv;
+            }
+        }
+        if (ch.nx > 0) bin_ray(ch, d, valid);
+    }
+}
+
+__global__ void k_finalize(const double* __restrict__ planes, double* __restrict__ H, size_t npix) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= npix) return;
+    const double a = planes[i], b = planes[2 * npix + i];     // Re(sum Ex), Re(sum Ey)
+    H[i] = sqrt(a * a + b * b);
+}
+
+template <bool PHASE, bool AUX64>
+__global__ void k_rhs(FieldView<double> F, const double* __restrict__ s, uint64_t n, double* __restrict__ out,
+                      int p0, int p1, int p2, double omega) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int perm[3] = {p0, p1, p2};
+    double p[3], v[3];
+    for (int k = 0; k < 3; ++k) { p[k] = s[(uint64_t)perm[k] * n + i]; v[k] = s[(uint64_t)(3 + perm[k]) * n + i]; }
+    Deriv<double> f;
+    deriv<double, PHASE, AUX64>(F, omega, p, v, f);
+    for (int k = 0; k < 3; ++k) { out[(uint64_t)perm[k] * n + i] = f.dp[k]; out[(uint64_t)(3 + perm[k]) * n + i] = f.dv[k]; }
+    out[6 * n + i] = 0.0; out[7 * n + i] = f.dph; out[8 * n + i] = 0.0;
+}
+
+__global__ void k_beam(BeamSpec B, uint64_t off, uint64_t n, double* __restrict__ s0) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double s[6];
+    beam_ray(B, off + i, s);
+    for (int k = 0; k < 6; ++k) s0[(uint64_t)k * n + i] = s[k];
+    s0[6 * n + i] = 1.0; s0[7 * n + i] = 0.0; s0[8 * n + i] = 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------- workspace
+struct sp_workspace {
+    uint32_t *keys = nullptr, *order = nullptr, *hist = nullptr;
+    size_t cap_rays = 0, cap_keys = 0;
+    unsigned long long* cursor = nullptr;
+    double* joint = nullptr; size_t joint_cap = 0;
+    double* host_pair = nullptr;     // pinned, 2 doubles
+    int sm_count = 0;
+};
+
+extern "C" int sp_workspace_create(sp_workspace** out) {
+    if (!out) return fail(SP_EINVAL, "null argument");
+    sp_workspace* w = new sp_workspace();
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&w->sm_count, cudaDevAttrMultiProcessorCount, dev));
+    CU(cudaMalloc(&w->cursor, sizeof(unsigned long long)));
+    CU(cudaMallocHost(&w->host_pair, 2 * sizeof(double)));
+    *out = w;
+    return SP_OK;
+}
+extern "C" int sp_workspace_destroy(sp_workspace* w) {
+    if (!w) return SP_OK;
+    cudaFree(w->keys); cudaFree(w->order); cudaFree(w->hist); cudaFree(w->cursor); cudaFree(w->joint);
+    cudaFreeHost(w->host_pair);
+    delete w;
+    return SP_OK;
+}
+
+static int ws_reserve_sort(sp_workspace* w, size_t rays, size_t keys) {
+    if (rays > w->cap_rays) {
+        cudaFree(w->keys); cudaFree(w->order); w->keys = w->order = nullptr; w->cap_rays = 0;
+        CU(cudaMalloc(&w->keys, rays * sizeof(uint32_t)));
+        CU(cudaMalloc(&w->order, rays * sizeof(uint32_t)));
+        w->cap_rays = rays;
+    }
+    if (keys > w->cap_keys) {
+        cudaFree(w->hist); w->hist = nullptr; w->cap_keys = 0;
+        CU(cudaMalloc(&w->hist, keys * sizeof(uint32_t)));
+        w->cap_keys = keys;
+    }
+    return SP_OK;
+}
+
+static BeamSpec beam_to_spec(const sp_beam* b) {
+    BeamSpec B; memset(&B, 0, sizeof(B));
+    if (b) {
+        B.beam_type = b->beam_type; B.probing_axis = b->probing_axis; B.size_a = b->size_a; B.size_b = b->size_b;
+        B.divergence = b->divergence; B.start = b->start; B.seed = b->seed;
+    }
+    return B;
+}
+
+static int kernel_index_of(const sp_field* f, int caller_axis) {
+    for (int k = 0; k < 3; ++k) if (f->perm[k] == caller_axis) return k;
+    return 0;
+}
+
+template <typename T, int METHOD>
+static int launch_propagate(const PropArgs<T>& A, const Epilogue& E, int grid, cudaStream_t st) {
+    const bool phase = (A.flags & SP_FLAG_PHASE) != 0, aux64 = phase && (A.flags & SP_FLAG_PHASE_F64) != 0;
+    if (!phase) k_propagate<T, METHOD, false, false><<<grid, 128, 0, st>>>(A, E);
+    else if (!aux64) k_propagate<T, METHOD, true, false><<<grid, 128, 0, st>>>(A, E);
+    else k_propagate<T, METHOD, true, true><<<grid, 128, 0, st>>>(A, E);
+    LAUNCH_CHECK();
+    return SP_OK;
+}
+
+template <typename T, int METHOD> static int occupancy_grid(int sm_count, int flags, int& grid) {
+    int per_sm = 0;
+    const bool phase = (flags & SP_FLAG_PHASE) != 0, aux64 = phase && (flags & SP_FLAG_PHASE_F64) != 0;
+    if (!phase) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<T, METHOD, false, false>, 128, 0));
+    else if (!aux64) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<T, METHOD, true, false>, 128, 0));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<T, METHOD, true, true>, 128, 0));
+    if (per_sm < 1) per_sm = 1;
+    grid = sm_count * per_sm;
+    return SP_OK;
+}
+
+static int joint_solve(const sp_field* field, const sp_params* P, sp_workspace* ws, const double* s0_dev, uint64_t n,
+                       const Epilogue& E, sp_stats* stats_dev, cudaStream_t st);
+
+extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_workspace* ws, const double* s0_dev,
+                            const sp_beam* beam, uint64_t n, uint64_t ray_offset, double* sf_dev, double* rf_dev,
+                            double* jf_dev, uint32_t* steps_dev, const sp_channel* channels_host, int n_channels,
+                            sp_stats* stats_dev, void* stream) {
+    if (!field || !P || !ws) return fail(SP_EINVAL, "null field / params / workspace");
+    if (!s0_dev && !beam) return fail(SP_EINVAL, "need either s0_dev or a beam spec");
+    if (n_channels < 0 || n_channels > SP_MAX_CHANNELS) return fail(SP_EINVAL, "at most 4 detector channels");
+    if (P->probing_axis < 0 || P->probing_axis > 2 || P->out_axis_a < 0 || P->out_axis_a > 2 || P->out_axis_b < 0 ||
+        P->out_axis_b > 2)
+        return fail(SP_EINVAL, "axis index out of range");
+    if (P->method == SP_METHOD_RK4 && (P->n_steps < 0 || !(P->h > 0))) return fail(SP_EINVAL, "RK4 needs n_steps >= 0 and h > 0");
+    if ((P->flags & SP_FLAG_PHASE_F64) && !field->aux64) return fail(SP_ESTATE, "field was built without SP_FIELD_PHASE_F64");
+    if (n == 0) return SP_OK;
+    cudaStream_t st = (cudaStream_t)stream;
+    Epilogue E; memset(&E, 0, sizeof(E));
+    E.sf = sf_dev; E.rf = rf_dev; E.jf = jf_dev; E.steps = steps_dev; E.n_channels = n_channels;
+    for (int c = 0; c < n_channels; ++c) {
+        int rc = channel_to_dev(channels_host + c, E.ch[c]);
+        if (rc) return rc;
+    }
+    if (P->method == SP_METHOD_RK45_JOINT) {
+        if (!s0_dev) return fail(SP_EINVAL, "joint RK45 needs explicit s0");
+        if (P->flags & SP_FLAG_FP32) return fail(SP_EINVAL, "joint RK45 is float64 only");
+        return joint_solve(field, P, ws, s0_dev, n, E, stats_dev, st);
+    }
+    if (P->method != SP_METHOD_RK4 && P->method != SP_METHOD_RK45) return fail(SP_EINVAL, "unknown method");
+
+    const bool fp32 = (P->flags & SP_FLAG_FP32) != 0;
+    const bool sort = !(P->flags & SP_FLAG_NO_SORT);
+    const uint64_t CHUNK = 1ull << 25;
+    // sort key geometry: Morton code over (u, v) cell columns, coarsened to at most 2^22 keys
+    int bits = 1;
+    while ((1 << bits) < (field->nk[0] > field->nk[1] ? field->nk[0] : field->nk[1])) ++bits;
+    int key_shift = 2 * bits > 22 ? 2 * bits - 22 : 0;
+    const uint32_t n_keys = 1u << (2 * bits - key_shift);
+
+    int grid = 0, rc = 0;
+    if (fp32) rc = (P->method == SP_METHOD_RK4) ? occupancy_grid<float, SP_METHOD_RK4>(ws->sm_count, P->flags, grid)
+                                                : occupancy_grid<float, SP_METHOD_RK45>(ws->sm_count, P->flags, grid);
+    else rc = (P->method == SP_METHOD_RK4) ? occupancy_grid<double, SP_METHOD_RK4>(ws->sm_count, P->flags, grid)
+                                           : occupancy_grid<double, SP_METHOD_RK45>(ws->sm_count, P->flags, grid);
+    if (rc) return rc;
+
+    for (uint64_t off = 0; off < n; off += CHUNK) {
+        const uint32_t cn = (uint32_t)((n - off) < CHUNK ? (n - off) : CHUNK);
+        const uint32_t* order = nullptr;
+        if (sort && cn > 64) {
+            rc = ws_reserve_sort(ws, cn, n_keys);
+            if (rc) return rc;
+            SortArgs S; memset(&S, 0, sizeof(S));
+            S.s0 = s0_dev; S.n_total = n; S.chunk_off = off; S.chunk_n = cn;
+            S.beam = beam_to_spec(beam); S.use_beam = s0_dev ? 0 : 1; S.ray_offset = ray_offset;
+            for (int k = 0; k < 3; ++k) S.perm[k] = field->perm[k];
+            S.g0u = field->g0[0]; S.inv_du = field->inv_d[0]; S.g0v = field->g0[1]; S.inv_dv = field->inv_d[1];
+            S.nu = field->nk[0]; S.nv = field->nk[1]; S.key_shift = key_shift; S.n_keys = n_keys;
+            CU(cudaMemsetAsync(ws->hist, 0, n_keys * sizeof(uint32_t), st));
+            k_sort_keys<<<(cn + 255) / 256, 256, 0, st>>>(S, ws->keys, ws->hist);
+            LAUNCH_CHECK();
+            k_scan<<<1, 1024, 0, st>>>(ws->hist, n_keys);
+            LAUNCH_CHECK();
+            k_sort_scatter<<<(cn + 255) / 256, 256, 0, st>>>(ws->keys, ws->hist, ws->order, cn);
+            LAUNCH_CHECK();
+            order = ws->order;
+        }
+        CU(cudaMemsetAsync(ws->cursor, 0, sizeof(unsigned long long), st));
+        const uint64_t bundles = (cn + 31) / 32;
+        int g = grid;
+        if ((uint64_t)g * 4 > bundles) g = (int)((bundles + 3) / 4);
+        if (g < 1) g = 1;
+#define FILL(T)                                                                                          \
+        PropArgs<T> A; memset(&A, 0, sizeof(A));                                                         \
+        A.F = make_view<T>(field); A.s0 = s0_dev; A.n_total = n; A.chunk_off = off; A.chunk_n = cn;      \
+        A.order = order; A.cursor = ws->cursor; A.beam = beam_to_spec(beam); A.use_beam = s0_dev ? 0 : 1; \
+        A.ray_offset = ray_offset;                                                                       \
+        for (int k = 0; k < 3; ++k) A.perm[k] = field->perm[k];                                          \
+        A.kp = kernel_index_of(field, P->probing_axis); A.ka = kernel_index_of(field, P->out_axis_a);    \
+        A.kb = kernel_index_of(field, P->out_axis_b);                                                    \
+        A.method = P->method; A.flags = P->flags; A.n_steps = P->n_steps; A.n_state = P->n_state > 0 ? P->n_state : 9; \
+        A.h = (T)P->h; A.t_end = (T)P->t_end; A.rtol = (T)P->rtol; A.atol = (T)P->atol; A.omega = (T)P->omega; \
+        A.extent = (T)P->extent; A.stats = stats_dev;
+        if (fp32) {
+            FILL(float)
+            rc = (P->method == SP_METHOD_RK4) ? launch_propagate<float, SP_METHOD_RK4>(A, E, g, st)
+                                              : launch_propagate<float, SP_METHOD_RK45>(A, E, g, st);
+        } else {
+            FILL(double)
+            rc = (P->method == SP_METHOD_RK4) ? launch_propagate<double, SP_METHOD_RK4>(A, E, g, st)
+                                              : launch_propagate<double, SP_METHOD_RK45>(A, E, g, st);
+        }
+#undef FILL
+        if (rc) return rc;
+    }
+    return SP_OK;
+}
+
+// Host controller of the joint solve: a line-for-line counterpart of scipy's RK45._step_impl loop, with the
+// vector norms evaluated on the device (deterministic two-level reduction).
+static int joint_solve(const sp_field* field, const sp_params* P, sp_workspace* ws, const double* s0_dev, uint64_t n,
+                       const Epilogue& E, sp_stats* stats_dev, cudaStream_t st) {
+    const int threads = 128;
+    const int nblocks = (int)((n + threads - 1) / threads);
+    const size_t per = n;
+    const size_t need = (size_t)(7 + 4 + 7 + 4 + 2) * per + 2 * (size_t)nblocks;
+    if (need > ws->joint_cap) {
+        cudaFree(ws->joint); ws->joint = nullptr; ws->joint_cap = 0;
+        CU(cudaMalloc(&ws->joint, need * sizeof(double)));
+        ws->joint_cap = need;
+    }
+    JointBuf B; double* q = ws->joint;
+    for (int k = 0; k < 3; ++k) { B.p[k] = q; q += per; }
+    for (int k = 0; k < 3; ++k) { B.v[k] = q; q += per; }
+    B.ph = q; q += per;
+    for (int k = 0; k < 3; ++k) { B.fv[k] = q; q += per; }
+    B.fph = q; q += per;
+    for (int k = 0; k < 3; ++k) { B.pn[k] = q; q += per; }
+    for (int k = 0; k < 3; ++k) { B.vn[k] = q; q += per; }
+    B.phn = q; q += per;
+    for (int k = 0; k < 3; ++k) { B.fvn[k] = q; q += per; }
+    B.fphn = q; q += per;
+    B.amp = q; q += per; B.pol = q; q += per;
+    B.partial = q;
+
+    FieldView<double> F = make_view<double>(field);
+    const bool phase = (P->flags & SP_FLAG_PHASE) != 0, aux64 = phase && (P->flags & SP_FLAG_PHASE_F64) != 0;
+    const int p0 = field->perm[0], p1 = field->perm[1], p2 = field->perm[2];
+    const double rtol = P->rtol, atol = P->atol, omega = P->omega, t_end = P->t_end;
+    const int n_state = P->n_state > 0 ? P->n_state : 9;
+    const double size = (double)n_state * (double)n;     // x.size of the flattened state
+    uint64_t evals = 0;
+
+    auto init_pass = [&](int pass, double h0) -> int {
+        if (!phase) k_joint_init<false, false><<<nblocks, threads, 0, st>>>(F, B, s0_dev, n, p0, p1, p2, omega, rtol, atol, pass, h0);
+        else if (!aux64) k_joint_init<true, false><<<nblocks, threads, 0, st>>>(F, B, s0_dev, n, p0, p1, p2, omega, rtol, atol, pass, h0);
+        else k_joint_init<true, true><<<nblocks, threads, 0, st>>>(F, B, s0_dev, n, p0, p1, p2, omega, rtol, atol, pass, h0);
+        LAUNCH_CHECK();
+        k_joint_reduce<<<1, 256, 0, st>>>(B.partial, nblocks, ws->host_pair);
+        LAUNCH_CHECK();
+        CU(cudaStreamSynchronize(st));
+        evals += n;
+        return SP_OK;
+    };
+    // select_initial_step (scipy/integrate/_ivp/common.py)
+    int rc = init_pass(0, 0.0);
+    if (rc) return rc;
+    const double d0 = sqrt(ws->host_pair[0]) / sqrt(size), d1 = sqrt(ws->host_pair[1]) / sqrt(size);
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    h0 = h0 < t_end ? h0 : t_end;
+    rc = init_pass(1, h0);
+    if (rc) return rc;
+    const double d2 = sqrt(ws->host_pair[0]) / sqrt(size) / h0;
+    double h1;
+    if (d1 <= 1e-15 && d2 <= 1e-15) h1 = (1e-6 > h0 * 1e-3) ? 1e-6 : h0 * 1e-3;
+    else h1 = pow(0.01 / (d1 > d2 ? d1 : d2), 0.2);
+    double h_abs = 100 * h0 < h1 ? 100 * h0 : h1;
+    h_abs = h_abs < t_end ? h_abs : t_end;
+
+    double t = 0.0;
+    uint64_t attempts = 0, accepted = 0;
+    const uint64_t cap = P->n_steps > 0 ? (uint64_t)P->n_steps : (1ull << 30);
+    bool failed = false;
+    while (t < t_end && !failed) {
+        const double min_step = 10 * fabs(nextafter(t, INFINITY) - t);
+        if (h_abs < min_step) h_abs = min_step;
+        bool rejected = false;
+        for (;;) {
+            if (attempts >= cap || h_abs < min_step) { failed = true; break; }
+            double t_new = t + h_abs;
+            if (t_new - t_end > 0) t_new = t_end;
+            const double h = t_new - t;
+            h_abs = fabs(h);
+            if (!phase) k_joint_attempt<false, false><<<nblocks, threads, 0, st>>>(F, B, n, omega, h, rtol, atol);
+            else if (!aux64) k_joint_attempt<true, false><<<nblocks, threads, 0, st>>>(F, B, n, omega, h, rtol, atol);
+            else k_joint_attempt<true, true><<<nblocks, threads, 0, st>>>(F, B, n, omega, h, rtol, atol);
+            LAUNCH_CHECK();
+            k_joint_reduce<<<1, 256, 0, st>>>(B.partial, nblocks, ws->host_pair);
+            LAUNCH_CHECK();
+            CU(cudaStreamSynchronize(st));
+            ++attempts; evals += 6 * n;
+            const double en = sqrt(ws->host_pair[0]) / sqrt(size);
+            if (en < 1) {
+                double f = (en == 0) ? DP::MAX_FACTOR : fmin(DP::MAX_FACTOR, DP::SAFETY * pow(en, -0.2));
+                if (rejected) f = fmin(1.0, f);
+                h_abs *= f;
+                t = t_new; ++accepted;
+                // accept: candidate becomes current (pointer swap)
+                for (int k = 0; k < 3; ++k) { std::swap(B.p[k], B.pn[k]); std::swap(B.v[k], B.vn[k]); std::swap(B.fv[k], B.fvn[k]); }
+                std::swap(B.ph, B.phn); std::swap(B.fph, B.fphn);
+                break;
+            }
+            h_abs *= fmax(DP::MIN_FACTOR, DP::SAFETY * pow(en, -0.2));
+            rejected = true;
+        }
+    }
+    k_joint_finish<<<nblocks, threads, 0, st>>>(B, n, 0, p0, p1, p2, kernel_index_of(field, P->probing_axis),
+                                                kernel_index_of(field, P->out_axis_a), kernel_index_of(field, P->out_axis_b),
+                                                P->extent, E, stats_dev);
+    LAUNCH_CHECK();
+    if (stats_dev) {
+        sp_stats hs; memset(&hs, 0, sizeof(hs));
+        sp_stats cur;
+        CU(cudaMemcpyAsync(&cur, stats_dev, sizeof(cur), cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        cur.ray_steps += attempts * n; cur.ray_steps_acc += accepted * n; cur.rhs_evals += evals;
+        cur.rays_capped += failed ? n : 0;
+        CU(cudaMemcpyAsync(stats_dev, &cur, sizeof(cur), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    if (E.steps) {
+        // every ray took the same number of attempts
+        std::vector<uint32_t> hsteps(n, (uint32_t)attempts);
+        CU(cudaMemcpyAsync(E.steps, hsteps.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CU(cudaStreamSynchronize(st));
+    }
+    return SP_OK;
+}
+
+extern "C" int sp_rhs(const sp_field* field, const sp_params* P, const double* s_dev, uint64_t n, double* dsdt_dev,
+                      void* stream) {
+    if (!field || !P || !s_dev || !dsdt_dev) return fail(SP_EINVAL, "null argument");
+    if ((P->flags & SP_FLAG_PHASE_F64) && !field->aux64) return fail(SP_ESTATE, "field was built without SP_FIELD_PHASE_F64");
+    if (n == 0) return SP_OK;
+    FieldView<double> F = make_view<double>(field);
+    const bool phase = (P->flags & SP_FLAG_PHASE) != 0, aux64 = phase && (P->flags & SP_FLAG_PHASE_F64) != 0;
+    const int blocks = (int)((n + 127) / 128);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int p0 = field->perm[0], p1 = field->perm[1], p2 = field->perm[2];
+    if (!phase) k_rhs<false, false><<<blocks, 128, 0, st>>>(F, s_dev, n, dsdt_dev, p0, p1, p2, P->omega);
+    else if (!aux64) k_rhs<true, false><<<blocks, 128, 0, st>>>(F, s_dev, n, dsdt_dev, p0, p1, p2, P->omega);
+    else k_rhs<true, true><<<blocks, 128, 0, st>>>(F, s_dev, n, dsdt_dev, p0, p1, p2, P->omega);
+    LAUNCH_CHECK();
+    return SP_OK;
+}
+
+extern "C" int sp_beam_generate(const sp_beam* beam, uint64_t ray_offset, uint64_t n, double* s0_dev, void* stream) {
+    if (!beam || !s0_dev) return fail(SP_EINVAL, "null argument");
+    if (n == 0) return SP_OK;
+    k_beam<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(beam_to_spec(beam), ray_offset, n, s0_dev);
+    LAUNCH_CHECK();
+    return SP_OK;
+}
+
+extern "C" int sp_optics_image(const double* rf_dev, const double* jf_dev, uint64_t n, const sp_channel* chan,
+                               double* rf_out_dev, double* jf_out_dev, void* stream) {
+    if (!rf_dev || !chan) return fail(SP_EINVAL, "null argument");
+    if (n == 0) return SP_OK;
+    ChannelDev ch;
+    int rc = channel_to_dev(chan, ch);
+    if (rc) return rc;
+    if (ch.kind == SP_IMG_INTERFEROGRAM && ch.nx > 0 && !jf_dev) return fail(SP_EINVAL, "interferogram needs Jones vectors");
+    uint64_t blocks = (n + 255) / 256;
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    k_optics_image<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rf_dev, jf_dev, n, ch, rf_out_dev, jf_out_dev);
+    LAUNCH_CHECK();
+    return SP_OK;
+}
+
+extern "C" int sp_image_finalize(const sp_image* img, double* H_dev, void* stream) {
+    if (!img || !H_dev || !img->planes_dev) return fail(SP_EINVAL, "null argument");
+    const size_t npix = (size_t)img->nx * img->ny;
+    if (npix == 0) return SP_OK;
+    k_finalize<<<(unsigned)((npix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img->planes_dev, H_dev, npix);
+    LAUNCH_CHECK();
+    return SP_OK;
+}

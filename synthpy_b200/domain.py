@@ -1,0 +1,105 @@
+"""Field container with the call shape of the reference's ``src/simulator/domain.py::ScalarDomain``.
+
+Only what the ray path needs is kept: float32-rounded axes, the ``ne`` grid, analytic test profiles and
+``external_*`` loaders (which, unlike upstream's frozen ``eqx.Module`` -- domain.py:310,453-461 -- work).
+The memory-driven domain batching of the reference (domain.py:137-243, WIP upstream) is not needed: a
+1024^3 packed field is 17 GB of a B200's 180 GB.  The packed device field is built lazily per wavelength.
+"""
+import numpy as np
+
+from . import engine
+
+
+class ScalarDomain:
+    def __init__(self, lengths, dims, *, ne_type=None, inv_brems=False, phaseshift=False, B_on=False,
+                 probing_direction="z", auto_batching=True, iteration=1, region_count=1, leeway_factor=None,
+                 coord_backup=None, future_dims=None, debug=False):
+        if inv_brems or B_on:
+            raise NotImplementedError("inverse-bremsstrahlung / Faraday channels are outside the accelerated "
+                                      "path (SURVEY.md 8f-3); phaseshift is supported")
+        self.inv_brems, self.phaseshift, self.B_on = inv_brems, phaseshift, B_on
+        self.probing_direction = probing_direction
+        self.ne_type = ne_type
+        self.leeway_factor = 1.1 if leeway_factor is None else leeway_factor
+        self.debug = debug
+        # domain.py:108-132: scalar or length-3
+        if np.ndim(lengths) == 0:
+            lengths = [lengths] * 3
+        if np.ndim(dims) == 0:
+            dims = [dims] * 3
+        if len(lengths) != 3:
+            raise Exception("lengths must have len = 3: (x,y,z)")
+        if len(dims) != 3:
+            raise Exception("n must have len = 3: (x_n, y_n, z_n)")
+        self.x_length, self.y_length, self.z_length = (float(v) for v in lengths)
+        self.lengths = np.array([self.x_length, self.y_length, self.z_length])
+        self.x_n, self.y_n, self.z_n = (int(v) for v in dims)
+        self.dims = np.array([self.x_n, self.y_n, self.z_n])
+        self.region_count = 1                       # no domain batching needed on a 180 GB part
+        self.coord_backup = self.future_dims = None
+        # domain.py:230-232: float32-rounded linspace axes
+        self._axes64 = [np.linspace(-L / 2, L / 2, n) for L, n in zip(self.lengths, self.dims)]
+        self.x, self.y, self.z = (np.float32(a) for a in self._axes64)
+        self.ne = self.B = self.Te = self.Z = None
+        self._fields = {}
+        # domain.py:380-390: optional profile selected by name
+        if ne_type is not None:
+            getattr(self, ne_type)()
+
+    # -- profiles (domain.py:392-451; arithmetic follows the runnable legacy code, full_solver.py:130-167)
+    def _mesh(self):
+        return np.meshgrid(*self._axes64, indexing="ij", copy=False)
+
+    def _set(self, ne):
+        self.ne = ne
+        self._fields.clear()
+
+    def test_null(self):
+        self._set(np.zeros(tuple(self.dims)))
+
+    def test_slab(self, s=1, ne_0=2e23):
+        self._set(ne_0 * (1.0 + s * self._mesh()[0] / self.x_length))
+
+    def test_linear_cos(self, s1=0.1, s2=0.1, ne_0=2e23, Ly=1):
+        XX, YY, _ = self._mesh()
+        self._set(ne_0 * (1.0 + s1 * XX / self.x_length) * (1 + s2 * np.cos(2 * np.pi * YY / Ly)))
+
+    def test_exponential_cos(self, ne_0=1e24, Ly=1e-3, s=2e-3):
+        XX, YY, _ = self._mesh()
+        self._set(ne_0 * 10 ** (XX / s) * (1 + np.cos(2 * np.pi * YY / Ly)))
+
+    # -- external grids (domain.py:453-491)
+    def external_ne(self, ne):
+        """ne: (x_n, y_n, z_n) numpy array or CUDA torch tensor (float64 or float32), m^-3."""
+        if tuple(ne.shape) != tuple(self.dims):
+            raise ValueError(f"ne has shape {tuple(ne.shape)}, domain is {tuple(self.dims)}")
+        self._set(ne)
+
+    def external_B(self, B):
+        self.B = B
+
+    def external_Te(self, Te, Te_min=1.0):
+        self.Te = np.maximum(Te_min, Te)
+
+    def external_Z(self, Z):
+        self.Z = Z
+
+    # -- device side
+    def device_field(self, lwl, *, phase=None, phase_f64=False):
+        """Packed float4 {grad, n-1} grid for wavelength ``lwl`` (cached)."""
+        if self.ne is None:
+            raise RuntimeError("no electron density loaded (call a test_* profile or external_ne)")
+        phase = self.phaseshift if phase is None else phase
+        key = (float(lwl), bool(phase), bool(phase_f64), self.probing_direction)
+        if key not in self._fields:
+            self._fields[key] = engine.DeviceField.from_ne(
+                self.ne, self.x, self.y, self.z, engine.omega_of(lwl),
+                march_axis=engine.AXIS[self.probing_direction], phase=phase, phase_f64=phase_f64)
+        return self._fields[key]
+
+    def cell_size(self, axis=None):
+        a = engine.AXIS[self.probing_direction] if axis is None else axis
+        return self.lengths[a] / (self.dims[a] - 1)
+
+    def cleanup(self):
+        pass

@@ -1,0 +1,128 @@
+"""``solve`` with the call shape of the reference's ``src/simulator/propagator.py::solve`` (propagator.py:351-702),
+plus the fused ``solve_and_image`` fast path that never materialises exit rays.
+
+Integrators (``method=``):
+  'rk4'        fixed-step classical RK4, default ``ds`` = half a cell along the probing axis, early exit once a
+               ray has left the grid.  The production default (the RHS is only C0, so ~2 steps
+               per cell is where accuracy saturates).
+  'rk45'       Dormand-Prince 5(4) with SciPy's controller and tolerances, step size chosen per ray
+               (== the legacy solver run one ray at a time).
+  'rk45_joint' the legacy solver exactly as shipped: one step size for the whole bundle
+               (src/solvers-legacy/full_solver.py:391).  Explicit s0 only.
+"""
+from time import time
+
+import numpy as np
+import torch
+
+from . import engine
+from .engine import C_LIGHT as c
+
+
+def _out_axes(probing_direction, convention):
+    p = engine.AXIS[probing_direction]
+    if convention == "legacy":            # full_solver.py:856-881
+        return {0: (1, 2), 1: (0, 2), 2: (0, 1)}[p]
+    return {0: (1, 2), 1: (2, 0), 2: (0, 1)}[p]      # propagator.py:222-262 ('y' swapped upstream)
+
+
+def _params(domain, probing_depth, lwl, method, n_steps, ds, rtol, atol, precision, early_exit, phase, phase_f64,
+            sort, convention, max_steps):
+    extent = float(probing_depth)
+    t_end = np.sqrt(8.0) * extent / c
+    h, n = 0.0, 0
+    if method == "rk4":
+        if ds is None and n_steps is None:
+            ds = 0.5 * domain.cell_size()
+        if ds is not None:
+            h = float(ds) / c
+            n = int(np.ceil(t_end / h)) if n_steps is None else int(n_steps)
+        else:
+            n = int(n_steps)
+            h = t_end / n
+    else:
+        n = int(max_steps or 0)
+    return engine.make_params(method, probing_direction=domain.probing_direction, extent=extent,
+                              omega=engine.omega_of(lwl), n_steps=n, h=h, t_end=t_end, rtol=rtol, atol=atol,
+                              phase=phase, phase_f64=phase_f64, early_exit=early_exit, fp32=(precision == "fp32"),
+                              sort=sort, out_axes=_out_axes(domain.probing_direction, convention))
+
+
+def solve(s0_import, ScalarDomain, probing_depth, *, return_E=False, parallelise=True, jitted=True, save_steps=2,
+          memory_debug=False, lwl=1064e-9, keep_domain=False,
+          method="rk4", n_steps=None, ds=None, rtol=1e-3, atol=1e-6, precision="fp64", early_exit=True,
+          phase_f64=False, sort=True, axis_convention="current", max_steps=None, return_stats=False,
+          return_state=False):
+    """Trace rays ``s0_import`` (9,N) through ``ScalarDomain``; returns ``(rf, Jf, duration)`` like the
+    reference: rf (4,N) [x, theta, y, phi] at the exit plane (m, rad), Jf (2,N) complex or None.
+    ``parallelise / jitted / save_steps / memory_debug / keep_domain`` are accepted for call compatibility.
+
+    numpy in -> numpy out; CUDA tensors in -> CUDA tensors out (no host round trip).
+    With ``return_stats`` / ``return_state`` a dict with 'stats', 'sf', 'steps' is appended to the tuple."""
+    engine.require_cuda()
+    as_numpy = not isinstance(s0_import, torch.Tensor)
+    s0 = engine.to_device(s0_import, torch.float64)
+    phase = bool(ScalarDomain.phaseshift)
+    field = ScalarDomain.device_field(lwl, phase=phase, phase_f64=phase_f64)
+    P = _params(ScalarDomain, probing_depth, lwl, method, n_steps, ds, rtol, atol, precision, early_exit, phase,
+                phase_f64, sort, axis_convention, max_steps)
+    torch.cuda.synchronize()
+    start = time()
+    out = engine.propagate(field, P, s0=s0, want_rf=True, want_jf=return_E, want_sf=return_state,
+                           want_steps=return_state, with_stats=True)
+    torch.cuda.synchronize()
+    duration = time() - start
+    rf, jf = out["rf"], out["jf"]
+    if as_numpy:
+        rf = rf.cpu().numpy()
+        jf = None if jf is None else jf.cpu().numpy()
+    if return_stats or return_state:
+        extra = {"stats": engine.stats_dict(out["stats_dev"])}
+        if return_state:
+            extra["sf"] = out["sf"].cpu().numpy() if as_numpy else out["sf"]
+            extra["steps"] = out["steps"].cpu().numpy() if as_numpy else out["steps"]
+        return rf, jf, duration, extra
+    return rf, jf, duration
+
+
+def solve_and_image(ScalarDomain, rays, probing_depth, diagnostics, *, lwl=1064e-9, n_rays=None, ray_offset=0,
+                    method="rk4", n_steps=None, ds=None, rtol=1e-3, atol=1e-6, precision="fp64", early_exit=True,
+                    phase_f64=False, sort=True, axis_convention="current", max_steps=None, sync=True):
+    """Fused hot path: rays -> ODE -> exit plane -> optics -> detector images, in one kernel per chunk.
+
+    rays         a (9,N) array/tensor, or a ``Beam(device=True)`` whose rays are generated on the GPU
+    diagnostics  list of ``DiagnosticSpec`` (see ``diagnostics.spec``); their images accumulate
+    Returns (stats dict or None, elapsed seconds or None)."""
+    engine.require_cuda()
+    need_phase = any(d.image.kind == "interferogram" for d in diagnostics)
+    phase = bool(ScalarDomain.phaseshift) or need_phase
+    field = ScalarDomain.device_field(lwl, phase=phase, phase_f64=phase_f64)
+    P = _params(ScalarDomain, probing_depth, lwl, method, n_steps, ds, rtol, atol, precision, early_exit, phase,
+                phase_f64, sort, axis_convention, max_steps)
+    chans = [(d.ops, d.image, d.wavelength if d.wavelength else lwl) for d in diagnostics]
+    kw = dict(want_rf=False, channels=chans)
+    if hasattr(rays, "spec"):                       # device Beam
+        n = rays.Np if n_rays is None else n_rays
+        kw.update(beam=rays.spec, n=n, ray_offset=ray_offset)
+    else:
+        kw.update(s0=engine.to_device(rays, torch.float64))
+    if sync:
+        torch.cuda.synchronize()
+    start = time()
+    out = engine.propagate(field, P, **kw)
+    if not sync:
+        return out["stats_dev"], None
+    torch.cuda.synchronize()
+    return engine.stats_dict(out["stats_dev"]), time() - start
+
+
+def rhs(s, ScalarDomain, *, lwl=1064e-9, phase_f64=False):
+    """d(state)/dt of the ray ODE (propagator.py:94-175 / full_solver.py:516-544) for a (9,N) state."""
+    as_numpy = not isinstance(s, torch.Tensor)
+    sd = engine.to_device(s, torch.float64)
+    phase = bool(ScalarDomain.phaseshift)
+    field = ScalarDomain.device_field(lwl, phase=phase, phase_f64=phase_f64)
+    P = engine.make_params("rk4", probing_direction=ScalarDomain.probing_direction, extent=1.0,
+                           omega=engine.omega_of(lwl), n_steps=1, h=1.0, phase=phase, phase_f64=phase_f64)
+    out = engine.rhs(field, P, sd)
+    return out.cpu().numpy() if as_numpy else out

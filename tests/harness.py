@@ -1,0 +1,124 @@
+"""ctypes loader of tests/host_harness.cpp (CPU self-test build of the product's per-ray math)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "_build", "libhost_harness.so")
+SRC = os.path.join(HERE, "host_harness.cpp")
+DEPS = [SRC, os.path.join(HERE, "..", "synthpy_b200", "csrc", "ray_core.h"),
+        os.path.join(HERE, "..", "synthpy_b200", "csrc", "field_prep.h")]
+
+OPK = {"travel": 0, "travel_noE": 1, "lens": 2, "circ_ap": 3, "circ_stop": 4, "rect_ap": 5, "knife": 6, "ref_beam": 7}
+
+
+def build():
+    os.makedirs(os.path.dirname(SO), exist_ok=True)
+    if os.path.exists(SO) and all(os.path.getmtime(SO) >= os.path.getmtime(d) for d in DEPS):
+        return SO
+    subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", SRC, "-o", SO], check=True)
+    return SO
+
+
+class HOp(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("pad", C.c_int32), ("p0", C.c_double), ("p1", C.c_double), ("p2", C.c_double)]
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class Harness:
+    def __init__(self):
+        self.lib = C.CDLL(build())
+        self.lib.hh_field_create.restype = C.c_void_p
+
+    def field(self, ne, x, y, z, omega, march_axis=2, phase=False, f64=False):
+        ne = np.ascontiguousarray(ne, dtype=np.float64)
+        ax = [np.ascontiguousarray(np.float32(a)) for a in (x, y, z)]
+        h = self.lib.hh_field_create(_p(ne), _p(ax[0]), _p(ax[1]), _p(ax[2]), C.c_int(len(ax[0])), C.c_int(len(ax[1])),
+                                     C.c_int(len(ax[2])), C.c_double(omega), C.c_int(march_axis),
+                                     C.c_int((1 if phase else 0) | (2 if f64 else 0)))
+        assert h
+        return HField(self, C.c_void_p(h), ne.shape, omega, phase, f64)
+
+    def optics(self, rf, ops, jf=None, wavelength=0.0, input_mm=False):
+        rf = np.ascontiguousarray(rf, dtype=np.float64)
+        n = rf.shape[1]
+        arr = (HOp * max(1, len(ops)))()
+        for i, op in enumerate(ops):
+            v = list(op[1:]) + [0.0] * (4 - len(op))
+            arr[i] = HOp(OPK[op[0]], 0, float(v[0]), float(v[1]), float(v[2]))
+        out = np.empty_like(rf)
+        jo = None
+        if jf is not None:
+            jf = np.ascontiguousarray(jf, dtype=np.complex128)
+            jo = np.empty_like(jf)
+        self.lib.hh_optics(_p(rf), _p(jf), C.c_uint64(n), arr, C.c_int(len(ops)), C.c_double(wavelength),
+                           C.c_int(int(input_mm)), _p(out), _p(jo))
+        return (out, jo) if jf is not None else out
+
+    def bins(self, v, lo, hi, nb, right_inclusive):
+        v = np.ascontiguousarray(v, dtype=np.float64)
+        out = np.empty(v.shape, dtype=np.int32)
+        self.lib.hh_bin(_p(v), C.c_uint64(v.size), C.c_double(lo), C.c_double(hi), C.c_int(nb), C.c_int(int(right_inclusive)),
+                        _p(out))
+        return out
+
+    def beam(self, beam_type, probing_axis, size_a, size_b, divergence, start, seed, off, n):
+        s0 = np.empty((9, n))
+        self.lib.hh_beam(C.c_int(beam_type), C.c_int(probing_axis), C.c_double(size_a), C.c_double(size_b),
+                         C.c_double(divergence), C.c_double(start), C.c_uint64(seed), C.c_uint64(off), C.c_uint64(n), _p(s0))
+        return s0
+
+    def philox(self, key, ctr):
+        out = np.empty(4, dtype=np.uint32)
+        self.lib.hh_philox(*(C.c_uint32(k) for k in key), *(C.c_uint32(c) for c in ctr), _p(out))
+        return out
+
+
+class HField:
+    def __init__(self, H, h, shape, omega, phase, f64):
+        self.H, self.h, self.shape, self.omega, self.phase, self.f64 = H, h, shape, omega, phase, f64
+
+    def __del__(self):
+        self.H.lib.hh_field_destroy(self.h)
+
+    def export(self):
+        outs = [np.empty(self.shape, dtype=np.float32) for _ in range(4)]
+        self.H.lib.hh_field_export(self.h, *[_p(o) for o in outs])
+        return outs
+
+    def rhs(self, s, aux64=None):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        out = np.empty_like(s)
+        self.H.lib.hh_rhs(self.h, _p(s), C.c_uint64(s.shape[1]), _p(out), C.c_double(self.omega), C.c_int(int(self.phase)),
+                          C.c_int(int(self.f64 if aux64 is None else aux64)))
+        return out
+
+    def rk4(self, s0, n_steps, h, early=False, fp32=False, aux64=None):
+        s0 = np.ascontiguousarray(s0, dtype=np.float64)
+        sf = np.empty_like(s0)
+        steps = np.empty(s0.shape[1], dtype=np.uint32)
+        self.H.lib.hh_rk4(self.h, _p(s0), C.c_uint64(s0.shape[1]), C.c_int(n_steps), C.c_double(h), C.c_double(self.omega),
+                          C.c_int(int(self.phase)), C.c_int(int(self.f64 if aux64 is None else aux64)), C.c_int(int(early)),
+                          C.c_int(int(fp32)), _p(sf), _p(steps))
+        return sf, steps
+
+    def rk45(self, s0, t_end, rtol=1e-3, atol=1e-6, n_state=9, cap=0, aux64=None):
+        s0 = np.ascontiguousarray(s0, dtype=np.float64)
+        sf = np.empty_like(s0)
+        att = np.empty(s0.shape[1], dtype=np.uint32)
+        nfev = np.empty(s0.shape[1], dtype=np.uint32)
+        self.H.lib.hh_rk45(self.h, _p(s0), C.c_uint64(s0.shape[1]), C.c_double(t_end), C.c_double(rtol), C.c_double(atol),
+                           C.c_double(self.omega), C.c_int(int(self.phase)), C.c_int(int(self.f64 if aux64 is None else aux64)),
+                           C.c_int(n_state), C.c_int(cap), _p(sf), _p(att), _p(nfev))
+        return sf, att, nfev
+
+    def exit(self, sf, p, a, b, extent):
+        sf = np.ascontiguousarray(sf, dtype=np.float64)
+        rf = np.empty((4, sf.shape[1]))
+        self.H.lib.hh_exit(self.h, _p(sf), C.c_uint64(sf.shape[1]), C.c_int(p), C.c_int(a), C.c_int(b), C.c_double(extent), _p(rf))
+        return rf

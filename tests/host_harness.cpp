@@ -1,0 +1,316 @@
+// CPU self-test build of the product's per-ray math (synthpy_b200/csrc/ray_core.h, field_prep.h).
+// The build container has no GPU; this harness lets the CPU test-suite run the very same source that is
+// inlined into the sm_100a kernels against the golden vectors.  It is TEST code: nothing in synthpy_b200/
+// loads it, and it is not a fallback.
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../synthpy_b200/csrc/field_prep.h"
+#include "../synthpy_b200/csrc/ray_core.h"
+
+using namespace sp;
+
+struct HostField {
+    int n[3], perm[3], nk[3];
+    std::vector<f4> data;
+    std::vector<double> aux64;
+    AxisTables tabs[3];
+    FieldView<double> view64() const {
+        FieldView<double> V;
+        V.data = data.data(); V.aux64 = aux64.empty() ? nullptr : aux64.data();
+        for (int k = 0; k < 3; ++k) {
+            V.ax[k].tab = tabs[k].t64.data(); V.ax[k].g0 = tabs[k].g0; V.ax[k].inv_d = tabs[k].inv_d;
+            V.ax[k].lo = tabs[k].lo; V.ax[k].hi = tabs[k].hi; V.ax[k].n = nk[k];
+        }
+        V.su = (long long)nk[1] * nk[2]; V.sv = nk[2];
+        return V;
+    }
+    FieldView<float> view32() const {
+        FieldView<float> V;
+        V.data = data.data(); V.aux64 = aux64.empty() ? nullptr : aux64.data();
+        for (int k = 0; k < 3; ++k) {
+            V.ax[k].tab = tabs[k].t32.data(); V.ax[k].g0 = (float)tabs[k].g0; V.ax[k].inv_d = (float)tabs[k].inv_d;
+            V.ax[k].lo = (float)tabs[k].lo; V.ax[k].hi = (float)tabs[k].hi; V.ax[k].n = nk[k];
+        }
+        V.su = (long long)nk[1] * nk[2]; V.sv = nk[2];
+        return V;
+    }
+};
+
+// Same arithmetic as sp_field_create: returns an opaque host field.
+extern "C" void* hh_field_create(const double* ne, const float* ax, const float* ay, const float* az, int nx, int ny, int nz,
+                      double omega, int march_axis, int flags) {
+    HostField* f = new HostField();
+    f->n[0] = nx; f->n[1] = ny; f->n[2] = nz;
+    f->perm[0] = (march_axis + 1) % 3; f->perm[1] = (march_axis + 2) % 3; f->perm[2] = march_axis;
+    const float* axh[3] = {ax, ay, az};
+    for (int k = 0; k < 3; ++k) {
+        f->nk[k] = f->n[f->perm[k]];
+        if (!build_axis_tables(axh[f->perm[k]], f->nk[k], f->tabs[k])) { delete f; return nullptr; }
+    }
+    const long long cells = (long long)nx * ny * nz;
+    const double nc = 3.14207787e-4 * omega * omega;
+    std::vector<float> ne_nc(cells);
+    for (long long i = 0; i < cells; ++i) ne_nc[i] = normalise_ne(ne[i], nc);
+    AxisCoef C[3];
+    PackArgs P; memset(&P, 0, sizeof(P));
+    for (int a = 0; a < 3; ++a) {
+        C[a] = axis_coef(axh[a], f->n[a]);
+        P.n[a] = f->n[a]; P.perm[a] = f->perm[a]; P.nk[a] = f->nk[a];
+        P.st[a].a = C[a].a.data(); P.st[a].b = C[a].b.data(); P.st[a].c = C[a].c.data();
+        P.st[a].two_dx = C[a].two_dx; P.st[a].dx0 = C[a].dx0; P.st[a].dxn = C[a].dxn;
+        P.st[a].uniform = C[a].uniform; P.st[a].n = f->n[a];
+    }
+    const double c = 299792458.0;
+    P.k32 = (float)(-0.5 * c * c); P.omega = omega; P.flags = flags;
+    f->data.resize(cells);
+    if (flags & 2) f->aux64.resize(cells);
+    for (long long t = 0; t < cells; ++t) {
+        double nm1;
+        f->data[t] = pack_cell<double>(t, ne_nc.data(), ne, P, nm1);
+        if (flags & 2) f->aux64[t] = nm1;
+    }
+    return f;
+}
+
+extern "C" void hh_field_destroy(void* h) { delete (HostField*)h; }
+
+// gradients back in caller order [x][y][z]
+extern "C" void hh_field_export(void* h, float* gx, float* gy, float* gz, float* aux) {
+    HostField* f = (HostField*)h;
+    PackArgs P; memset(&P, 0, sizeof(P));
+    for (int a = 0; a < 3; ++a) { P.n[a] = f->n[a]; P.perm[a] = f->perm[a]; P.nk[a] = f->nk[a]; }
+    const long long cells = (long long)f->n[0] * f->n[1] * f->n[2];
+    for (long long t = 0; t < cells; ++t) {
+        int ic[3];
+        const long long idx = unpack_index(t, P, ic);
+        float g[3];
+        g[P.perm[0]] = f->data[t].x; g[P.perm[1]] = f->data[t].y; g[P.perm[2]] = f->data[t].z;
+        gx[idx] = g[0]; gy[idx] = g[1]; gz[idx] = g[2]; aux[idx] = f->data[t].w;
+    }
+}
+
+static void load(const HostField* f, const double* s, uint64_t n, uint64_t i, Ray<double>& r) {
+    for (int k = 0; k < 3; ++k) { r.p[k] = s[(uint64_t)f->perm[k] * n + i]; r.v[k] = s[(uint64_t)(3 + f->perm[k]) * n + i]; }
+    r.ph = s[7 * n + i];
+}
+static void store(const HostField* f, double* s, const double* s0, uint64_t n, uint64_t i, const Ray<double>& r) {
+    for (int k = 0; k < 3; ++k) { s[(uint64_t)f->perm[k] * n + i] = r.p[k]; s[(uint64_t)(3 + f->perm[k]) * n + i] = r.v[k]; }
+    s[6 * n + i] = s0[6 * n + i]; s[7 * n + i] = r.ph; s[8 * n + i] = s0[8 * n + i];
+}
+
+template <bool PH, bool A64>
+static void rhs_t(const HostField* f, const double* s, uint64_t n, double* out, double omega) {
+    FieldView<double> F = f->view64();
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray<double> r; load(f, s, n, i, r);
+        Deriv<double> d;
+        deriv<double, PH, A64>(F, omega, r.p, r.v, d);
+        for (int k = 0; k < 3; ++k) { out[(uint64_t)f->perm[k] * n + i] = d.dp[k]; out[(uint64_t)(3 + f->perm[k]) * n + i] = d.dv[k]; }
+        out[6 * n + i] = 0; out[7 * n + i] = d.dph; out[8 * n + i] = 0;
+    }
+}
+extern "C" void hh_rhs(void* h, const double* s, uint64_t n, double* out, double omega, int phase, int aux64) {
+    const HostField* f = (const HostField*)h;
+    if (!phase) rhs_t<false, false>(f, s, n, out, omega);
+    else if (!aux64) rhs_t<true, false>(f, s, n, out, omega);
+    else rhs_t<true, true>(f, s, n, out, omega);
+}
+
+template <typename T, bool PH, bool A64>
+static void rk4_t(const HostField* f, const FieldView<T>& F, const double* s0, uint64_t n, int n_steps, double h,
+                  double omega, int early, double* sf, uint32_t* steps) {
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray<double> rd; load(f, s0, n, i, rd);
+        Ray<T> r;
+        for (int k = 0; k < 3; ++k) { r.p[k] = (T)rd.p[k]; r.v[k] = (T)rd.v[k]; }
+        r.ph = (T)rd.ph;
+        uint32_t it = 0;
+        for (; it < (uint32_t)n_steps; ++it) {
+            if (early && escaped(F, r)) break;
+            rk4_step<T, PH, A64>(F, (T)h, (T)omega, r);
+        }
+        for (int k = 0; k < 3; ++k) { rd.p[k] = r.p[k]; rd.v[k] = r.v[k]; }
+        rd.ph = r.ph;
+        store(f, sf, s0, n, i, rd);
+        if (steps) steps[i] = it;
+    }
+}
+extern "C" void hh_rk4(void* h, const double* s0, uint64_t n, int n_steps, double hstep, double omega, int phase, int aux64,
+            int early, int fp32, double* sf, uint32_t* steps) {
+    const HostField* f = (const HostField*)h;
+    if (fp32) {
+        FieldView<float> F = f->view32();
+        if (!phase) rk4_t<float, false, false>(f, F, s0, n, n_steps, hstep, omega, early, sf, steps);
+        else rk4_t<float, true, false>(f, F, s0, n, n_steps, hstep, omega, early, sf, steps);
+        return;
+    }
+    FieldView<double> F = f->view64();
+    if (!phase) rk4_t<double, false, false>(f, F, s0, n, n_steps, hstep, omega, early, sf, steps);
+    else if (!aux64) rk4_t<double, true, false>(f, F, s0, n, n_steps, hstep, omega, early, sf, steps);
+    else rk4_t<double, true, true>(f, F, s0, n, n_steps, hstep, omega, early, sf, steps);
+}
+
+// per-ray adaptive driver: same control flow as k_propagate<.., SP_METHOD_RK45, ..>
+template <bool PH, bool A64>
+static void rk45_t(const HostField* f, const double* s0, uint64_t n, double t_end, double rtol, double atol, double omega,
+                   int n_state, int cap_in, double* sf, uint32_t* attempts, uint32_t* nfev) {
+    FieldView<double> F = f->view64();
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray<double> r; load(f, s0, n, i, r);
+        const double amp = s0[6 * n + i], pol = s0[8 * n + i];
+        Deriv<double> fd; int touched = 0; uint32_t evals = 1;
+        deriv<double, PH, A64>(F, omega, r.p, r.v, fd);
+        double h_abs = dp5_initial_step<double, PH, A64>(F, omega, t_end, rtol, atol, n_state, amp, pol, r, fd, touched);
+        evals += 1;
+        double t = 0; uint32_t n_att = 0;
+        const uint32_t cap = cap_in > 0 ? (uint32_t)cap_in : (1u << 30);
+        bool failed = false;
+        while (t < t_end && !failed) {
+            const double min_step = 10 * (nextafter(t, INFINITY) - t);
+            if (h_abs < min_step) h_abs = min_step;
+            bool rejected = false;
+            for (;;) {
+                if (n_att >= cap || h_abs < min_step) { failed = true; break; }
+                double t_new = t + h_abs;
+                if (t_new - t_end > 0) t_new = t_end;
+                const double h = t_new - t;
+                h_abs = fabs(h);
+                Ray<double> rn; Deriv<double> fn; double esq;
+                dp5_attempt<double, PH, A64>(F, omega, h, rtol, atol, r, fd, rn, fn, esq);
+                ++n_att; evals += 6;
+                const double en = sqrt(esq / n_state);
+                if (en < 1) { h_abs *= dp5_factor<double>(en, true, rejected); t = t_new; r = rn; fd = fn; break; }
+                h_abs *= dp5_factor<double>(en, false, rejected);
+                rejected = true;
+            }
+        }
+        store(f, sf, s0, n, i, r);
+        if (attempts) attempts[i] = n_att;
+        if (nfev) nfev[i] = evals;
+    }
+}
+extern "C" void hh_rk45(void* h, const double* s0, uint64_t n, double t_end, double rtol, double atol, double omega, int phase,
+             int aux64, int n_state, int cap, double* sf, uint32_t* attempts, uint32_t* nfev) {
+    const HostField* f = (const HostField*)h;
+    if (!phase) rk45_t<false, false>(f, s0, n, t_end, rtol, atol, omega, n_state, cap, sf, attempts, nfev);
+    else if (!aux64) rk45_t<true, false>(f, s0, n, t_end, rtol, atol, omega, n_state, cap, sf, attempts, nfev);
+    else rk45_t<true, true>(f, s0, n, t_end, rtol, atol, omega, n_state, cap, sf, attempts, nfev);
+}
+
+// exit projection in the caller frame: kp/ka/kb are caller axes
+extern "C" void hh_exit(void* h, const double* sf, uint64_t n, int p, int a, int b, double extent, double* rf) {
+    const HostField* f = (const HostField*)h;
+    int inv[3];
+    for (int k = 0; k < 3; ++k) inv[f->perm[k]] = k;
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray<double> r; load(f, sf, n, i, r);
+        exit_project<double>(r, inv[p], inv[a], inv[b], extent, rf[i], rf[n + i], rf[2 * n + i], rf[3 * n + i]);
+    }
+}
+
+struct HOp { int32_t kind, pad; double p0, p1, p2; };
+
+extern "C" void hh_optics(const double* rf, const double* jf, uint64_t n, const HOp* ops, int n_ops, double wavelength, int input_mm,
+               double* rf_out, double* jf_out) {
+    std::vector<OpticOp> o(n_ops > 0 ? n_ops : 1);
+    for (int i = 0; i < n_ops; ++i) { o[i].kind = ops[i].kind; o[i].p0 = ops[i].p0; o[i].p1 = ops[i].p1; o[i].p2 = ops[i].p2; }
+    const double kw = wavelength > 0 ? 2.0 * 3.14159265358979323846 / wavelength : 0.0;
+    const double nanv = NAN;
+    for (uint64_t i = 0; i < n; ++i) {
+        DetRay d; d.alive = true;
+        const double unit = input_mm ? 1.0 : 1e3;
+        d.x = rf[i] * unit; d.th = rf[n + i]; d.y = rf[2 * n + i] * unit; d.ph = rf[3 * n + i];
+        d.ex_re = d.ex_im = d.ey_re = d.ey_im = 0;
+        if (jf) { d.ex_re = jf[2 * i]; d.ex_im = jf[2 * i + 1]; d.ey_re = jf[2 * (n + i)]; d.ey_im = jf[2 * (n + i) + 1]; }
+        run_optics(d, rf[i], rf[2 * n + i], o.data(), n_ops, jf != nullptr, kw);
+        rf_out[i] = d.alive ? d.x : nanv; rf_out[n + i] = d.alive ? d.th : nanv;
+        rf_out[2 * n + i] = d.alive ? d.y : nanv; rf_out[3 * n + i] = d.alive ? d.ph : nanv;
+        if (jf_out) {
+            jf_out[2 * i] = d.alive ? d.ex_re : nanv; jf_out[2 * i + 1] = d.alive ? d.ex_im : nanv;
+            jf_out[2 * (n + i)] = d.alive ? d.ey_re : nanv; jf_out[2 * (n + i) + 1] = d.alive ? d.ey_im : nanv;
+        }
+    }
+}
+
+extern "C" void hh_bin(const double* v, uint64_t n, double lo, double hi, int nb, int right_inclusive, int32_t* out) {
+    for (uint64_t i = 0; i < n; ++i) out[i] = bin_index(v[i], lo, hi, nb, right_inclusive != 0);
+}
+
+extern "C" void hh_beam(int beam_type, int probing_axis, double size_a, double size_b, double divergence, double start,
+             uint64_t seed, uint64_t off, uint64_t n, double* s0) {
+    BeamSpec B; B.beam_type = beam_type; B.probing_axis = probing_axis; B.size_a = size_a; B.size_b = size_b;
+    B.divergence = divergence; B.start = start; B.seed = seed;
+    for (uint64_t i = 0; i < n; ++i) {
+        double s[6]; beam_ray(B, off + i, s);
+        for (int k = 0; k < 6; ++k) s0[(uint64_t)k * n + i] = s[k];
+        s0[6 * n + i] = 1.0; s0[7 * n + i] = 0.0; s0[8 * n + i] = 0.0;
+    }
+}
+
+extern "C" void hh_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t* out) {
+    Philox p; p.k0 = k0; p.k1 = k1; p.block(c0, c1, c2, c3, out);
+}
+
+// debug helper: initial step size chosen for each ray (phase + aux64 variant)
+extern "C" void hh_rk45_h0(void* h, const double* s0, uint64_t n, double t_end, double rtol, double atol, double omega,
+                           int n_state, double* h0) {
+    const HostField* f = (const HostField*)h;
+    FieldView<double> F = f->view64();
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray<double> r; load(f, s0, n, i, r);
+        Deriv<double> fd; int touched = 0;
+        deriv<double, true, true>(F, omega, r.p, r.v, fd);
+        h0[i] = dp5_initial_step<double, true, true>(F, omega, t_end, rtol, atol, n_state, s0[6 * n + i], s0[8 * n + i], r, fd, touched);
+    }
+}
+
+// debug helper: trace of accepted steps for ONE ray: t and the 7 live state values after each accepted step
+extern "C" int hh_rk45_trace(void* hnd, const double* s0, double t_end, double rtol, double atol, double omega, int n_state,
+                             int max_out, double* t_out, double* y_out, double* en_out) {
+    const HostField* f = (const HostField*)hnd;
+    FieldView<double> F = f->view64();
+    Ray<double> r; load(f, s0, 1, 0, r);
+    Deriv<double> fd; int touched = 0;
+    deriv<double, true, true>(F, omega, r.p, r.v, fd);
+    double h_abs = dp5_initial_step<double, true, true>(F, omega, t_end, rtol, atol, n_state, s0[6], s0[8], r, fd, touched);
+    double t = 0; int k = 0;
+    while (t < t_end && k < max_out) {
+        const double min_step = 10 * (nextafter(t, INFINITY) - t);
+        if (h_abs < min_step) h_abs = min_step;
+        bool rejected = false;
+        for (;;) {
+            double t_new = t + h_abs;
+            if (t_new - t_end > 0) t_new = t_end;
+            const double h = t_new - t;
+            h_abs = fabs(h);
+            Ray<double> rn; Deriv<double> fn; double esq;
+            dp5_attempt<double, true, true>(F, omega, h, rtol, atol, r, fd, rn, fn, esq);
+            const double en = sqrt(esq / n_state);
+            if (en < 1) { h_abs *= dp5_factor<double>(en, true, rejected); t = t_new; r = rn; fd = fn; en_out[k] = en; break; }
+            h_abs *= dp5_factor<double>(en, false, rejected);
+            rejected = true;
+        }
+        t_out[k] = t;
+        for (int c = 0; c < 3; ++c) { y_out[7 * k + f->perm[c]] = r.p[c]; y_out[7 * k + 3 + f->perm[c]] = r.v[c]; }
+        y_out[7 * k + 6] = r.ph;
+        ++k;
+    }
+    return k;
+}
+
+// debug/test helper: RHS evaluated with the float32 code path (state rounded to float32 first)
+extern "C" void hh_rhs_fp32(void* hnd, const double* s, uint64_t n, double* out) {
+    const HostField* f = (const HostField*)hnd;
+    FieldView<float> F = f->view32();
+    for (uint64_t i = 0; i < n; ++i) {
+        float p[3], v[3];
+        for (int k = 0; k < 3; ++k) { p[k] = (float)s[(uint64_t)f->perm[k] * n + i]; v[k] = (float)s[(uint64_t)(3 + f->perm[k]) * n + i]; }
+        Deriv<float> d;
+        deriv<float, false, false>(F, 0.f, p, v, d);
+        for (int k = 0; k < 3; ++k) { out[(uint64_t)f->perm[k] * n + i] = d.dp[k]; out[(uint64_t)(3 + f->perm[k]) * n + i] = d.dv[k]; }
+        out[6 * n + i] = out[7 * n + i] = out[8 * n + i] = 0;
+    }
+}

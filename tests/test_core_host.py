@@ -1,0 +1,218 @@
+"""CPU self-test: the product's per-ray math (csrc/ray_core.h, field_prep.h), compiled for the host by
+tests/host_harness.cpp, against the golden vectors of the real reference.  The -m gpu tests repeat these
+through the C ABI on the device; this file is what can run in a container without a GPU."""
+import numpy as np
+import pytest
+
+from conftest import rel_err
+from harness import Harness
+from oracle import synthpy_oracle as O
+
+C_LIGHT = 299792458.0
+omega_of = lambda lwl: 2 * np.pi * (C_LIGHT / lwl)
+
+
+@pytest.fixture(scope="module")
+def H():
+    return Harness()
+
+
+def test_field_stencil_bit_equal_numpy(H, golden):
+    g = golden("g1_rhs")
+    for march in (0, 1, 2):
+        f = H.field(g["ne"], g["x"], g["y"], g["z"], omega_of(float(g["lwl"])), march_axis=march, phase=True)
+        gx, gy, gz, aux = f.export()
+        assert np.array_equal(gx, g["gradx"]) and np.array_equal(gy, g["grady"]) and np.array_equal(gz, g["gradz"])
+    # uniform-spacing branch of np.gradient: axes whose float32 spacings are all equal
+    x = np.arange(12) * 0.25 - 1.0
+    ne = 1e24 * np.random.default_rng(0).random((12, 12, 12))
+    d = O.Domain(x, x, x, 1.0)
+    d.external_ne(ne)
+    d.calc_dndr(1064e-9)
+    f = H.field(ne, x, x, x, omega_of(1064e-9))
+    gx, gy, gz, _ = f.export()
+    assert np.array_equal(gx, d.grads[0]) and np.array_equal(gy, d.grads[1]) and np.array_equal(gz, d.grads[2])
+
+
+def test_rhs_matches_reference(H, golden):
+    g = golden("g1_rhs")
+    for ph in (False, True):
+        f = H.field(g["ne"], g["x"], g["y"], g["z"], omega_of(float(g["lwl"])), phase=ph, f64=ph)
+        out = f.rhs(g["s"])
+        ref = g["dsdt_phase%d" % ph]
+        assert np.array_equal(out[:3], ref[:3])
+        assert np.array_equal(out[3:6] == 0, ref[3:6] == 0)          # identical in/out-of-bounds decisions
+        assert rel_err(out[3:6], ref[3:6], floor=1e3) < 1e-13
+        if ph:
+            # the reference interpolates n ~ 1 and subtracts 1 afterwards: its own rounding floor is a few
+            # eps * omega in absolute terms (we interpolate n-1, which is more accurate at low density)
+            assert np.all(np.abs(out[7] - ref[7]) <= 1e-15 * f.omega + 1e-12 * np.abs(ref[7]))
+    # float32 aux lane: ~1e-7 relative phase-rate error (documented), still zero outside
+    f = H.field(g["ne"], g["x"], g["y"], g["z"], omega_of(float(g["lwl"])), phase=True, f64=False)
+    out = f.rhs(g["s"])
+    assert np.all(np.abs(out[7] - g["dsdt_phase1"][7]) <= 1e-15 * f.omega + 2e-7 * np.abs(g["dsdt_phase1"][7]))
+
+
+def test_rk4_matches_reference_rhs_loop(H, golden):
+    for name, ph in (("g2_expcos", True), ("g3_turb", False)):
+        g = golden(name)
+        ext, n = float(g["extent"]), int(g["rk4_nsteps"])
+        f = H.field(g["ne"], g["x"], g["y"], g["z"], omega_of(float(g["lwl"])), phase=ph, f64=ph)
+        h = np.sqrt(8.0) * ext / C_LIGHT / n
+        sf, steps = f.rk4(g["s0"][:, :128], n, h)
+        assert (steps == n).all()
+        assert rel_err(sf[:6], g["rk4_sf"][:6], floor=1e-6) < 1e-11
+        rf = f.exit(sf, 2, 0, 1, ext)
+        ref_rf, _ = O.ray_to_jones(g["rk4_sf"], ext)
+        assert rel_err(rf, ref_rf, floor=1e-7) < 1e-9
+        if ph:
+            assert rel_err(sf[7], g["rk4_sf"][7], floor=1e-3) < 1e-11
+        # early exit leaves every ray on the same straight line
+        sfe, st = f.rk4(g["s0"][:, :128], n, h, early=True)
+        assert st.max() < n
+        assert rel_err(f.exit(sfe, 2, 0, 1, ext), ref_rf, floor=1e-7) < 1e-9
+
+
+def test_rk4_other_probing_directions(H, golden):
+    g = golden("g3_turb")
+    ext = float(g["extent"])
+    for pd, (p, a, b) in {"x": (0, 1, 2), "y": (1, 0, 2)}.items():
+        f = H.field(g["ne"], g[pd + "_x"], g[pd + "_y"], g[pd + "_z"], omega_of(float(g["lwl"])), march_axis=p)
+        h = np.sqrt(8.0) * ext / C_LIGHT / 120
+        sf, _ = f.rk4(g[pd + "_s0"], 120, h)
+        assert rel_err(sf[:6], g[pd + "_sf"][:6], floor=1e-6) < 1e-11
+        assert rel_err(f.exit(sf, p, a, b, ext), g[pd + "_rf"], floor=1e-7) < 1e-9
+
+
+def test_rk45_per_ray_matches_solve_ivp(H, golden):
+    g = golden("g2_expcos")
+    ext = float(g["extent"])
+    f = H.field(g["ne"], g["x"], g["y"], g["z"], omega_of(float(g["lwl"])), phase=True, f64=True)
+    t_end = np.sqrt(8.0) * ext / C_LIGHT
+    # (a) SciPy's default tolerances (what the reference ships): identical accept/reject sequences
+    for tag, (rtol, atol) in {"def": (1e-3, 1e-6)}.items():
+        sf, att, nfev = f.rk45(g["s0"][:, :32], t_end, rtol, atol)
+        assert np.array_equal(nfev, g["perray_nfev_" + tag])
+        ref = g["perray_sf_" + tag]
+        # Same algorithm, same step sequence.  Bitwise agreement is not attainable for an ADAPTIVE method: the
+        # controller scales h by err_norm**-0.2 and err_norm is a cancelling sum (5th minus 4th order) whose
+        # rounding noise (order of BLAS summation inside np.dot) reaches 1e-8 relative when err_norm ~ 1e-4,
+        # i.e. h differs by ~4e-9 relative and the (rtol 1e-3) truncation error moves with it.  Hence the bar is
+        # 1e-9 of the natural scales: domain size, c, and the phase magnitude.
+        assert np.max(np.abs(sf[:3] - ref[:3])) < 1e-9 * ext
+        assert np.max(np.abs(sf[3:6] - ref[3:6])) < 1e-9 * C_LIGHT
+        assert np.max(np.abs(sf[7] - ref[7])) < 1e-9 * np.abs(ref[7]).max()
+        rf, rf_ref = f.exit(sf, 2, 0, 1, ext), O.ray_to_jones(ref, ext)[0]
+        assert np.max(np.abs(rf - rf_ref)) < 1e-9
+    # (b) tight tolerances (1e-7 / 1e-9, the reference's "intended" diffrax values).  In the free-flight legs the
+    # true local error is zero, so SciPy's err_norm is pure rounding noise (~1e-5) and its step factor
+    # 0.9 * noise**-0.2 ~ 9.2 is noise too: the reference's own step sequence is not reproducible across BLAS
+    # builds.  Parity there means: same solution to within the requested tolerance, and no worse than SciPy
+    # against a near-converged (rtol 1e-11) solve of the same RHS.
+    sf, att, nfev = f.rk45(g["s0"][:, :32], t_end, 1e-7, 1e-9)
+    ref = g["perray_sf_tight"]
+    assert abs(int(nfev.sum()) - int(g["perray_nfev_tight"].sum())) < 0.05 * g["perray_nfev_tight"].sum()
+    rf, rf_ref = f.exit(sf, 2, 0, 1, ext), O.ray_to_jones(ref, ext)[0]
+    assert np.max(np.abs(rf[[0, 2]] - rf_ref[[0, 2]])) < 1e-7 * ext
+    assert np.max(np.abs(rf[[1, 3]] - rf_ref[[1, 3]])) < 5e-7
+    rf_conv = O.ray_to_jones(g["perray_sf_conv"], ext)[0]
+    err_ours = np.abs(rf[:, :8] - rf_conv).max(axis=1)
+    err_scipy = np.abs(rf_ref[:, :8] - rf_conv).max(axis=1)
+    assert np.all(err_ours <= 2 * err_scipy + 1e-12)
+
+
+def test_fp32_mode_within_1e4(H, golden):
+    """FP32 state/arithmetic (the JAX generation's default precision) against the FP64 oracle.  The golden rays
+    start at z = -extent, which is OUTSIDE the float32-rounded z[0] in float64 but ON it once rounded to
+    float32 -- a knife-edge the two precisions legitimately resolve differently -- so the rays are first moved
+    back along their (straight) path by a fraction of a cell."""
+    g = golden("g3_turb")
+    ext, n = float(g["extent"]), int(g["rk4_nsteps"])
+    s0 = g["s0"][:, :128].copy()
+    s0[:3] -= s0[3:6] * (2e-4 / C_LIGHT)
+    d = O.Domain(g["x"], g["y"], g["z"], ext)
+    d.external_ne(g["ne"])
+    d.calc_dndr(float(g["lwl"]))
+    h = np.sqrt(8.0) * ext / C_LIGHT / n
+    ref_rf, _ = O.ray_to_jones(d.solve_rk4(s0, n, h)[0], ext)
+    f = H.field(g["ne"], g["x"], g["y"], g["z"], omega_of(float(g["lwl"])))
+    sf, _ = f.rk4(s0, n, h, fp32=True)
+    rf = f.exit(sf, 2, 0, 1, ext)
+    assert np.max(np.abs(rf[[0, 2]] - ref_rf[[0, 2]])) < 1e-4 * np.abs(ref_rf[[0, 2]]).max()
+    assert np.max(np.abs(rf[[1, 3]] - ref_rf[[1, 3]])) < 1e-4 * np.abs(ref_rf[[1, 3]]).max()
+
+
+def test_optics_elements_and_chains(H, golden):
+    g = golden("g4_optics")
+    rmm = O.m_to_mm(g["r0"][:, 1000:2000])
+    for key, op in [("el_distance", ("travel", 123.0)), ("el_lens", ("lens", 200.0, 133.0)),
+                    ("el_circ_ap", ("circ_ap", 4.0)), ("el_circ_stop", ("circ_stop", 4.0)),
+                    ("el_rect_ap", ("rect_ap", 3.0, 2.0)), ("el_knife_y", ("knife", 0.5, 2, 1)),
+                    ("el_knife_x", ("knife", -0.5, 0, -1))]:
+        out = H.optics(rmm, [op], input_mm=True)
+        assert rel_err(out, g[key], floor=1e-9) < 1e-12, key      # np.matmul (BLAS) fuses multiply-adds
+    for tag in ("shadow_single", "shadow_two", "schlieren_DF", "schlieren_LF", "refracto_incoherent"):
+        out = H.optics(g["r0"], O.chain(tag))
+        assert rel_err(out, g[tag + "_rf"], floor=1e-3) < 1e-11, tag      # imaging chains cancel: abs 1e-14 mm
+    lwl = 1064e-9
+    for tag, key in (("interf_two", "interf"), ("refracto_coherent", "refr_coh")):
+        r, E = H.optics(g["coh_r0"], O.chain(tag), jf=g["coh_E"], wavelength=lwl)
+        assert rel_err(r, g[key + "_rf"], floor=1e-3) < 1e-11
+        assert np.array_equal(np.isnan(E.real), np.isnan(g[key + "_rE"].real))
+        m = ~np.isnan(E.real)
+        assert np.max(np.abs(E[m] - g[key + "_rE"][m])) < 1e-6            # k*r ~ 1e8 rad: 1 ulp of the argument ~ 1e-8
+
+
+def test_bin_search_matches_numpy(H):
+    rng = np.random.default_rng(3)
+    for lo, hi, nb in [(-9.0, 9.0, 3448), (-6.75, 6.75, 2574), (-9.0, 9.0, 137), (-7.0, 6.0, 63)]:
+        edges = np.linspace(lo, hi, nb + 1)
+        v = np.concatenate([rng.uniform(lo - 1, hi + 1, 20000), edges, np.nextafter(edges, -np.inf),
+                            np.nextafter(edges, np.inf), [np.nan, np.inf, -np.inf]])
+        # histogram2d semantics
+        want = np.searchsorted(edges, v, side="right") - 1
+        want[v == edges[-1]] = nb - 1
+        want[(want < 0) | (want > nb - 1) | np.isnan(v)] = -1
+        assert np.array_equal(H.bins(v, lo, hi, nb, True), want)
+        # digitize - 1 semantics
+        want = np.digitize(v, edges) - 1
+        want[(want < 0) | (want > nb - 1)] = -1
+        assert np.array_equal(H.bins(v, lo, hi, nb, False), want)
+
+
+def test_histogram_via_bins_equals_reference(H, golden):
+    g = golden("g4_optics")
+    for tag in ("shadow_single", "schlieren_DF", "refracto_incoherent"):
+        r = H.optics(g["r0"], O.chain(tag))
+        for bs in (25, 8):
+            nx, ny = 3448 // bs, 2574 // bs
+            ix, iy = H.bins(r[0], -9.0, 9.0, nx, True), H.bins(r[2], -6.75, 6.75, ny, True)
+            ok = (ix >= 0) & (iy >= 0)
+            Hh = np.zeros((ny, nx))
+            np.add.at(Hh, (iy[ok], ix[ok]), 1.0)
+            assert np.array_equal(Hh, g[f"{tag}_H{bs}"]), (tag, bs)
+
+
+def test_philox_known_answer_and_beam_statistics(H):
+    # Random123 known-answer vectors for philox4x32-10
+    assert list(H.philox((0, 0), (0, 0, 0, 0))) == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    assert list(H.philox((0xffffffff, 0xffffffff), (0xffffffff,) * 4)) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
+    assert list(H.philox((0xa4093822, 0x299f31d0), (0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344))) == \
+        [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
+    n, R, div, ext = 200000, 4e-3, 5e-5, 10e-3
+    for bt in (0, 1):                                    # fold(U+U) and power(2) radial laws
+        s0 = H.beam(bt, 2, R, R, div, -ext, 7, 0, n)
+        r = np.hypot(s0[0], s0[1]) / R
+        assert r.max() <= 1.0 and np.all(s0[2] == -ext)
+        # both laws have pdf 2r on [0,1] (uniform over the disc): mean 2/3, E[r^2] = 1/2
+        assert abs(r.mean() - 2 / 3) < 3e-3 and abs((r ** 2).mean() - 0.5) < 3e-3
+        ang = np.arctan2(s0[1], s0[0])
+        assert abs(np.cos(ang).mean()) < 5e-3 and abs(np.sin(2 * ang).mean()) < 5e-3
+        v = s0[3:6]
+        assert np.allclose(np.linalg.norm(v, axis=0), C_LIGHT, rtol=1e-12)
+        chi_abs = np.arcsin(np.hypot(v[0], v[1]) / C_LIGHT)          # |chi|, chi ~ divergence * N(0,1)
+        assert abs(np.sqrt((chi_abs ** 2).mean()) / div - 1.0) < 0.01
+    # partition invariance: ray i depends on (seed, i) only
+    a = H.beam(1, 2, R, R, div, -ext, 7, 1000, 50)
+    b = H.beam(1, 2, R, R, div, -ext, 7, 0, 1050)[:, 1000:]
+    assert np.array_equal(a, b)
