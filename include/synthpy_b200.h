@@ -218,6 +218,10 @@ int sp_propagate(const sp_field* field, const sp_params* params, sp_workspace* w
                  double* jf_dev, uint32_t* steps_dev, const sp_channel* channels_host, int n_channels,
                  sp_stats* stats_dev, void* stream);
 
+/* Device time of the k_propagate launches issued through `ws` since the last call (CUDA events recorded
+ * around each launch on its stream; this call waits for the last one).  bench.py's roofline figure. */
+int sp_workspace_propagate_ms(sp_workspace* ws, double* total_ms, int* n_launches);
+
 /* Right-hand side only: d(state)/dt for arbitrary states (parity level L0; full_solver.py:516-544). */
 int sp_rhs(const sp_field* field, const sp_params* params, const double* s_dev, uint64_t n, double* dsdt_dev,
            void* stream);

@@ -784,7 +784,34 @@ struct sp_workspace {
     double* joint = nullptr; size_t joint_cap = 0;
     double* host_pair = nullptr;     // pinned, 2 doubles
     int sm_count = 0;
+    std::vector<cudaEvent_t> ev;     // start/stop pairs around k_propagate launches
+    size_t ev_used = 0;
 };
+
+static int ws_event(sp_workspace* w, cudaStream_t st) {
+    if (w->ev_used == w->ev.size()) {
+        if (w->ev.size() >= 512) return SP_OK;          // stop recording, keep running
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        w->ev.push_back(e);
+    }
+    CU(cudaEventRecord(w->ev[w->ev_used++], st));
+    return SP_OK;
+}
+
+extern "C" int sp_workspace_propagate_ms(sp_workspace* w, double* total_ms, int* n_launches) {
+    if (!w || !total_ms || !n_launches) return fail(SP_EINVAL, "null argument");
+    double tot = 0.0; int n = 0;
+    for (size_t i = 0; i + 1 < w->ev_used; i += 2) {
+        CU(cudaEventSynchronize(w->ev[i + 1]));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, w->ev[i], w->ev[i + 1]));
+        tot += ms; ++n;
+    }
+    w->ev_used = 0;
+    *total_ms = tot; *n_launches = n;
+    return SP_OK;
+}
 
 extern "C" int sp_workspace_create(sp_workspace** out) {
     if (!out) return fail(SP_EINVAL, "null argument");
@@ -801,6 +828,7 @@ extern "C" int sp_workspace_destroy(sp_workspace* w) {
     if (!w) return SP_OK;
     cudaFree(w->keys); cudaFree(w->order); cudaFree(w->hist); cudaFree(w->cursor); cudaFree(w->joint);
     cudaFreeHost(w->host_pair);
+    for (cudaEvent_t e : w->ev) cudaEventDestroy(e);
     delete w;
     return SP_OK;
 }
@@ -938,6 +966,8 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
         A.method = P->method; A.flags = P->flags; A.n_steps = P->n_steps; A.n_state = P->n_state > 0 ? P->n_state : 9; \
         A.h = (T)P->h; A.t_end = (T)P->t_end; A.rtol = (T)P->rtol; A.atol = (T)P->atol; A.omega = (T)P->omega; \
         A.extent = (T)P->extent; A.stats = stats_dev;
+        rc = ws_event(ws, st);
+        if (rc) return rc;
         if (fp32) {
             FILL(float)
             rc = (P->method == SP_METHOD_RK4) ? launch_propagate<float, SP_METHOD_RK4>(A, E, g, st)
@@ -948,6 +978,8 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
                                               : launch_propagate<double, SP_METHOD_RK45>(A, E, g, st);
         }
 #undef FILL
+        if (rc) return rc;
+        rc = ws_event(ws, st);
         if (rc) return rc;
     }
     return SP_OK;

@@ -120,6 +120,13 @@ def workspace():
     return _workspaces[dev]
 
 
+def propagate_kernel_ms():
+    """(total ms, launches) of the k_propagate launches since the last call -- CUDA events on the launch stream."""
+    ms, n = C.c_double(), C.c_int()
+    L.check(L.lib.sp_workspace_propagate_ms(workspace(), C.byref(ms), C.byref(n)))
+    return ms.value, n.value
+
+
 def make_params(method="rk4", *, probing_direction="z", extent, omega, n_steps=0, h=0.0, t_end=None, rtol=1e-3,
                 atol=1e-6, phase=False, phase_f64=False, early_exit=True, fp32=False, sort=True, n_state=9,
                 out_axes=None):
@@ -201,7 +208,7 @@ def _null_image():
 
 
 def make_channel(ops, image=None, wavelength=0.0, input_mm=False):
-    """ops: list of tuples in the oracle's vocabulary, e.g. [("travel", 300.0), ("circ_ap", 25), ...].
+    """ops: list of (kind, params...) tuples, e.g. [("travel", 300.0), ("circ_ap", 25), ...].
     Returns (Channel struct, keepalive)."""
     arr = (L.OpticOp * max(1, len(ops)))()
     for i, op in enumerate(ops):

@@ -1,5 +1,5 @@
 """Legacy-shaped aliases (``src/solvers-legacy/full_solver.py`` + ``rtm_solver.py`` call shapes) over the same
-CUDA path.  The parity tests use these so that they read like the oracle's own calls:
+CUDA path.  The parity tests use these so that they read like the reference's own calls:
 
     dom = legacy.ScalarDomain(x, y, z, extent); dom.external_ne(ne); dom.calc_dndr(lwl)
     rf = dom.solve(s0)                        # the reference as shipped: joint RK45

@@ -1,0 +1,282 @@
+"""GPU parity tests: CUDA path (through the Python boundary -> C ABI) against the oracle / golden vectors.
+
+Tolerances (north_star): exit rays 1e-9 relative (FP64), 1e-4 (FP32 mode); histograms exact in total counts,
+<= 1e-3 L1 per image.  Bit-exact: float32 gradient stencil, bin indices."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+from oracle import synthpy_oracle as O
+
+pytestmark = pytest.mark.gpu
+C_LIGHT = 299792458.0
+
+
+@pytest.fixture(scope="module")
+def sp():
+    assert torch.cuda.is_available(), "run with -m gpu on a CUDA box"
+    import synthpy_b200
+    from synthpy_b200 import legacy
+    return legacy
+
+
+def _legacy_dom(sp, g, phaseshift=False, pd="z", pre=""):
+    d = sp.ScalarDomain(g[pre + "x"], g[pre + "y"], g[pre + "z"], float(g["extent"]), phaseshift=phaseshift,
+                        probing_direction=pd)
+    d.external_ne(g["ne"])
+    d.calc_dndr(float(g["lwl"]))
+    return d
+
+
+def test_field_stencil_bit_equal(sp, golden):
+    g = golden("g1_rhs")
+    for pd in ("x", "y", "z"):
+        d = _legacy_dom(sp, g, phaseshift=True, pd=pd)
+        gx, gy, gz, aux = [t.cpu().numpy() for t in d.field.export_gradients()]
+        assert np.array_equal(gx, g["gradx"]) and np.array_equal(gy, g["grady"]) and np.array_equal(gz, g["gradz"])
+    # float32 ne input and the uniform branch of np.gradient
+    x = np.arange(12) * 0.25 - 1.0
+    ne = (1e24 * np.random.default_rng(0).random((12, 12, 12)))
+    for dt in (np.float64, np.float32):
+        o = O.Domain(x, x, x, 1.0)
+        o.external_ne(ne.astype(dt))
+        o.calc_dndr(1064e-9)
+        d = sp.ScalarDomain(x, x, x, 1.0)
+        d.external_ne(ne.astype(dt))
+        d.calc_dndr(1064e-9)
+        got = [t.cpu().numpy() for t in d.field.export_gradients()[:3]]
+        for a in range(3):
+            assert np.array_equal(got[a], o.grads[a]), (dt, a)
+
+
+def test_rhs_L0(sp, golden):
+    g = golden("g1_rhs")
+    for ph in (False, True):
+        d = _legacy_dom(sp, g, phaseshift=ph)
+        out = d.dsdt(g["s"])
+        ref = g["dsdt_phase%d" % ph]
+        assert np.array_equal(out[:3], ref[:3])
+        assert np.array_equal(out[3:6] == 0, ref[3:6] == 0)
+        assert rel_err(out[3:6], ref[3:6], floor=1e3) < 1e-12
+        if ph:
+            assert np.all(np.abs(out[7] - ref[7]) <= 1e-15 * d.omega + 1e-12 * np.abs(ref[7]))
+
+
+def test_rk4_L1(sp, golden):
+    for name, ph in (("g2_expcos", True), ("g3_turb", False)):
+        g = golden(name)
+        ext, n = float(g["extent"]), int(g["rk4_nsteps"])
+        d = _legacy_dom(sp, g, phaseshift=ph)
+        h = np.sqrt(8.0) * ext / C_LIGHT / n
+        ref_rf, ref_J = O.ray_to_jones(g["rk4_sf"], ext)
+        for sort in (True, False):
+            rf, Jf = d.solve(g["s0"][:, :128], return_E=True, method="rk4", n_steps=n, h=h, sort=sort)
+            assert (d.steps == n).all() and d.stats["ray_steps"] == 128 * n
+            assert rel_err(d.sf[:6], g["rk4_sf"][:6], floor=1e-6) < 1e-10
+            assert rel_err(rf, ref_rf, floor=1e-7) < 1e-9
+            if ph:
+                assert rel_err(d.sf[7], g["rk4_sf"][7], floor=1e-3) < 1e-10
+                assert np.max(np.abs(Jf - ref_J)) < 1e-9
+        rf = d.solve(g["s0"][:, :128], method="rk4", n_steps=n, h=h, early_exit=True)
+        assert d.steps.max() < n and rel_err(rf, ref_rf, floor=1e-7) < 1e-9
+
+
+def test_rk4_probing_directions(sp, golden):
+    g = golden("g3_turb")
+    ext = float(g["extent"])
+    for pd in ("x", "y"):
+        d = _legacy_dom(sp, g, pd=pd, pre=pd + "_")
+        rf = d.solve(g[pd + "_s0"], method="rk4", n_steps=120, h=np.sqrt(8.0) * ext / C_LIGHT / 120)
+        assert rel_err(d.sf[:6], g[pd + "_sf"][:6], floor=1e-6) < 1e-10
+        assert rel_err(rf, g[pd + "_rf"], floor=1e-7) < 1e-9
+
+
+def test_rk45_joint_is_the_shipped_solver(sp, golden):
+    """legacy.ScalarDomain.solve(s0) == full_solver.ScalarDomain.solve(s0) (one step size for all rays)."""
+    for name, ph in (("g2_expcos", True), ("g3_turb", False)):
+        g = golden(name)
+        ext = float(g["extent"])
+        d = _legacy_dom(sp, g, phaseshift=ph)
+        rf = d.solve(g["s0"])
+        assert np.max(np.abs(d.sf[:3] - g["sf"][:3])) < 1e-9 * ext
+        assert np.max(np.abs(d.sf[3:6] - g["sf"][3:6])) < 1e-9 * C_LIGHT
+        assert np.max(np.abs(rf - g["rf"])) < 1e-9
+        if ph:
+            assert np.max(np.abs(d.sf[7] - g["sf"][7])) < 1e-9 * np.abs(g["sf"][7]).max()
+
+
+def test_rk45_per_ray(sp, golden):
+    g = golden("g2_expcos")
+    ext = float(g["extent"])
+    d = _legacy_dom(sp, g, phaseshift=True)
+    rf = d.solve(g["s0"][:, :32], method="rk45")
+    ref = g["perray_sf_def"]
+    assert np.array_equal(6 * d.steps.astype(np.int64) + 2, g["perray_nfev_def"])    # same accept/reject sequence
+    assert np.max(np.abs(d.sf[:3] - ref[:3])) < 1e-9 * ext
+    assert np.max(np.abs(d.sf[3:6] - ref[3:6])) < 1e-9 * C_LIGHT
+    assert np.max(np.abs(rf - O.ray_to_jones(ref, ext)[0])) < 1e-9
+    # tight tolerances: tolerance-level agreement (see tests/test_core_host.py for why not bitwise)
+    rf = d.solve(g["s0"][:, :32], method="rk45", rtol=1e-7, atol=1e-9)
+    rf_ref = O.ray_to_jones(g["perray_sf_tight"], ext)[0]
+    assert np.max(np.abs(rf[[0, 2]] - rf_ref[[0, 2]])) < 1e-7 * ext and np.max(np.abs(rf[[1, 3]] - rf_ref[[1, 3]])) < 5e-7
+    rf_conv = O.ray_to_jones(g["perray_sf_conv"], ext)[0]
+    assert np.all(np.abs(rf[:, :8] - rf_conv).max(axis=1) <= 2 * np.abs(rf_ref[:, :8] - rf_conv).max(axis=1) + 1e-12)
+
+
+def test_fp32_mode(sp, golden):
+    g = golden("g3_turb")
+    ext, n = float(g["extent"]), int(g["rk4_nsteps"])
+    s0 = g["s0"][:, :128].copy()
+    s0[:3] -= s0[3:6] * (2e-4 / C_LIGHT)              # off the float32 knife-edge at z = -extent (see CPU test)
+    o = O.Domain(g["x"], g["y"], g["z"], ext)
+    o.external_ne(g["ne"])
+    o.calc_dndr(float(g["lwl"]))
+    h = np.sqrt(8.0) * ext / C_LIGHT / n
+    ref_rf, _ = O.ray_to_jones(o.solve_rk4(s0, n, h)[0], ext)
+    d = _legacy_dom(sp, g)
+    rf = d.solve(s0, method="rk4", n_steps=n, h=h, fp32=True)
+    assert np.max(np.abs(rf[[0, 2]] - ref_rf[[0, 2]])) < 1e-4 * np.abs(ref_rf[[0, 2]]).max()
+    assert np.max(np.abs(rf[[1, 3]] - ref_rf[[1, 3]])) < 1e-4 * np.abs(ref_rf[[1, 3]]).max()
+
+
+def test_docstring_kats(sp, golden):
+    g = golden("g5_kat")
+    a, ext = g["axis"], float(g["extent"])
+    for name in ("null", "slab"):
+        d = sp.ScalarDomain(a, a, a, ext)
+        d.test_null() if name == "null" else d.test_slab(s=10, n_e0=1e25)
+        d.calc_dndr()
+        rf = d.solve(g[name + "_s0"])
+        assert np.max(np.abs(rf - g[name + "_rf"])) < 1e-9
+        if name == "null":                       # NULL test: exactly no deflection
+            s0 = g["null_s0"]
+            assert np.array_equal(rf[1], np.arctan(s0[3] / s0[5])) and np.array_equal(rf[3], np.arctan(s0[4] / s0[5]))
+
+
+def test_optics_and_histograms(sp, golden):
+    g = golden("g4_optics")
+    cases = [("shadow_single", sp.Shadowgraphy, "single_lens_solve", {}), ("shadow_two", sp.Shadowgraphy, "two_lens_solve", {}),
+             ("schlieren_DF", sp.Schlieren, "DF_solve", {"R": 1}), ("schlieren_LF", sp.Schlieren, "LF_solve", {"R": 1}),
+             ("refracto_incoherent", sp.Refractometry, "incoherent_solve", {})]
+    for tag, cls, meth, kw in cases:
+        o = cls(g["r0"].copy(), L=400, R=25)
+        getattr(o, meth)(**kw)
+        assert rel_err(o.rf, g[tag + "_rf"], floor=1e-3) < 1e-11, tag
+        for bs in (25, 8):
+            o.histogram(bin_scale=bs)
+            ref = g[f"{tag}_H{bs}"]
+            assert o.H.shape == ref.shape and o.H.sum() == ref.sum()           # total counts exact
+            assert np.abs(o.H - ref).sum() <= 1e-3 * ref.sum()                 # L1 per image
+            assert np.array_equal(o.H, ref)                                    # in fact identical here
+
+
+def test_element_functions(sp, golden):
+    from synthpy_b200 import diagnostics as D
+    g = golden("g4_optics")
+    rmm = O.m_to_mm(g["r0"][:, 1000:2000])
+    assert rel_err(D.travel(rmm, 123.0), g["el_distance"], floor=1e-9) < 1e-12
+    assert rel_err(D.lens(rmm, 200.0, 133.0), g["el_lens"], floor=1e-9) < 1e-12
+    assert np.array_equal(D.circular_aperture(rmm, 4.0), g["el_circ_ap"], equal_nan=True)
+    assert np.array_equal(D.circular_stop(rmm, 4.0), g["el_circ_stop"], equal_nan=True)
+    assert np.array_equal(D.rect_aperture(rmm, 3.0, 2.0), g["el_rect_ap"], equal_nan=True)
+    assert np.array_equal(D.knife_edge(rmm, 0.5, "y", 1), g["el_knife_y"], equal_nan=True)
+    assert np.array_equal(D.knife_edge(rmm, -0.5, "x", -1), g["el_knife_x"], equal_nan=True)
+    assert np.array_equal(D.m_to_mm(g["r0"]), O.m_to_mm(g["r0"]))
+
+
+def test_coherent_chains_and_interferogram(sp, golden):
+    g = golden("g4_optics")
+    it = sp.Interferometry(g["coh_r0"].copy(), E=g["coh_E"].copy(), L=400, R=25)
+    it.two_lens_solve(wl=1064e-9)
+    assert rel_err(it.rf, g["interf_rf"], floor=1e-3) < 1e-11
+    m = ~np.isnan(g["interf_rE"].real)
+    assert np.array_equal(~np.isnan(it.rE.real), m) and np.max(np.abs(it.rE[m] - g["interf_rE"][m])) < 1e-6
+    it.interferogram(bin_scale=40)
+    ref = g["interf_H40"]
+    assert it.H.shape == ref.shape
+    assert np.abs(it.H - ref).sum() <= 1e-3 * ref.sum() and np.max(np.abs(it.H - ref)) < 1e-5
+    rc = sp.Refractometry(g["coh_r0"].copy(), E=g["coh_E"].copy(), L=400, R=25)
+    rc.coherent_solve(wl=1064e-9)
+    assert rel_err(rc.rf, g["refr_coh_rf"], floor=1e-3) < 1e-11
+    m = ~np.isnan(g["refr_coh_rE"].real)
+    assert np.max(np.abs(rc.rE[m] - g["refr_coh_rE"][m])) < 1e-6
+
+
+def test_fused_path_equals_two_stage(sp, golden):
+    """solve_and_image (optics + binning in the propagation kernel's epilogue) == solve -> Diagnostic -> histogram,
+    and == the oracle end to end, on the current-API classes."""
+    from synthpy_b200 import beam as B, diagnostics as D, domain as Dm, propagator as P
+    g = golden("g2_expcos")
+    lwl, ext = float(g["lwl"]), float(g["extent"])
+    dom = Dm.ScalarDomain([10e-3, 10e-3, 20e-3], [40, 36, 48], phaseshift=True)
+    dom.external_ne(g["ne"])
+    assert np.array_equal(dom.x, np.float32(g["x"])) and np.array_equal(dom.z, np.float32(g["z"]))
+    np.random.seed(5)
+    s0 = sp.init_beam(20000, 4e-3, 2e-3, ext, "circular", "z")       # large divergence: many rays hit the apertures
+    rf, Jf, dt, extra = P.solve(s0, dom, ext, lwl=lwl, return_E=True, method="rk4", n_steps=96, early_exit=False,
+                                return_stats=True)
+    # oracle end to end
+    o = O.Domain(g["x"], g["y"], g["z"], ext, phaseshift=True)
+    o.external_ne(g["ne"])
+    o.calc_dndr(lwl)
+    sf_o, _ = o.solve_rk4(s0, 96)
+    rf_o, J_o = O.ray_to_jones(sf_o, ext)
+    assert rel_err(rf, rf_o, floor=1e-7) < 1e-9
+    specs = [D.spec("shadow_single", bin_scale=20), D.spec("schlieren_DF", bin_scale=20, R_stop=0.5),
+             D.spec("interf_two", bin_scale=40, interferogram=True, wavelength=lwl)]
+    stats, _ = P.solve_and_image(dom, s0, ext, specs, lwl=lwl, method="rk4", n_steps=96, early_exit=False)
+    for sp_, tag in zip(specs[:2], ("shadow_single", "schlieren_DF")):
+        ref = O.histogram(O.run_chain(rf_o, O.chain(tag, R_stop=0.5)), bin_scale=20)
+        H = sp_.image.result().cpu().numpy()
+        assert H.sum() == ref.sum() and np.abs(H - ref).sum() <= 1e-3 * ref.sum()
+    r_o, E_o = O.run_chain(rf_o, O.chain("interf_two"), E=J_o, wl=lwl)
+    ref = O.interferogram(r_o, E_o, bin_scale=40)
+    H = specs[2].image.result().cpu().numpy()
+    assert np.abs(H - ref).sum() <= 1e-3 * ref.sum()
+    assert stats["ray_steps"] == 20000 * 96
+    # two-stage API on the same rays gives the same shadowgraph
+    sh = D.Shadowgraphy(lwl, rf)
+    sh.single_lens_solve()
+    sh.histogram(bin_scale=20)
+    assert np.array_equal(sh.H, specs[0].image.result().cpu().numpy())
+
+
+def test_device_beam_partition_invariance_and_statistics(sp):
+    from synthpy_b200 import beam as B, engine
+    b = B.Beam(100000, 4e-3, 5e-5, 10e-3, device=True, seed=11)
+    full = b.materialise().cpu().numpy()
+    part = b.materialise(n=1000, ray_offset=5000).cpu().numpy()
+    assert np.array_equal(part, full[:, 5000:6000])
+    r = np.hypot(full[0], full[1]) / 4e-3
+    assert r.max() <= 1 and abs(r.mean() - 2 / 3) < 5e-3 and np.all(full[2] == -10e-3)
+    assert np.allclose(np.linalg.norm(full[3:6], axis=0), C_LIGHT, rtol=1e-12)
+
+
+def test_edge_cases(sp, golden):
+    from synthpy_b200 import engine
+    g = golden("g3_turb")
+    d = _legacy_dom(sp, g)
+    ext = float(g["extent"])
+    # empty bundle
+    out = engine.propagate(d.field, d.params("rk4", n_steps=10, h=1e-12), s0=torch.empty((9, 0), dtype=torch.float64, device="cuda"))
+    assert out["rf"].shape == (4, 0)
+    # ragged sizes (not a multiple of the warp / bundle size), NaN rays, rays that never enter the grid
+    for n in (1, 31, 33, 65, 127):
+        s0 = g["s0"][:, :n].copy()
+        rf = d.solve(s0, method="rk4", n_steps=50, h=np.sqrt(8.0) * ext / C_LIGHT / 50)
+        sf_o, _ = O.Domain.solve_rk4(_odom(g), s0, 50)
+        assert rel_err(rf, O.ray_to_jones(sf_o, ext)[0], floor=1e-7) < 1e-9
+    s0 = g["s0"][:, :40].copy()
+    s0[0, 3] = np.nan
+    s0[0, 7] = 1.0                                           # far outside in x: straight line
+    rf = d.solve(s0, method="rk4", n_steps=50, h=np.sqrt(8.0) * ext / C_LIGHT / 50)
+    assert np.isnan(rf[0, 3]) and not np.isnan(np.delete(rf, 3, axis=1)).any()
+    assert rf[1, 7] == np.arctan(s0[3, 7] / s0[5, 7])
+
+
+def _odom(g):
+    o = O.Domain(g["x"], g["y"], g["z"], float(g["extent"]))
+    o.external_ne(g["ne"])
+    o.calc_dndr(float(g["lwl"]))
+    return o
