@@ -222,6 +222,10 @@ int sp_propagate(const sp_field* field, const sp_params* params, sp_workspace* w
  * around each launch on its stream; this call waits for the last one).  bench.py's roofline figure. */
 int sp_workspace_propagate_ms(sp_workspace* ws, double* total_ms, int* n_launches);
 
+/* (h, error_norm) of every attempted step of the last SP_METHOD_RK45_JOINT solve issued through `ws`
+ * (the counterpart of instrumenting scipy's RK45._estimate_error_norm).  Copies min(cap, n) entries. */
+int sp_workspace_joint_log(const sp_workspace* ws, double* h_out, double* en_out, int cap, int* n_out);
+
 /* Right-hand side only: d(state)/dt for arbitrary states (parity level L0; full_solver.py:516-544). */
 int sp_rhs(const sp_field* field, const sp_params* params, const double* s_dev, uint64_t n, double* dsdt_dev,
            void* stream);

@@ -42,6 +42,21 @@ def quiet(fn, *a, **k):
         return fn(*a, **k)
 
 
+def joint_log(fs, dom, s0):
+    """(h, error_norm) of every attempted step of the shipped joint solve (instrumented scipy RK45)."""
+    from scipy.integrate import RK45
+    s = RK45(lambda t, y: fs.dsdt(t, y, dom), 0.0, s0.ravel().copy(), np.sqrt(8.0) * dom.extent / fs.c)
+    orig, log = s._estimate_error_norm, []
+    def est(K, h, scale):
+        e = orig(K, h, scale)
+        log.append((h, e))
+        return e
+    s._estimate_error_norm = est
+    while s.status == "running":
+        s.step()
+    return np.array(log).T
+
+
 def axes(lengths, dims):
     return [np.linspace(-L / 2, L / 2, n) for L, n in zip(lengths, dims)]
 
@@ -103,7 +118,8 @@ def main():
     np.random.seed(0)
     s0 = fs.init_beam(384, 4e-3, 5e-5, extent, "circular", "z")
     rf, Jf = quiet(dom.solve, s0.copy(), return_E=True)
-    g2 = dict(x=x, y=y, z=z, extent=extent, lwl=lwl, ne=dom.ne, s0=s0, sf=dom.sf, rf=rf, Jf=Jf)
+    g2 = dict(x=x, y=y, z=z, extent=extent, lwl=lwl, ne=dom.ne, s0=s0, sf=dom.sf, rf=rf, Jf=Jf,
+              joint_log=joint_log(fs, dom, s0))
 
     # per-ray adaptive (== ScalarDomain.solve with Np=1 per ray), default and tight tolerances
     from scipy.integrate import solve_ivp
@@ -147,7 +163,7 @@ def main():
     np.random.seed(2)
     s0 = fs.init_beam(256, 4.5e-3, 5e-5, extent, "circular", "z")
     rf = quiet(dom.solve, s0.copy())
-    g3d = dict(x=x, y=y, z=z, extent=extent, lwl=lwl, ne=ne, s0=s0, sf=dom.sf, rf=rf,
+    g3d = dict(x=x, y=y, z=z, extent=extent, lwl=lwl, ne=ne, s0=s0, sf=dom.sf, rf=rf, joint_log=joint_log(fs, dom, s0),
                rk4_nsteps=200, rk4_sf=rk4(dom, s0[:, :128], 200))
     # other probing directions (legacy conventions, full_solver.py:574-610,856-881)
     for pd in ("x", "y"):

@@ -72,6 +72,7 @@ EXPORTS = {
     "sp_image_finalize": (C.c_int, [C.POINTER(Image), C.c_void_p, C.c_void_p]),
     "sp_workspace_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "sp_workspace_destroy": (C.c_int, [C.c_void_p]),
+    "sp_workspace_joint_log": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]),
     "sp_workspace_propagate_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "sp_propagate": (C.c_int, [C.c_void_p, C.POINTER(Params), C.c_void_p, C.c_void_p, C.POINTER(Beam), C.c_uint64,
                                C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(Channel),

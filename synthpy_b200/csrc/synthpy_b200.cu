@@ -786,7 +786,16 @@ struct sp_workspace {
     int sm_count = 0;
     std::vector<cudaEvent_t> ev;     // start/stop pairs around k_propagate launches
     size_t ev_used = 0;
+    std::vector<double> jlog_h, jlog_en;   // attempts of the last joint solve
 };
+
+extern "C" int sp_workspace_joint_log(const sp_workspace* w, double* h_out, double* en_out, int cap, int* n_out) {
+    if (!w || !n_out) return fail(SP_EINVAL, "null argument");
+    const int n = (int)w->jlog_h.size();
+    for (int i = 0; i < n && i < cap; ++i) { if (h_out) h_out[i] = w->jlog_h[i]; if (en_out) en_out[i] = w->jlog_en[i]; }
+    *n_out = n;
+    return SP_OK;
+}
 
 static int ws_event(sp_workspace* w, cudaStream_t st) {
     if (w->ev_used == w->ev.size()) {
@@ -1048,6 +1057,7 @@ static int joint_solve(const sp_field* field, const sp_params* P, sp_workspace* 
 
     double t = 0.0;
     uint64_t attempts = 0, accepted = 0;
+    ws->jlog_h.clear(); ws->jlog_en.clear();
     const uint64_t cap = P->n_steps > 0 ? (uint64_t)P->n_steps : (1ull << 30);
     bool failed = false;
     while (t < t_end && !failed) {
@@ -1069,6 +1079,7 @@ static int joint_solve(const sp_field* field, const sp_params* P, sp_workspace* 
             CU(cudaStreamSynchronize(st));
             ++attempts; evals += 6 * n;
             const double en = sqrt(ws->host_pair[0]) / sqrt(size);
+            ws->jlog_h.push_back(h); ws->jlog_en.push_back(en);
             if (en < 1) {
                 double f = (en == 0) ? DP::MAX_FACTOR : fmin(DP::MAX_FACTOR, DP::SAFETY * pow(en, -0.2));
                 if (rejected) f = fmin(1.0, f);

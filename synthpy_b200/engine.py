@@ -127,6 +127,15 @@ def propagate_kernel_ms():
     return ms.value, n.value
 
 
+def joint_log():
+    """(h, error_norm) arrays of every attempted step of the last 'rk45_joint' solve."""
+    n = C.c_int()
+    L.check(L.lib.sp_workspace_joint_log(workspace(), None, None, 0, C.byref(n)))
+    h, en = np.empty(n.value), np.empty(n.value)
+    L.check(L.lib.sp_workspace_joint_log(workspace(), h.ctypes.data, en.ctypes.data, n.value, C.byref(n)))
+    return h, en
+
+
 def make_params(method="rk4", *, probing_direction="z", extent, omega, n_steps=0, h=0.0, t_end=None, rtol=1e-3,
                 atol=1e-6, phase=False, phase_f64=False, early_exit=True, fp32=False, sort=True, n_state=9,
                 out_axes=None):
