@@ -131,68 +131,100 @@ template <typename T> struct FieldView {
     int sv;               // element stride of v  (= nw)
 };
 
-// Cell index i with g[i] <= x < g[i+1] (clipped to [0, n-2]; x == g[n-1] -> n-2) and normalised distance
-// (x - g[i]) / (g[i+1] - g[i]); false when x is outside [g[0], g[n-1]] (fill value applies).  NaN is "in
-// bounds" with a NaN weight, as in scipy (_rgi.py: find_indices + _find_out_of_bounds).
-// The weights come from the real (float32-rounded) coordinate table, not from an ideal uniform grid.
-template <typename T> SP_HD bool locate(const AxisTab<T>& A, T x, int& i, T& w) {
+// Cell index i with g[i] <= x < g[i+1] (clipped to [0, n-2]; x == g[n-1] -> n-2); false when x is outside
+// [g[0], g[n-1]] (the fill value applies).  NaN is "in bounds" (cell 0, NaN weight later), as in scipy
+// (_rgi.py: find_indices + _find_out_of_bounds).  The decision is made against the real (float32-rounded)
+// coordinate table, not an ideal uniform grid: uniform first guess, then an exact walk if needed.
+template <typename T> SP_HD bool locate(const AxisTab<T>& A, T x, int& i) {
     if (x < A.lo || x > A.hi) return false;
     int k = floor_to_int((x - A.g0) * A.inv_d);
     k = k < 0 ? 0 : (k > A.n - 2 ? A.n - 2 : k);
-    typename Pair<T>::type e = ldg(A.tab + k);
-    T d = x - e.x;
-    T ww = d * e.y;
-    if (!(d >= (T)0) || !(ww < (T)0.999999)) {
-        if (x == x) {  // exact walk against the table (rare: first guess off by one, or x within 1e-6 of a node)
-            while (k > 0 && x < ldg(A.tab + k).x) --k;
-            while (k < A.n - 2 && x >= ldg(A.tab + k + 1).x) ++k;
-            e = ldg(A.tab + k);
-            ww = (x - e.x) * e.y;
-        }
+    if (x == x) {
+        while (k > 0 && x < ldg(A.tab + k).x) --k;
+        while (k < A.n - 2 && x >= ldg(A.tab + k + 1).x) ++k;
     }
-    i = k; w = ww;
+    i = k;
     return true;
 }
 
-// Acceleration a = interp(grad) and, optionally, n-1 at (pu, pv, pw).  Returns false (and zeros) when
-// the point is outside the grid: no memory is touched then.
-// Corner / product order follows scipy's _evaluate_linear: weight = ((1*wu)*wv)*ww, corners in
-// itertools.product order, value accumulated left to right (fused multiply-adds differ by <= 1 ulp).
+// Per-ray register cache of the cell the ray is in.  A ray takes ~8 RHS evaluations per cell (two RK4 steps
+// of four stages), so the 8 corner reads, the float32->float64 conversions and the axis-table lookups are
+// done once per cell instead of once per evaluation; ncu on the uncached kernel showed the L1 data pipe
+// (l1tex__data_pipe_lsu_wavefronts) at 88 % of peak and DRAM at 0.2 %, i.e. the gathers, not HBM, were the
+// bound.  The cell is held as the trilinear polynomial
+//     f = a0 + ww a1 + wv (a2 + ww a3) + wu (a4 + ww a5 + wv (a6 + ww a7))
+// (7 fused multiply-adds per component), whose coefficients are corner differences.
+template <typename T, bool PHASE> struct CellCache {
+    T lo[3], hi[3], rinv[3];            // g[i], g[i+1], 1/(g[i+1]-g[i]) of the cached cell, per axis
+    T a[PHASE ? 4 : 3][8];
+    bool valid;
+    SP_HD CellCache() : valid(false) {}
+};
+
+template <typename T> SP_HD void tri_coef(T c000, T c001, T c010, T c011, T c100, T c101, T c110, T c111, T* a) {
+    a[0] = c000;
+    a[1] = c001 - c000;
+    a[2] = c010 - c000;
+    a[3] = (c011 - c010) - (c001 - c000);
+    a[4] = c100 - c000;
+    a[5] = (c101 - c100) - (c001 - c000);
+    a[6] = (c110 - c100) - (c010 - c000);
+    a[7] = ((c111 - c110) - (c101 - c100)) - ((c011 - c010) - (c001 - c000));
+}
+
+template <typename T> SP_HD T tri_eval(const T* a, T wu, T wv, T ww) {
+    const T t0 = sp_fma(ww, a[1], a[0]);
+    const T t1 = sp_fma(ww, a[3], a[2]);
+    const T t2 = sp_fma(ww, a[5], a[4]);
+    const T t3 = sp_fma(ww, a[7], a[6]);
+    return sp_fma(wu, sp_fma(wv, t3, t2), sp_fma(wv, t1, t0));
+}
+
+// Acceleration a = interp(grad) and, optionally, n-1 at (pu, pv, pw).  Returns false (and zeros) when the
+// point is outside the grid: no memory is touched then.  Trilinear weights are the reference's normalised
+// distances (x - g[i]) / (g[i+1] - g[i]) (reciprocal multiply: <= 1 ulp from the division).
 template <typename T, bool PHASE, bool AUX64>
-SP_HD bool rhs(const FieldView<T>& F, T pu, T pv, T pw, T& au, T& av, T& aw, T& nm1) {
-    int iu, iv, iw; T wu, wv, ww;
-    au = av = aw = nm1 = (T)0;
-    if (!locate(F.ax[0], pu, iu, wu)) return false;
-    if (!locate(F.ax[1], pv, iv, wv)) return false;
-    if (!locate(F.ax[2], pw, iw, ww)) return false;
-    const long long base = (long long)iu * F.su + (long long)iv * F.sv + iw;
-    const f4* p = F.data + base;
-    const f4 c000 = ldg(p), c001 = ldg(p + 1);
-    const f4 c010 = ldg(p + F.sv), c011 = ldg(p + F.sv + 1);
-    const f4 c100 = ldg(p + F.su), c101 = ldg(p + F.su + 1);
-    const f4 c110 = ldg(p + F.su + F.sv), c111 = ldg(p + F.su + F.sv + 1);
-    const T mu = (T)1 - wu, mv = (T)1 - wv, mw = (T)1 - ww;
-    const T w00 = mu * mv, w01 = mu * wv, w10 = wu * mv, w11 = wu * wv;
-    const T k000 = w00 * mw, k001 = w00 * ww, k010 = w01 * mw, k011 = w01 * ww;
-    const T k100 = w10 * mw, k101 = w10 * ww, k110 = w11 * mw, k111 = w11 * ww;
-#define SP_ACC(comp)                                                                                     \
-    sp_fma((T)c111.comp, k111, sp_fma((T)c110.comp, k110, sp_fma((T)c101.comp, k101,                      \
-    sp_fma((T)c100.comp, k100, sp_fma((T)c011.comp, k011, sp_fma((T)c010.comp, k010,                      \
-    sp_fma((T)c001.comp, k001, (T)c000.comp * k000)))))))
-    au = SP_ACC(x); av = SP_ACC(y); aw = SP_ACC(z);
-    if (PHASE) {
-        if (AUX64) {
-            const double* q = F.aux64 + base;
-            const double a000 = ldg(q), a001 = ldg(q + 1), a010 = ldg(q + F.sv), a011 = ldg(q + F.sv + 1);
-            const double a100 = ldg(q + F.su), a101 = ldg(q + F.su + 1);
-            const double a110 = ldg(q + F.su + F.sv), a111 = ldg(q + F.su + F.sv + 1);
-            nm1 = sp_fma((T)a111, k111, sp_fma((T)a110, k110, sp_fma((T)a101, k101, sp_fma((T)a100, k100,
-                  sp_fma((T)a011, k011, sp_fma((T)a010, k010, sp_fma((T)a001, k001, (T)a000 * k000)))))));
-        } else {
-            nm1 = SP_ACC(w);
+SP_HD bool rhs(const FieldView<T>& F, CellCache<T, PHASE>& cc, T pu, T pv, T pw, T& au, T& av, T& aw, T& nm1) {
+    const bool hit = cc.valid && pu >= cc.lo[0] && pu < cc.hi[0] && pv >= cc.lo[1] && pv < cc.hi[1] &&
+                     pw >= cc.lo[2] && pw < cc.hi[2];
+    if (!hit) {
+        int iu, iv, iw;
+        au = av = aw = nm1 = (T)0;
+        if (!locate(F.ax[0], pu, iu)) return false;
+        if (!locate(F.ax[1], pv, iv)) return false;
+        if (!locate(F.ax[2], pw, iw)) return false;
+        {
+            const typename Pair<T>::type eu = ldg(F.ax[0].tab + iu), ev = ldg(F.ax[1].tab + iv), ew = ldg(F.ax[2].tab + iw);
+            cc.lo[0] = eu.x; cc.rinv[0] = eu.y; cc.hi[0] = ldg(F.ax[0].tab + iu + 1).x;
+            cc.lo[1] = ev.x; cc.rinv[1] = ev.y; cc.hi[1] = ldg(F.ax[1].tab + iv + 1).x;
+            cc.lo[2] = ew.x; cc.rinv[2] = ew.y; cc.hi[2] = ldg(F.ax[2].tab + iw + 1).x;
         }
+        const long long base = (long long)iu * F.su + (long long)iv * F.sv + iw;
+        const f4* p = F.data + base;
+        const f4 c000 = ldg(p), c001 = ldg(p + 1);
+        const f4 c010 = ldg(p + F.sv), c011 = ldg(p + F.sv + 1);
+        const f4 c100 = ldg(p + F.su), c101 = ldg(p + F.su + 1);
+        const f4 c110 = ldg(p + F.su + F.sv), c111 = ldg(p + F.su + F.sv + 1);
+        tri_coef<T>((T)c000.x, (T)c001.x, (T)c010.x, (T)c011.x, (T)c100.x, (T)c101.x, (T)c110.x, (T)c111.x, cc.a[0]);
+        tri_coef<T>((T)c000.y, (T)c001.y, (T)c010.y, (T)c011.y, (T)c100.y, (T)c101.y, (T)c110.y, (T)c111.y, cc.a[1]);
+        tri_coef<T>((T)c000.z, (T)c001.z, (T)c010.z, (T)c011.z, (T)c100.z, (T)c101.z, (T)c110.z, (T)c111.z, cc.a[2]);
+        if (PHASE) {
+            if (AUX64) {
+                const double* q = F.aux64 + base;
+                tri_coef<T>((T)ldg(q), (T)ldg(q + 1), (T)ldg(q + F.sv), (T)ldg(q + F.sv + 1), (T)ldg(q + F.su),
+                            (T)ldg(q + F.su + 1), (T)ldg(q + F.su + F.sv), (T)ldg(q + F.su + F.sv + 1), cc.a[PHASE ? 3 : 0]);
+            } else {
+                tri_coef<T>((T)c000.w, (T)c001.w, (T)c010.w, (T)c011.w, (T)c100.w, (T)c101.w, (T)c110.w, (T)c111.w,
+                            cc.a[PHASE ? 3 : 0]);
+            }
+        }
+        cc.valid = true;
     }
-#undef SP_ACC
+    const T wu = (pu - cc.lo[0]) * cc.rinv[0], wv = (pv - cc.lo[1]) * cc.rinv[1], ww = (pw - cc.lo[2]) * cc.rinv[2];
+    au = tri_eval<T>(cc.a[0], wu, wv, ww);
+    av = tri_eval<T>(cc.a[1], wu, wv, ww);
+    aw = tri_eval<T>(cc.a[2], wu, wv, ww);
+    nm1 = PHASE ? tri_eval<T>(cc.a[PHASE ? 3 : 0], wu, wv, ww) : (T)0;
     return true;
 }
 
@@ -216,23 +248,23 @@ template <typename T> SP_HD bool escaped(const FieldView<T>& F, const Ray<T>& r)
 // Classical RK4 step of  p' = v, v' = a(p), ph' = omega (n(p) - 1).  Returns how many of the four RHS
 // evaluations touched the field.  Combination order is y + (h/6)(((k1 + 2k2) + 2k3) + k4).
 template <typename T, bool PHASE, bool AUX64>
-SP_HD int rk4_step(const FieldView<T>& F, T h, T omega, Ray<T>& r) {
+SP_HD int rk4_step(const FieldView<T>& F, CellCache<T, PHASE>& cc, T h, T omega, Ray<T>& r) {
     const T hh = (T)0.5 * h, h6 = h / (T)6;
     T a1[3], a2[3], a3[3], a4[3], n1, n2, n3, n4;
     T v2[3], v3[3], v4[3];
     int touched = 0;
-    touched += rhs<T, PHASE, AUX64>(F, r.p[0], r.p[1], r.p[2], a1[0], a1[1], a1[2], n1);
+    touched += rhs<T, PHASE, AUX64>(F, cc, r.p[0], r.p[1], r.p[2], a1[0], a1[1], a1[2], n1);
 #pragma unroll
     for (int k = 0; k < 3; ++k) v2[k] = sp_fma(hh, a1[k], r.v[k]);
-    touched += rhs<T, PHASE, AUX64>(F, sp_fma(hh, r.v[0], r.p[0]), sp_fma(hh, r.v[1], r.p[1]),
+    touched += rhs<T, PHASE, AUX64>(F, cc, sp_fma(hh, r.v[0], r.p[0]), sp_fma(hh, r.v[1], r.p[1]),
                                     sp_fma(hh, r.v[2], r.p[2]), a2[0], a2[1], a2[2], n2);
 #pragma unroll
     for (int k = 0; k < 3; ++k) v3[k] = sp_fma(hh, a2[k], r.v[k]);
-    touched += rhs<T, PHASE, AUX64>(F, sp_fma(hh, v2[0], r.p[0]), sp_fma(hh, v2[1], r.p[1]),
+    touched += rhs<T, PHASE, AUX64>(F, cc, sp_fma(hh, v2[0], r.p[0]), sp_fma(hh, v2[1], r.p[1]),
                                     sp_fma(hh, v2[2], r.p[2]), a3[0], a3[1], a3[2], n3);
 #pragma unroll
     for (int k = 0; k < 3; ++k) v4[k] = sp_fma(h, a3[k], r.v[k]);
-    touched += rhs<T, PHASE, AUX64>(F, sp_fma(h, v3[0], r.p[0]), sp_fma(h, v3[1], r.p[1]),
+    touched += rhs<T, PHASE, AUX64>(F, cc, sp_fma(h, v3[0], r.p[0]), sp_fma(h, v3[1], r.p[1]),
                                     sp_fma(h, v3[2], r.p[2]), a4[0], a4[1], a4[2], n4);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
@@ -268,9 +300,9 @@ struct DP {
 template <typename T> struct Deriv { T dp[3]; T dv[3]; T dph; };
 
 template <typename T, bool PHASE, bool AUX64>
-SP_HD int deriv(const FieldView<T>& F, T omega, const T* p, const T* v, Deriv<T>& k) {
+SP_HD int deriv(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega, const T* p, const T* v, Deriv<T>& k) {
     T nm1;
-    int t = rhs<T, PHASE, AUX64>(F, p[0], p[1], p[2], k.dv[0], k.dv[1], k.dv[2], nm1);
+    int t = rhs<T, PHASE, AUX64>(F, cc, p[0], p[1], p[2], k.dv[0], k.dv[1], k.dv[2], nm1);
     k.dp[0] = v[0]; k.dp[1] = v[1]; k.dp[2] = v[2];
     k.dph = PHASE ? omega * nm1 : (T)0;
     return t;
@@ -280,7 +312,7 @@ SP_HD int deriv(const FieldView<T>& F, T omega, const T* p, const T* v, Deriv<T>
 // and sum over the live components of (err_i / scale_i)^2 with scale = atol + rtol max(|y|, |y_new|)
 // (rk.py:_step_impl).  amp (|y| = amp0) and pol contribute zero error.
 template <typename T, bool PHASE, bool AUX64>
-SP_HD int dp5_attempt(const FieldView<T>& F, T omega, T h, T rtol, T atol, const Ray<T>& r, const Deriv<T>& k1,
+SP_HD int dp5_attempt(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega, T h, T rtol, T atol, const Ray<T>& r, const Deriv<T>& k1,
                       Ray<T>& rn, Deriv<T>& k7, T& err_sq) {
     Deriv<T> k2, k3, k4, k5, k6;
     T p[3], v[3];
@@ -292,20 +324,20 @@ SP_HD int dp5_attempt(const FieldView<T>& F, T omega, T h, T rtol, T atol, const
         v[c] = r.v[c] + (expr_v) * h;                     \
     }
     SP_STAGE((T)DP::a21 * k1.dp[c], (T)DP::a21 * k1.dv[c]);
-    touched += deriv<T, PHASE, AUX64>(F, omega, p, v, k2);
+    touched += deriv<T, PHASE, AUX64>(F, cc, omega, p, v, k2);
     SP_STAGE((T)DP::a31 * k1.dp[c] + (T)DP::a32 * k2.dp[c], (T)DP::a31 * k1.dv[c] + (T)DP::a32 * k2.dv[c]);
-    touched += deriv<T, PHASE, AUX64>(F, omega, p, v, k3);
+    touched += deriv<T, PHASE, AUX64>(F, cc, omega, p, v, k3);
     SP_STAGE((T)DP::a41 * k1.dp[c] + (T)DP::a42 * k2.dp[c] + (T)DP::a43 * k3.dp[c],
              (T)DP::a41 * k1.dv[c] + (T)DP::a42 * k2.dv[c] + (T)DP::a43 * k3.dv[c]);
-    touched += deriv<T, PHASE, AUX64>(F, omega, p, v, k4);
+    touched += deriv<T, PHASE, AUX64>(F, cc, omega, p, v, k4);
     SP_STAGE((T)DP::a51 * k1.dp[c] + (T)DP::a52 * k2.dp[c] + (T)DP::a53 * k3.dp[c] + (T)DP::a54 * k4.dp[c],
              (T)DP::a51 * k1.dv[c] + (T)DP::a52 * k2.dv[c] + (T)DP::a53 * k3.dv[c] + (T)DP::a54 * k4.dv[c]);
-    touched += deriv<T, PHASE, AUX64>(F, omega, p, v, k5);
+    touched += deriv<T, PHASE, AUX64>(F, cc, omega, p, v, k5);
     SP_STAGE((T)DP::a61 * k1.dp[c] + (T)DP::a62 * k2.dp[c] + (T)DP::a63 * k3.dp[c] + (T)DP::a64 * k4.dp[c] +
                  (T)DP::a65 * k5.dp[c],
              (T)DP::a61 * k1.dv[c] + (T)DP::a62 * k2.dv[c] + (T)DP::a63 * k3.dv[c] + (T)DP::a64 * k4.dv[c] +
                  (T)DP::a65 * k5.dv[c]);
-    touched += deriv<T, PHASE, AUX64>(F, omega, p, v, k6);
+    touched += deriv<T, PHASE, AUX64>(F, cc, omega, p, v, k6);
 #undef SP_STAGE
     // y_new = y + h * (K[:-1].T @ B)
 #pragma unroll
@@ -319,7 +351,7 @@ SP_HD int dp5_attempt(const FieldView<T>& F, T omega, T h, T rtol, T atol, const
     if (PHASE)
         rn.ph = r.ph + h * ((T)DP::b1 * k1.dph + (T)DP::b3 * k3.dph + (T)DP::b4 * k4.dph + (T)DP::b5 * k5.dph +
                             (T)DP::b6 * k6.dph);
-    touched += deriv<T, PHASE, AUX64>(F, omega, rn.p, rn.v, k7);
+    touched += deriv<T, PHASE, AUX64>(F, cc, omega, rn.p, rn.v, k7);
     // error estimate  (K.T @ E) * h / scale
     T acc = (T)0;
 #define SP_ERR(y0, y1, K1, K3, K4, K5, K6, K7)                                                           \
@@ -354,7 +386,7 @@ template <typename T> SP_HD T dp5_factor(T en, bool accepted, bool rejected_befo
 // Hairer's initial step as coded in scipy/integrate/_ivp/common.py::select_initial_step (order = 4), with
 // the RMS norms taken over the ray's own n_state components (amp contributes (amp/scale)^2 to d0 only).
 template <typename T, bool PHASE, bool AUX64>
-SP_HD T dp5_initial_step(const FieldView<T>& F, T omega, T t_end, T rtol, T atol, int n_state, T amp, T pol,
+SP_HD T dp5_initial_step(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega, T t_end, T rtol, T atol, int n_state, T amp, T pol,
                          const Ray<T>& r, const Deriv<T>& f0, int& touched) {
     if (t_end == (T)0) return (T)0;
     const T inv_n = (T)1 / (T)n_state;
@@ -382,7 +414,7 @@ SP_HD T dp5_initial_step(const FieldView<T>& F, T omega, T t_end, T rtol, T atol
 #pragma unroll
     for (int c = 0; c < 3; ++c) { p1[c] = r.p[c] + h0 * f0.dp[c]; v1[c] = r.v[c] + h0 * f0.dv[c]; }
     Deriv<T> f1;
-    touched += deriv<T, PHASE, AUX64>(F, omega, p1, v1, f1);
+    touched += deriv<T, PHASE, AUX64>(F, cc, omega, p1, v1, f1);
     T s2 = (T)0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {

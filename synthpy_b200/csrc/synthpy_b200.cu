@@ -460,20 +460,21 @@ __global__ void __launch_bounds__(128) k_propagate(const PropArgs<T> A, const Ep
         for (int k = 0; k < 3; ++k) { r.p[k] = (T)s[A.perm[k]]; r.v[k] = (T)s[3 + A.perm[k]]; }
         r.ph = (T)ph0;
         unsigned n_att = 0;
+        CellCache<T, PHASE> cc;
         if (valid) {
             if (METHOD == SP_METHOD_RK4) {
                 const T h = A.h;
                 for (int it = 0; it < A.n_steps; ++it) {
                     if (early && escaped(A.F, r)) break;
-                    ls.evals += rk4_step<T, PHASE, AUX64>(A.F, h, A.omega, r);
+                    ls.evals += rk4_step<T, PHASE, AUX64>(A.F, cc, h, A.omega, r);
                     ++n_att;
                 }
                 ls.acc += n_att;
             } else {
                 // SciPy RK45 driven as solve_ivp does (rk.py:_step_impl), one controller per ray
                 Deriv<T> f; int touched = 0;
-                touched += deriv<T, PHASE, AUX64>(A.F, A.omega, r.p, r.v, f);
-                T h_abs = dp5_initial_step<T, PHASE, AUX64>(A.F, A.omega, A.t_end, A.rtol, A.atol, A.n_state, (T)amp,
+                touched += deriv<T, PHASE, AUX64>(A.F, cc, A.omega, r.p, r.v, f);
+                T h_abs = dp5_initial_step<T, PHASE, AUX64>(A.F, cc, A.omega, A.t_end, A.rtol, A.atol, A.n_state, (T)amp,
                                                             (T)pol, r, f, touched);
                 T t = (T)0;
                 const unsigned cap = A.n_steps > 0 ? (unsigned)A.n_steps : (1u << 30);
@@ -492,7 +493,7 @@ __global__ void __launch_bounds__(128) k_propagate(const PropArgs<T> A, const Ep
                         const T h = t_new - t;
                         h_abs = fabs(h);
                         Ray<T> rn; Deriv<T> fn; T esq;
-                        touched += dp5_attempt<T, PHASE, AUX64>(A.F, A.omega, h, A.rtol, A.atol, r, f, rn, fn, esq);
+                        touched += dp5_attempt<T, PHASE, AUX64>(A.F, cc, A.omega, h, A.rtol, A.atol, r, f, rn, fn, esq);
                         ++n_att;
                         const T en = sqrt(esq * inv_n);
                         if (en < (T)1) {
@@ -586,11 +587,12 @@ __global__ void k_joint_init(FieldView<double> F, JointBuf B, const double* s0, 
     if (i < n) {
         const int perm[3] = {p0, p1, p2};
         Ray<double> r; Deriv<double> f;
+        CellCache<double, PHASE> cc;
         if (pass == 0) {
             for (int k = 0; k < 3; ++k) { r.p[k] = s0[(uint64_t)perm[k] * n + i]; r.v[k] = s0[(uint64_t)(3 + perm[k]) * n + i]; }
             r.ph = s0[7 * n + i];
             B.amp[i] = s0[6 * n + i]; B.pol[i] = s0[8 * n + i];
-            deriv<double, PHASE, AUX64>(F, omega, r.p, r.v, f);
+            deriv<double, PHASE, AUX64>(F, cc, omega, r.p, r.v, f);
             for (int k = 0; k < 3; ++k) { B.p[k][i] = r.p[k]; B.v[k][i] = r.v[k]; B.fv[k][i] = f.dv[k]; }
             B.ph[i] = r.ph; B.fph[i] = f.dph;
             for (int k = 0; k < 3; ++k) {
@@ -608,7 +610,7 @@ __global__ void k_joint_init(FieldView<double> F, JointBuf B, const double* s0, 
                 r.p[k] = B.p[k][i]; r.v[k] = B.v[k][i];
                 p1_[k] = r.p[k] + h0 * r.v[k]; v1_[k] = r.v[k] + h0 * B.fv[k][i];
             }
-            deriv<double, PHASE, AUX64>(F, omega, p1_, v1_, f);
+            deriv<double, PHASE, AUX64>(F, cc, omega, p1_, v1_, f);
             for (int k = 0; k < 3; ++k) {
                 const double sp_ = atol + fabs(r.p[k]) * rtol, sv_ = atol + fabs(r.v[k]) * rtol;
                 double q = (f.dp[k] - r.v[k]) / sp_; s_a += q * q;
@@ -635,9 +637,10 @@ __global__ void k_joint_attempt(FieldView<double> F, JointBuf B, uint64_t n, dou
     double esq = 0.0;
     if (i < n) {
         Ray<double> r, rn; Deriv<double> f, fn;
+        CellCache<double, PHASE> cc;
         for (int k = 0; k < 3; ++k) { r.p[k] = B.p[k][i]; r.v[k] = B.v[k][i]; f.dp[k] = r.v[k]; f.dv[k] = B.fv[k][i]; }
         r.ph = B.ph[i]; f.dph = B.fph[i];
-        dp5_attempt<double, PHASE, AUX64>(F, omega, h, rtol, atol, r, f, rn, fn, esq);
+        dp5_attempt<double, PHASE, AUX64>(F, cc, omega, h, rtol, atol, r, f, rn, fn, esq);
         for (int k = 0; k < 3; ++k) { B.pn[k][i] = rn.p[k]; B.vn[k][i] = rn.v[k]; B.fvn[k][i] = fn.dv[k]; }
         B.phn[i] = rn.ph; B.fphn[i] = fn.dph;
     }
@@ -762,7 +765,8 @@ __global__ void k_rhs(FieldView<double> F, const double* __restrict__ s, uint64_
     double p[3], v[3];
     for (int k = 0; k < 3; ++k) { p[k] = s[(uint64_t)perm[k] * n + i]; v[k] = s[(uint64_t)(3 + perm[k]) * n + i]; }
     Deriv<double> f;
-    deriv<double, PHASE, AUX64>(F, omega, p, v, f);
+    CellCache<double, PHASE> cc;
+    deriv<double, PHASE, AUX64>(F, cc, omega, p, v, f);
     for (int k = 0; k < 3; ++k) { out[(uint64_t)perm[k] * n + i] = f.dp[k]; out[(uint64_t)(3 + perm[k]) * n + i] = f.dv[k]; }
     out[6 * n + i] = 0.0; out[7 * n + i] = f.dph; out[8 * n + i] = 0.0;
 }

@@ -109,7 +109,8 @@ static void rhs_t(const HostField* f, const double* s, uint64_t n, double* out, 
     for (uint64_t i = 0; i < n; ++i) {
         Ray<double> r; load(f, s, n, i, r);
         Deriv<double> d;
-        deriv<double, PH, A64>(F, omega, r.p, r.v, d);
+        CellCache<double, PH> cc;
+        deriv<double, PH, A64>(F, cc, omega, r.p, r.v, d);
         for (int k = 0; k < 3; ++k) { out[(uint64_t)f->perm[k] * n + i] = d.dp[k]; out[(uint64_t)(3 + f->perm[k]) * n + i] = d.dv[k]; }
         out[6 * n + i] = 0; out[7 * n + i] = d.dph; out[8 * n + i] = 0;
     }
@@ -130,9 +131,10 @@ static void rk4_t(const HostField* f, const FieldView<T>& F, const double* s0, u
         for (int k = 0; k < 3; ++k) { r.p[k] = (T)rd.p[k]; r.v[k] = (T)rd.v[k]; }
         r.ph = (T)rd.ph;
         uint32_t it = 0;
+        CellCache<T, PH> cc;
         for (; it < (uint32_t)n_steps; ++it) {
             if (early && escaped(F, r)) break;
-            rk4_step<T, PH, A64>(F, (T)h, (T)omega, r);
+            rk4_step<T, PH, A64>(F, cc, (T)h, (T)omega, r);
         }
         for (int k = 0; k < 3; ++k) { rd.p[k] = r.p[k]; rd.v[k] = r.v[k]; }
         rd.ph = r.ph;
@@ -164,8 +166,9 @@ static void rk45_t(const HostField* f, const double* s0, uint64_t n, double t_en
         Ray<double> r; load(f, s0, n, i, r);
         const double amp = s0[6 * n + i], pol = s0[8 * n + i];
         Deriv<double> fd; int touched = 0; uint32_t evals = 1;
-        deriv<double, PH, A64>(F, omega, r.p, r.v, fd);
-        double h_abs = dp5_initial_step<double, PH, A64>(F, omega, t_end, rtol, atol, n_state, amp, pol, r, fd, touched);
+        CellCache<double, PH> cc;
+        deriv<double, PH, A64>(F, cc, omega, r.p, r.v, fd);
+        double h_abs = dp5_initial_step<double, PH, A64>(F, cc, omega, t_end, rtol, atol, n_state, amp, pol, r, fd, touched);
         evals += 1;
         double t = 0; uint32_t n_att = 0;
         const uint32_t cap = cap_in > 0 ? (uint32_t)cap_in : (1u << 30);
@@ -181,7 +184,7 @@ static void rk45_t(const HostField* f, const double* s0, uint64_t n, double t_en
                 const double h = t_new - t;
                 h_abs = fabs(h);
                 Ray<double> rn; Deriv<double> fn; double esq;
-                dp5_attempt<double, PH, A64>(F, omega, h, rtol, atol, r, fd, rn, fn, esq);
+                dp5_attempt<double, PH, A64>(F, cc, omega, h, rtol, atol, r, fd, rn, fn, esq);
                 ++n_att; evals += 6;
                 const double en = sqrt(esq / n_state);
                 if (en < 1) { h_abs *= dp5_factor<double>(en, true, rejected); t = t_new; r = rn; fd = fn; break; }
@@ -256,53 +259,6 @@ extern "C" void hh_philox(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, ui
     Philox p; p.k0 = k0; p.k1 = k1; p.block(c0, c1, c2, c3, out);
 }
 
-// debug helper: initial step size chosen for each ray (phase + aux64 variant)
-extern "C" void hh_rk45_h0(void* h, const double* s0, uint64_t n, double t_end, double rtol, double atol, double omega,
-                           int n_state, double* h0) {
-    const HostField* f = (const HostField*)h;
-    FieldView<double> F = f->view64();
-    for (uint64_t i = 0; i < n; ++i) {
-        Ray<double> r; load(f, s0, n, i, r);
-        Deriv<double> fd; int touched = 0;
-        deriv<double, true, true>(F, omega, r.p, r.v, fd);
-        h0[i] = dp5_initial_step<double, true, true>(F, omega, t_end, rtol, atol, n_state, s0[6 * n + i], s0[8 * n + i], r, fd, touched);
-    }
-}
-
-// debug helper: trace of accepted steps for ONE ray: t and the 7 live state values after each accepted step
-extern "C" int hh_rk45_trace(void* hnd, const double* s0, double t_end, double rtol, double atol, double omega, int n_state,
-                             int max_out, double* t_out, double* y_out, double* en_out) {
-    const HostField* f = (const HostField*)hnd;
-    FieldView<double> F = f->view64();
-    Ray<double> r; load(f, s0, 1, 0, r);
-    Deriv<double> fd; int touched = 0;
-    deriv<double, true, true>(F, omega, r.p, r.v, fd);
-    double h_abs = dp5_initial_step<double, true, true>(F, omega, t_end, rtol, atol, n_state, s0[6], s0[8], r, fd, touched);
-    double t = 0; int k = 0;
-    while (t < t_end && k < max_out) {
-        const double min_step = 10 * (nextafter(t, INFINITY) - t);
-        if (h_abs < min_step) h_abs = min_step;
-        bool rejected = false;
-        for (;;) {
-            double t_new = t + h_abs;
-            if (t_new - t_end > 0) t_new = t_end;
-            const double h = t_new - t;
-            h_abs = fabs(h);
-            Ray<double> rn; Deriv<double> fn; double esq;
-            dp5_attempt<double, true, true>(F, omega, h, rtol, atol, r, fd, rn, fn, esq);
-            const double en = sqrt(esq / n_state);
-            if (en < 1) { h_abs *= dp5_factor<double>(en, true, rejected); t = t_new; r = rn; fd = fn; en_out[k] = en; break; }
-            h_abs *= dp5_factor<double>(en, false, rejected);
-            rejected = true;
-        }
-        t_out[k] = t;
-        for (int c = 0; c < 3; ++c) { y_out[7 * k + f->perm[c]] = r.p[c]; y_out[7 * k + 3 + f->perm[c]] = r.v[c]; }
-        y_out[7 * k + 6] = r.ph;
-        ++k;
-    }
-    return k;
-}
-
 // debug/test helper: RHS evaluated with the float32 code path (state rounded to float32 first)
 extern "C" void hh_rhs_fp32(void* hnd, const double* s, uint64_t n, double* out) {
     const HostField* f = (const HostField*)hnd;
@@ -311,110 +267,9 @@ extern "C" void hh_rhs_fp32(void* hnd, const double* s, uint64_t n, double* out)
         float p[3], v[3];
         for (int k = 0; k < 3; ++k) { p[k] = (float)s[(uint64_t)f->perm[k] * n + i]; v[k] = (float)s[(uint64_t)(3 + f->perm[k]) * n + i]; }
         Deriv<float> d;
-        deriv<float, false, false>(F, 0.f, p, v, d);
+        CellCache<float, false> cc;
+        deriv<float, false, false>(F, cc, 0.f, p, v, d);
         for (int k = 0; k < 3; ++k) { out[(uint64_t)f->perm[k] * n + i] = d.dp[k]; out[(uint64_t)(3 + f->perm[k]) * n + i] = d.dv[k]; }
         out[6 * n + i] = out[7 * n + i] = out[8 * n + i] = 0;
-    }
-}
-
-// Host mirror of the joint-step controller in synthpy_b200.cu::joint_solve (same per-ray functions, same
-// controller arithmetic), used to debug/verify the logic without a GPU.
-template <bool PH, bool A64>
-static int joint_t(void* hnd, const double* s0, uint64_t n, double t_end, double rtol, double atol, double omega,
-                             int n_state, double* sf) {
-    const HostField* f = (const HostField*)hnd;
-    FieldView<double> F = f->view64();
-    std::vector<Ray<double>> r(n), rn(n);
-    std::vector<Deriv<double>> fd(n), fn(n);
-    const double size = (double)n_state * (double)n;
-    double s_a = 0, s_b = 0;
-    for (uint64_t i = 0; i < n; ++i) {
-        load(f, s0, n, i, r[i]);
-        deriv<double, PH, A64>(F, omega, r[i].p, r[i].v, fd[i]);
-        for (int k = 0; k < 3; ++k) {
-            const double sp_ = atol + fabs(r[i].p[k]) * rtol, sv_ = atol + fabs(r[i].v[k]) * rtol;
-            double q = r[i].p[k] / sp_; s_a += q * q; q = r[i].v[k] / sv_; s_a += q * q;
-            q = fd[i].dp[k] / sp_; s_b += q * q; q = fd[i].dv[k] / sv_; s_b += q * q;
-        }
-        const double sph = atol + fabs(r[i].ph) * rtol;
-        double q = r[i].ph / sph; s_a += q * q; q = fd[i].dph / sph; s_b += q * q;
-        const double amp = s0[6 * n + i], pol = s0[8 * n + i];
-        q = amp / (atol + fabs(amp) * rtol); s_a += q * q;
-        q = pol / (atol + fabs(pol) * rtol); s_a += q * q;
-    }
-    const double d0 = sqrt(s_a) / sqrt(size), d1 = sqrt(s_b) / sqrt(size);
-    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-    h0 = h0 < t_end ? h0 : t_end;
-    double s_c = 0;
-    for (uint64_t i = 0; i < n; ++i) {
-        double p1[3], v1[3];
-        for (int k = 0; k < 3; ++k) { p1[k] = r[i].p[k] + h0 * r[i].v[k]; v1[k] = r[i].v[k] + h0 * fd[i].dv[k]; }
-        Deriv<double> f1;
-        deriv<double, PH, A64>(F, omega, p1, v1, f1);
-        for (int k = 0; k < 3; ++k) {
-            const double sp_ = atol + fabs(r[i].p[k]) * rtol, sv_ = atol + fabs(r[i].v[k]) * rtol;
-            double q = (f1.dp[k] - r[i].v[k]) / sp_; s_c += q * q;
-            q = (f1.dv[k] - fd[i].dv[k]) / sv_; s_c += q * q;
-        }
-        const double sph = atol + fabs(r[i].ph) * rtol;
-        const double q = (f1.dph - fd[i].dph) / sph; s_c += q * q;
-    }
-    const double d2 = sqrt(s_c) / sqrt(size) / h0;
-    double h1;
-    if (d1 <= 1e-15 && d2 <= 1e-15) h1 = (1e-6 > h0 * 1e-3) ? 1e-6 : h0 * 1e-3;
-    else h1 = pow(0.01 / (d1 > d2 ? d1 : d2), 0.2);
-    double h_abs = 100 * h0 < h1 ? 100 * h0 : h1;
-    h_abs = h_abs < t_end ? h_abs : t_end;
-    double t = 0; int attempts = 0;
-    while (t < t_end) {
-        const double min_step = 10 * fabs(nextafter(t, INFINITY) - t);
-        if (h_abs < min_step) h_abs = min_step;
-        bool rejected = false;
-        for (;;) {
-            if (h_abs < min_step) return -1;
-            double t_new = t + h_abs;
-            if (t_new - t_end > 0) t_new = t_end;
-            const double h = t_new - t;
-            h_abs = fabs(h);
-            double tot = 0;
-            for (uint64_t i = 0; i < n; ++i) {
-                double esq;
-                dp5_attempt<double, PH, A64>(F, omega, h, rtol, atol, r[i], fd[i], rn[i], fn[i], esq);
-                tot += esq;
-            }
-            ++attempts;
-            const double en = sqrt(tot) / sqrt(size);
-            if (getenv("HH_DEBUG")) fprintf(stderr, "%.6e %.6e\n", h, en);
-            if (en < 1) {
-                double fac = (en == 0) ? DP::MAX_FACTOR : fmin(DP::MAX_FACTOR, DP::SAFETY * pow(en, -0.2));
-                if (rejected) fac = fmin(1.0, fac);
-                h_abs *= fac; t = t_new; r.swap(rn); fd.swap(fn);
-                break;
-            }
-            h_abs *= fmax(DP::MIN_FACTOR, DP::SAFETY * pow(en, -0.2));
-            rejected = true;
-        }
-    }
-    for (uint64_t i = 0; i < n; ++i) store(f, sf, s0, n, i, r[i]);
-    return attempts;
-}
-
-extern "C" int hh_rk45_joint(void* hnd, const double* s0, uint64_t n, double t_end, double rtol, double atol, double omega,
-                             int n_state, int phase, double* sf) {
-    return phase ? joint_t<true, true>(hnd, s0, n, t_end, rtol, atol, omega, n_state, sf)
-                 : joint_t<false, false>(hnd, s0, n, t_end, rtol, atol, omega, n_state, sf);
-}
-
-// debug helper: one DP5 attempt of size h for every ray from its initial state; per-ray err_sq and new state
-extern "C" void hh_dp5_attempt(void* hnd, const double* s0, uint64_t n, double h, double rtol, double atol, double omega,
-                               double* esq_out, double* sf) {
-    const HostField* f = (const HostField*)hnd;
-    FieldView<double> F = f->view64();
-    for (uint64_t i = 0; i < n; ++i) {
-        Ray<double> r, rn; Deriv<double> fd, fn;
-        load(f, s0, n, i, r);
-        deriv<double, false, false>(F, omega, r.p, r.v, fd);
-        dp5_attempt<double, false, false>(F, omega, h, rtol, atol, r, fd, rn, fn, esq_out[i]);
-        store(f, sf, s0, n, i, rn);
     }
 }

@@ -42,7 +42,7 @@ def test_rhs_matches_reference(H, golden):
         ref = g["dsdt_phase%d" % ph]
         assert np.array_equal(out[:3], ref[:3])
         assert np.array_equal(out[3:6] == 0, ref[3:6] == 0)          # identical in/out-of-bounds decisions
-        assert rel_err(out[3:6], ref[3:6], floor=1e3) < 1e-13
+        assert rel_err(out[3:6], ref[3:6], floor=1e3) < 1e-11      # polynomial form of the trilinear: few-ulp of the corner scale
         if ph:
             # the reference interpolates n ~ 1 and subtracts 1 afterwards: its own rounding floor is a few
             # eps * omega in absolute terms (we interpolate n-1, which is more accurate at low density)
