@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libsynthpy_b200.so")
+LIB_PATH = os.environ.get("SYNTHPY_B200_LIB") or os.path.join(_HERE, "csrc", "libsynthpy_b200.so")   # override: A/B builds
 
 # ---- constants (mirror the header) ---------------------------------------------------------------
 FIELD_PHASE, FIELD_PHASE_F64 = 1, 2

@@ -16,6 +16,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define SP_HD __host__ __device__ __forceinline__
@@ -112,6 +113,23 @@ SP_HD f2 ldg(const f2* p) {
 #endif
 }
 
+// 0 <= w < 1 decided on the bit pattern (one integer compare on the ALU pipe instead of two FP64 compares on the
+// FP64 pipe, whose latency the dependent branch would expose).  -0.0, negatives, w >= 1, inf and NaN all fail.
+SP_HD bool unit_interval(double w) {
+#if defined(__CUDA_ARCH__)
+    return (unsigned)__double2hiint(w) < 0x3FF00000u;
+#else
+    uint64_t b; memcpy(&b, &w, 8); return (uint32_t)(b >> 32) < 0x3FF00000u;
+#endif
+}
+SP_HD bool unit_interval(float w) {
+#if defined(__CUDA_ARCH__)
+    return (unsigned)__float_as_int(w) < 0x3F800000u;
+#else
+    uint32_t b; memcpy(&b, &w, 4); return b < 0x3F800000u;
+#endif
+}
+
 // ---- field view --------------------------------------------------------------------------------------
 // Kernel frame: axes (u, v, w) = (m+1, m+2, m) mod 3 of the caller's (x, y, z), m = march (probing) axis;
 // w is the fastest-varying axis of the packed grid, so the two corners a ray needs along its direction of
@@ -157,9 +175,31 @@ template <typename T> SP_HD bool locate(const AxisTab<T>& A, T x, int& i) {
 template <typename T, bool PHASE> struct CellCache {
     T lo[3], hi[3], rinv[3];            // g[i], g[i+1], 1/(g[i+1]-g[i]) of the cached cell, per axis
     T a[PHASE ? 4 : 3][8];
+    int idx[3];
     bool valid;
-    SP_HD CellCache() : valid(false) {}
+    SP_HD CellCache() : valid(false) {
+        for (int k = 0; k < 3; ++k) { lo[k] = hi[k] = rinv[k] = (T)0; idx[k] = 0; }
+    }
 };
+
+// Move the cached interval of one axis to the cell containing x.  Common case: the neighbouring cell (one or
+// two table reads); anything else falls back to the exact search.  False = x is outside the grid.
+template <typename T> SP_HD bool relocate_axis(const AxisTab<T>& A, T x, bool valid, int& i, T& lo, T& hi, T& rinv) {
+    if (valid) {
+        if (x >= lo && x < hi) return true;
+        if (x >= hi && i + 2 < A.n) {
+            const typename Pair<T>::type e1 = ldg(A.tab + i + 1), e2 = ldg(A.tab + i + 2);
+            if (x < e2.x) { ++i; lo = e1.x; rinv = e1.y; hi = e2.x; return true; }
+        } else if (x < lo && i > 0) {
+            const typename Pair<T>::type e0 = ldg(A.tab + i - 1);
+            if (x >= e0.x) { --i; hi = lo; lo = e0.x; rinv = e0.y; return true; }
+        }
+    }
+    if (!locate(A, x, i)) return false;
+    const typename Pair<T>::type e = ldg(A.tab + i);
+    lo = e.x; rinv = e.y; hi = ldg(A.tab + i + 1).x;
+    return true;
+}
 
 template <typename T> SP_HD void tri_coef(T c000, T c001, T c010, T c011, T c100, T c101, T c110, T c111, T* a) {
     a[0] = c000;
@@ -183,23 +223,21 @@ template <typename T> SP_HD T tri_eval(const T* a, T wu, T wv, T ww) {
 // Acceleration a = interp(grad) and, optionally, n-1 at (pu, pv, pw).  Returns false (and zeros) when the
 // point is outside the grid: no memory is touched then.  Trilinear weights are the reference's normalised
 // distances (x - g[i]) / (g[i+1] - g[i]) (reciprocal multiply: <= 1 ulp from the division).
+// Fast path: the point is still in the cached cell iff all three weights are in [0, 1) -- decided from the
+// weights (needed anyway) with integer compares.  (A point within one ulp above a cell face can thus still be
+// evaluated with the previous cell's polynomial; the trilinear interpolant is continuous across faces, so
+// the value is the same to rounding.  Every decision taken on a miss is exact against the axis tables.)
 template <typename T, bool PHASE, bool AUX64>
 SP_HD bool rhs(const FieldView<T>& F, CellCache<T, PHASE>& cc, T pu, T pv, T pw, T& au, T& av, T& aw, T& nm1) {
-    const bool hit = cc.valid && pu >= cc.lo[0] && pu < cc.hi[0] && pv >= cc.lo[1] && pv < cc.hi[1] &&
-                     pw >= cc.lo[2] && pw < cc.hi[2];
-    if (!hit) {
-        int iu, iv, iw;
+    T wu = (pu - cc.lo[0]) * cc.rinv[0], wv = (pv - cc.lo[1]) * cc.rinv[1], ww = (pw - cc.lo[2]) * cc.rinv[2];
+    if (!(cc.valid && unit_interval(wu) && unit_interval(wv) && unit_interval(ww))) {
         au = av = aw = nm1 = (T)0;
-        if (!locate(F.ax[0], pu, iu)) return false;
-        if (!locate(F.ax[1], pv, iv)) return false;
-        if (!locate(F.ax[2], pw, iw)) return false;
-        {
-            const typename Pair<T>::type eu = ldg(F.ax[0].tab + iu), ev = ldg(F.ax[1].tab + iv), ew = ldg(F.ax[2].tab + iw);
-            cc.lo[0] = eu.x; cc.rinv[0] = eu.y; cc.hi[0] = ldg(F.ax[0].tab + iu + 1).x;
-            cc.lo[1] = ev.x; cc.rinv[1] = ev.y; cc.hi[1] = ldg(F.ax[1].tab + iv + 1).x;
-            cc.lo[2] = ew.x; cc.rinv[2] = ew.y; cc.hi[2] = ldg(F.ax[2].tab + iw + 1).x;
-        }
-        const long long base = (long long)iu * F.su + (long long)iv * F.sv + iw;
+        const bool v = cc.valid;
+        cc.valid = false;
+        if (!relocate_axis(F.ax[0], pu, v, cc.idx[0], cc.lo[0], cc.hi[0], cc.rinv[0])) return false;
+        if (!relocate_axis(F.ax[1], pv, v, cc.idx[1], cc.lo[1], cc.hi[1], cc.rinv[1])) return false;
+        if (!relocate_axis(F.ax[2], pw, v, cc.idx[2], cc.lo[2], cc.hi[2], cc.rinv[2])) return false;
+        const long long base = (long long)cc.idx[0] * F.su + (long long)cc.idx[1] * F.sv + cc.idx[2];
         const f4* p = F.data + base;
         const f4 c000 = ldg(p), c001 = ldg(p + 1);
         const f4 c010 = ldg(p + F.sv), c011 = ldg(p + F.sv + 1);
@@ -219,8 +257,8 @@ SP_HD bool rhs(const FieldView<T>& F, CellCache<T, PHASE>& cc, T pu, T pv, T pw,
             }
         }
         cc.valid = true;
+        wu = (pu - cc.lo[0]) * cc.rinv[0]; wv = (pv - cc.lo[1]) * cc.rinv[1]; ww = (pw - cc.lo[2]) * cc.rinv[2];
     }
-    const T wu = (pu - cc.lo[0]) * cc.rinv[0], wv = (pv - cc.lo[1]) * cc.rinv[1], ww = (pw - cc.lo[2]) * cc.rinv[2];
     au = tri_eval<T>(cc.a[0], wu, wv, ww);
     av = tri_eval<T>(cc.a[1], wu, wv, ww);
     aw = tri_eval<T>(cc.a[2], wu, wv, ww);
@@ -245,38 +283,47 @@ template <typename T> SP_HD bool escaped(const FieldView<T>& F, const Ray<T>& r)
     return e;
 }
 
-// Classical RK4 step of  p' = v, v' = a(p), ph' = omega (n(p) - 1).  Returns how many of the four RHS
-// evaluations touched the field.  Combination order is y + (h/6)(((k1 + 2k2) + 2k3) + k4).
+// Classical RK4 step of  p' = v, v' = a(p), ph' = omega (n(p) - 1), combined as
+// y + (h/6)(((k1 + 2 k2) + 2 k3) + k4) with running sums (same association, fewer live registers).
+// Returns how many of the four RHS evaluations touched the field, or -1 (state untouched) when `early` is set
+// and the ray has escaped: that test is only evaluated when the first stage is out of bounds, which is
+// necessary for "escaped" and costs nothing on the in-grid path.
 template <typename T, bool PHASE, bool AUX64>
-SP_HD int rk4_step(const FieldView<T>& F, CellCache<T, PHASE>& cc, T h, T omega, Ray<T>& r) {
+SP_HD int rk4_step(const FieldView<T>& F, CellCache<T, PHASE>& cc, T h, T omega, Ray<T>& r, bool early = false) {
     const T hh = (T)0.5 * h, h6 = h / (T)6;
-    T a1[3], a2[3], a3[3], a4[3], n1, n2, n3, n4;
-    T v2[3], v3[3], v4[3];
+    T a[3], n, sv[3], sp[3], vs[3], sn = (T)0;
     int touched = 0;
-    touched += rhs<T, PHASE, AUX64>(F, cc, r.p[0], r.p[1], r.p[2], a1[0], a1[1], a1[2], n1);
+    const bool in1 = rhs<T, PHASE, AUX64>(F, cc, r.p[0], r.p[1], r.p[2], a[0], a[1], a[2], n);
+    if (early && !in1 && escaped(F, r)) return -1;
+    touched += in1;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) v2[k] = sp_fma(hh, a1[k], r.v[k]);
+    for (int k = 0; k < 3; ++k) { sv[k] = a[k]; sp[k] = r.v[k]; vs[k] = sp_fma(hh, a[k], r.v[k]); }   // vs = v2
+    if (PHASE) sn = n;
     touched += rhs<T, PHASE, AUX64>(F, cc, sp_fma(hh, r.v[0], r.p[0]), sp_fma(hh, r.v[1], r.p[1]),
-                                    sp_fma(hh, r.v[2], r.p[2]), a2[0], a2[1], a2[2], n2);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) v3[k] = sp_fma(hh, a2[k], r.v[k]);
-    touched += rhs<T, PHASE, AUX64>(F, cc, sp_fma(hh, v2[0], r.p[0]), sp_fma(hh, v2[1], r.p[1]),
-                                    sp_fma(hh, v2[2], r.p[2]), a3[0], a3[1], a3[2], n3);
-#pragma unroll
-    for (int k = 0; k < 3; ++k) v4[k] = sp_fma(h, a3[k], r.v[k]);
-    touched += rhs<T, PHASE, AUX64>(F, cc, sp_fma(h, v3[0], r.p[0]), sp_fma(h, v3[1], r.p[1]),
-                                    sp_fma(h, v3[2], r.p[2]), a4[0], a4[1], a4[2], n4);
+                                    sp_fma(hh, r.v[2], r.p[2]), a[0], a[1], a[2], n);
+    T pn[3];
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const T sp_ = ((r.v[k] + (T)2 * v2[k]) + (T)2 * v3[k]) + v4[k];
-        const T sv_ = ((a1[k] + (T)2 * a2[k]) + (T)2 * a3[k]) + a4[k];
-        r.p[k] = sp_fma(h6, sp_, r.p[k]);
-        r.v[k] = sp_fma(h6, sv_, r.v[k]);
+        sv[k] = sv[k] + (T)2 * a[k]; sp[k] = sp[k] + (T)2 * vs[k];
+        pn[k] = sp_fma(hh, vs[k], r.p[k]);            // stage-3 position uses v2
+        vs[k] = sp_fma(hh, a[k], r.v[k]);             // vs = v3
     }
-    if (PHASE) {
-        const T sn = ((n1 + (T)2 * n2) + (T)2 * n3) + n4;
-        r.ph = sp_fma(h6, omega * sn, r.ph);
+    if (PHASE) sn = sn + (T)2 * n;
+    touched += rhs<T, PHASE, AUX64>(F, cc, pn[0], pn[1], pn[2], a[0], a[1], a[2], n);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        sv[k] = sv[k] + (T)2 * a[k]; sp[k] = sp[k] + (T)2 * vs[k];
+        pn[k] = sp_fma(h, vs[k], r.p[k]);             // stage-4 position uses v3
+        vs[k] = sp_fma(h, a[k], r.v[k]);              // vs = v4
     }
+    if (PHASE) sn = sn + (T)2 * n;
+    touched += rhs<T, PHASE, AUX64>(F, cc, pn[0], pn[1], pn[2], a[0], a[1], a[2], n);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        r.p[k] = sp_fma(h6, sp[k] + vs[k], r.p[k]);
+        r.v[k] = sp_fma(h6, sv[k] + a[k], r.v[k]);
+    }
+    if (PHASE) r.ph = sp_fma(h6, omega * (sn + n), r.ph);
     return touched;
 }
 

@@ -282,6 +282,9 @@ extern "C" int sp_field_export_gradients(const sp_field* f, float* gx_dev, float
 }
 
 // -------------------------------------------------------------------------------------- detector channels
+#ifndef SP_RK4_MIN_BLOCKS
+#define SP_RK4_MIN_BLOCKS 3
+#endif
 #define SP_MAX_OPS 16
 #define SP_MAX_CHANNELS 4
 
@@ -433,7 +436,7 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 }
 
 template <typename T, int METHOD, bool PHASE, bool AUX64>
-__global__ void __launch_bounds__(128) k_propagate(const PropArgs<T> A, const Epilogue E) {
+__global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 8) ? SP_RK4_MIN_BLOCKS : 1) k_propagate(const PropArgs<T> A, const Epilogue E) {
     const int lane = threadIdx.x & 31;
     LaneStats ls = {0, 0, 0, 0, 0, 0};
     const bool early = (A.flags & SP_FLAG_EARLY_EXIT) != 0;
@@ -465,8 +468,9 @@ __global__ void __launch_bounds__(128) k_propagate(const PropArgs<T> A, const Ep
             if (METHOD == SP_METHOD_RK4) {
                 const T h = A.h;
                 for (int it = 0; it < A.n_steps; ++it) {
-                    if (early && escaped(A.F, r)) break;
-                    ls.evals += rk4_step<T, PHASE, AUX64>(A.F, cc, h, A.omega, r);
+                    const int t = rk4_step<T, PHASE, AUX64>(A.F, cc, h, A.omega, r, early);
+                    if (t < 0) break;
+                    ls.evals += t;
                     ++n_att;
                 }
                 ls.acc += n_att;

@@ -132,10 +132,8 @@ static void rk4_t(const HostField* f, const FieldView<T>& F, const double* s0, u
         r.ph = (T)rd.ph;
         uint32_t it = 0;
         CellCache<T, PH> cc;
-        for (; it < (uint32_t)n_steps; ++it) {
-            if (early && escaped(F, r)) break;
-            rk4_step<T, PH, A64>(F, cc, (T)h, (T)omega, r);
-        }
+        for (; it < (uint32_t)n_steps; ++it)
+            if (rk4_step<T, PH, A64>(F, cc, (T)h, (T)omega, r, early != 0) < 0) break;
         for (int k = 0; k < 3; ++k) { rd.p[k] = r.p[k]; rd.v[k] = r.v[k]; }
         rd.ph = r.ph;
         store(f, sf, s0, n, i, rd);
