@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--cpu-rays-per-worker", type=int, default=1000)
     ap.add_argument("--fp32", action="store_true")
+    ap.add_argument("--ds-frac", type=float, default=0.5, help="RK4 step as a fraction of the cell size along the probing axis")
     return ap.parse_args()
 
 
@@ -175,7 +176,7 @@ def run_reference(a):
 def workload_config(a):
     return {"workload": f"C2: {int(a.rays):d} rays/GPU through a {a.grid}^3 turbulent (k^-11/3) n_e field, "
                         f"shadowgraphy(two-lens) + schlieren(DF) at bin_scale {a.bin_scale}",
-            "grid": a.grid, "rays_per_gpu": int(a.rays), "integrator": "rk4, ds = half a cell, early exit",
+            "grid": a.grid, "rays_per_gpu": int(a.rays), "integrator": f"rk4, ds = {a.ds_frac:g} cell, early exit",
             "precision": "fp32" if a.fp32 else "fp64", "field_bytes": 16 * a.grid ** 3,
             "l2_policy": "inputs larger than L2 (packed field 2.1 GB at 512^3 vs 126 MB L2)",
             "rays": "generated on device (Philox4x32-10), sorted into cell-column bundles" if not a.no_sort else
@@ -203,7 +204,8 @@ def run_ours(a):
     torch.cuda.empty_cache()
     specs = [D.spec("shadow_two", bin_scale=a.bin_scale), D.spec("schlieren_DF", bin_scale=a.bin_scale, R_stop=1)]
     beam = B.Beam(n_rays, BEAM_R, BEAM_DIV, EXTENT, device=True, seed=2, beam_type="circular")
-    kw = dict(lwl=LWL, method="rk4", precision="fp32" if a.fp32 else "fp64", sort=not a.no_sort)
+    kw = dict(lwl=LWL, method="rk4", precision="fp32" if a.fp32 else "fp64", sort=not a.no_sort,
+              ds=a.ds_frac * dom.cell_size())
 
     def one_pass(rays, sync=False):
         for s in specs:

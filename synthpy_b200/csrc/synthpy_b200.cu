@@ -283,7 +283,7 @@ extern "C" int sp_field_export_gradients(const sp_field* f, float* gx_dev, float
 
 // -------------------------------------------------------------------------------------- detector channels
 #ifndef SP_RK4_MIN_BLOCKS
-#define SP_RK4_MIN_BLOCKS 3
+#define SP_RK4_MIN_BLOCKS 4
 #endif
 #define SP_MAX_OPS 16
 #define SP_MAX_CHANNELS 4
