@@ -130,6 +130,23 @@ SP_HD bool unit_interval(float w) {
 #endif
 }
 
+// float32 -> T.  For T = double the default is the hardware conversion (F2F on the quarter-rate XU pipe);
+// -DSP_INT_CVT re-biases the exponent with integer ops on the ALU pipe instead (exact for normal numbers;
+// zero / denormal / inf / nan take the hardware path).
+template <typename T> SP_HD T cvt(float f);
+template <> SP_HD float cvt<float>(float f) { return f; }
+template <> SP_HD double cvt<double>(float f) {
+#if defined(__CUDA_ARCH__) && defined(SP_INT_CVT)
+    const unsigned b = __float_as_uint(f);
+    const unsigned m = b & 0x7fffffffu;
+    if (m - 0x00800000u < 0x7f000000u)
+        return __hiloint2double((int)((b & 0x80000000u) | ((m >> 3) + 0x38000000u)), (int)(b << 29));
+    return (double)f;
+#else
+    return (double)f;
+#endif
+}
+
 // ---- field view --------------------------------------------------------------------------------------
 // Kernel frame: axes (u, v, w) = (m+1, m+2, m) mod 3 of the caller's (x, y, z), m = march (probing) axis;
 // w is the fastest-varying axis of the packed grid, so the two corners a ray needs along its direction of
@@ -173,31 +190,35 @@ template <typename T> SP_HD bool locate(const AxisTab<T>& A, T x, int& i) {
 //     f = a0 + ww a1 + wv (a2 + ww a3) + wu (a4 + ww a5 + wv (a6 + ww a7))
 // (7 fused multiply-adds per component), whose coefficients are corner differences.
 template <typename T, bool PHASE> struct CellCache {
-    T lo[3], hi[3], rinv[3];            // g[i], g[i+1], 1/(g[i+1]-g[i]) of the cached cell, per axis
+    T lo[3], rinv[3];                   // g[i] and 1/(g[i+1]-g[i]) of the cached cell, per axis
     T a[PHASE ? 4 : 3][8];
     int idx[3];
     bool valid;
     SP_HD CellCache() : valid(false) {
-        for (int k = 0; k < 3; ++k) { lo[k] = hi[k] = rinv[k] = (T)0; idx[k] = 0; }
+        for (int k = 0; k < 3; ++k) { lo[k] = rinv[k] = (T)0; idx[k] = 0; }
     }
 };
 
-// Move the cached interval of one axis to the cell containing x.  Common case: the neighbouring cell (one or
-// two table reads); anything else falls back to the exact search.  False = x is outside the grid.
-template <typename T> SP_HD bool relocate_axis(const AxisTab<T>& A, T x, bool valid, int& i, T& lo, T& hi, T& rinv) {
+// Move the cached interval of one axis to the cell containing x.  `w_ok` = the weight test already placed x
+// in the cached cell.  Common case: the neighbouring cell (two table reads, exact comparisons); anything else
+// falls back to the exact search.  False = x is outside the grid.
+template <typename T> SP_HD bool relocate_axis(const AxisTab<T>& A, T x, bool w_ok, bool valid, int& i, T& lo, T& rinv) {
     if (valid) {
-        if (x >= lo && x < hi) return true;
-        if (x >= hi && i + 2 < A.n) {
-            const typename Pair<T>::type e1 = ldg(A.tab + i + 1), e2 = ldg(A.tab + i + 2);
-            if (x < e2.x) { ++i; lo = e1.x; rinv = e1.y; hi = e2.x; return true; }
+        if (w_ok) return true;
+        if (x >= lo) {
+            if (i + 2 < A.n) {
+                const typename Pair<T>::type e1 = ldg(A.tab + i + 1), e2 = ldg(A.tab + i + 2);
+                if (x < e1.x) return true;                       // weight rounded up to 1: still this cell
+                if (x < e2.x) { ++i; lo = e1.x; rinv = e1.y; return true; }
+            }
         } else if (x < lo && i > 0) {
             const typename Pair<T>::type e0 = ldg(A.tab + i - 1);
-            if (x >= e0.x) { --i; hi = lo; lo = e0.x; rinv = e0.y; return true; }
+            if (x >= e0.x) { --i; lo = e0.x; rinv = e0.y; return true; }
         }
     }
     if (!locate(A, x, i)) return false;
     const typename Pair<T>::type e = ldg(A.tab + i);
-    lo = e.x; rinv = e.y; hi = ldg(A.tab + i + 1).x;
+    lo = e.x; rinv = e.y;
     return true;
 }
 
@@ -230,29 +251,30 @@ template <typename T> SP_HD T tri_eval(const T* a, T wu, T wv, T ww) {
 template <typename T, bool PHASE, bool AUX64>
 SP_HD bool rhs(const FieldView<T>& F, CellCache<T, PHASE>& cc, T pu, T pv, T pw, T& au, T& av, T& aw, T& nm1) {
     T wu = (pu - cc.lo[0]) * cc.rinv[0], wv = (pv - cc.lo[1]) * cc.rinv[1], ww = (pw - cc.lo[2]) * cc.rinv[2];
-    if (!(cc.valid && unit_interval(wu) && unit_interval(wv) && unit_interval(ww))) {
+    const bool oku = unit_interval(wu), okv = unit_interval(wv), okw = unit_interval(ww);
+    if (!(cc.valid && oku && okv && okw)) {
         au = av = aw = nm1 = (T)0;
         const bool v = cc.valid;
         cc.valid = false;
-        if (!relocate_axis(F.ax[0], pu, v, cc.idx[0], cc.lo[0], cc.hi[0], cc.rinv[0])) return false;
-        if (!relocate_axis(F.ax[1], pv, v, cc.idx[1], cc.lo[1], cc.hi[1], cc.rinv[1])) return false;
-        if (!relocate_axis(F.ax[2], pw, v, cc.idx[2], cc.lo[2], cc.hi[2], cc.rinv[2])) return false;
+        if (!relocate_axis(F.ax[0], pu, oku, v, cc.idx[0], cc.lo[0], cc.rinv[0])) return false;
+        if (!relocate_axis(F.ax[1], pv, okv, v, cc.idx[1], cc.lo[1], cc.rinv[1])) return false;
+        if (!relocate_axis(F.ax[2], pw, okw, v, cc.idx[2], cc.lo[2], cc.rinv[2])) return false;
         const long long base = (long long)cc.idx[0] * F.su + (long long)cc.idx[1] * F.sv + cc.idx[2];
         const f4* p = F.data + base;
         const f4 c000 = ldg(p), c001 = ldg(p + 1);
         const f4 c010 = ldg(p + F.sv), c011 = ldg(p + F.sv + 1);
         const f4 c100 = ldg(p + F.su), c101 = ldg(p + F.su + 1);
         const f4 c110 = ldg(p + F.su + F.sv), c111 = ldg(p + F.su + F.sv + 1);
-        tri_coef<T>((T)c000.x, (T)c001.x, (T)c010.x, (T)c011.x, (T)c100.x, (T)c101.x, (T)c110.x, (T)c111.x, cc.a[0]);
-        tri_coef<T>((T)c000.y, (T)c001.y, (T)c010.y, (T)c011.y, (T)c100.y, (T)c101.y, (T)c110.y, (T)c111.y, cc.a[1]);
-        tri_coef<T>((T)c000.z, (T)c001.z, (T)c010.z, (T)c011.z, (T)c100.z, (T)c101.z, (T)c110.z, (T)c111.z, cc.a[2]);
+        tri_coef<T>(cvt<T>(c000.x), cvt<T>(c001.x), cvt<T>(c010.x), cvt<T>(c011.x), cvt<T>(c100.x), cvt<T>(c101.x), cvt<T>(c110.x), cvt<T>(c111.x), cc.a[0]);
+        tri_coef<T>(cvt<T>(c000.y), cvt<T>(c001.y), cvt<T>(c010.y), cvt<T>(c011.y), cvt<T>(c100.y), cvt<T>(c101.y), cvt<T>(c110.y), cvt<T>(c111.y), cc.a[1]);
+        tri_coef<T>(cvt<T>(c000.z), cvt<T>(c001.z), cvt<T>(c010.z), cvt<T>(c011.z), cvt<T>(c100.z), cvt<T>(c101.z), cvt<T>(c110.z), cvt<T>(c111.z), cc.a[2]);
         if (PHASE) {
             if (AUX64) {
                 const double* q = F.aux64 + base;
                 tri_coef<T>((T)ldg(q), (T)ldg(q + 1), (T)ldg(q + F.sv), (T)ldg(q + F.sv + 1), (T)ldg(q + F.su),
                             (T)ldg(q + F.su + 1), (T)ldg(q + F.su + F.sv), (T)ldg(q + F.su + F.sv + 1), cc.a[PHASE ? 3 : 0]);
             } else {
-                tri_coef<T>((T)c000.w, (T)c001.w, (T)c010.w, (T)c011.w, (T)c100.w, (T)c101.w, (T)c110.w, (T)c111.w,
+                tri_coef<T>(cvt<T>(c000.w), cvt<T>(c001.w), cvt<T>(c010.w), cvt<T>(c011.w), cvt<T>(c100.w), cvt<T>(c101.w), cvt<T>(c110.w), cvt<T>(c111.w),
                             cc.a[PHASE ? 3 : 0]);
             }
         }

@@ -438,9 +438,9 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 template <typename T, int METHOD, bool PHASE, bool AUX64>
 __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 8) ? SP_RK4_MIN_BLOCKS : 1) k_propagate(const PropArgs<T> A, const Epilogue E) {
     const int lane = threadIdx.x & 31;
-    LaneStats ls = {0, 0, 0, 0, 0, 0};
     const bool early = (A.flags & SP_FLAG_EARLY_EXIT) != 0;
     for (;;) {
+        LaneStats ls = {0, 0, 0, 0, 0, 0};      // per bundle: nothing but the ray itself is live across the integration
         unsigned long long slot0 = 0;
         if (lane == 0) slot0 = atomicAdd(A.cursor, 32ull);
         slot0 = __shfl_sync(0xffffffffu, slot0, 0);
@@ -450,10 +450,10 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
         const uint64_t li = valid ? (A.order ? (uint64_t)A.order[slot] : slot) : 0;
         const uint64_t gi = A.chunk_off + li;         // index into the caller's arrays
         double s[6];
-        double amp = 1.0, ph0 = 0.0, pol = 0.0;
+        double ph0 = 0.0;
         if (valid) {
             load_ray_caller(A.s0, A.n_total, gi, A.beam, A.use_beam, A.ray_offset, s);
-            if (!A.use_beam) { amp = A.s0[6 * A.n_total + gi]; ph0 = A.s0[7 * A.n_total + gi]; pol = A.s0[8 * A.n_total + gi]; }
+            if (!A.use_beam) ph0 = A.s0[7 * A.n_total + gi];
         } else {
 #pragma unroll
             for (int k = 0; k < 6; ++k) s[k] = 0.0;
@@ -478,8 +478,9 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
                 // SciPy RK45 driven as solve_ivp does (rk.py:_step_impl), one controller per ray
                 Deriv<T> f; int touched = 0;
                 touched += deriv<T, PHASE, AUX64>(A.F, cc, A.omega, r.p, r.v, f);
-                T h_abs = dp5_initial_step<T, PHASE, AUX64>(A.F, cc, A.omega, A.t_end, A.rtol, A.atol, A.n_state, (T)amp,
-                                                            (T)pol, r, f, touched);
+                const double amp0 = A.use_beam ? 1.0 : A.s0[6 * A.n_total + gi], pol0 = A.use_beam ? 0.0 : A.s0[8 * A.n_total + gi];
+                T h_abs = dp5_initial_step<T, PHASE, AUX64>(A.F, cc, A.omega, A.t_end, A.rtol, A.atol, A.n_state, (T)amp0,
+                                                            (T)pol0, r, f, touched);
                 T t = (T)0;
                 const unsigned cap = A.n_steps > 0 ? (unsigned)A.n_steps : (1u << 30);
                 const T inv_n = (T)1 / (T)A.n_state;
@@ -517,6 +518,8 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
         T xa = 0, tha = 0, xb = 0, thb = 0;
         if (valid) exit_project<T>(r, A.kp, A.ka, A.kb, A.extent, xa, tha, xb, thb);
         const uint64_t N = A.n_total;
+        double amp = 1.0, pol = 0.0;              // constant along the ray (zero derivative): re-read instead of kept live
+        if (valid && !A.use_beam) { amp = A.s0[6 * N + gi]; pol = A.s0[8 * N + gi]; }
         if (valid) {
             if (E.sf) {
 #pragma unroll
@@ -553,8 +556,7 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
                 ls.rejected += (valid && !d.alive) ? 1 : 0;
             }
         }
-    }
-    if (A.stats) {
+        if (A.stats) {
         const unsigned long long a = warp_sum(ls.steps), b = warp_sum(ls.acc), c = warp_sum(ls.capped),
                                  d = warp_sum(ls.binned), e = warp_sum(ls.rejected), f = warp_sum(ls.evals);
         if (lane == 0) {
@@ -564,6 +566,7 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
             if (d) atomicAdd((unsigned long long*)&A.stats->rays_binned, d);
             if (e) atomicAdd((unsigned long long*)&A.stats->rays_rejected, e);
             if (f) atomicAdd((unsigned long long*)&A.stats->rhs_evals, f);
+        }
         }
     }
 }

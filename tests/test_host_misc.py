@@ -1,0 +1,66 @@
+"""CPU tests of host-side pieces that need no GPU: field generator restatement, Beam host RNG stream, API shapes,
+bench.py's reference arm contract."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_field_generator_matches_reference_realisation(golden):
+    """synthpy_b200.field_generator.domain_fft (torch FFT) reproduces the field the reference's
+    gaussian3D.domain_fft produced for np.random.seed(1) (stored in tests/golden/g3_turb.npz)."""
+    from synthpy_b200 import field_generator as fg
+    g = golden("g3_turb")
+    np.random.seed(1)
+    ne = fg.turbulent_ne(16, noise="numpy", device="cpu").numpy()
+    assert ne.shape == g["ne"].shape
+    assert np.max(np.abs(ne - g["ne"])) < 1e-6 * np.abs(g["ne"]).max()
+    a = fg.turbulent_ne(8, noise="torch", seed=5, device="cpu")
+    b = fg.turbulent_ne(8, noise="torch", seed=5, device="cpu")
+    assert bool((a == b).all()) and float(a.min()) > 0
+
+
+def test_beam_host_stream_and_shapes():
+    from synthpy_b200 import beam as B, legacy
+    b = B.Beam(1000, 5e-3, 5e-5, 10e-3, seeded=True)
+    assert b.s0.shape == (9, 1000) and np.all(b.s0[2] == -10e-3) and np.all(b.s0[6] == 1.0)
+    # seeded draws re-seed before every draw (utils.py:8-24): t, u and chi come from the same stream start
+    np.random.seed(0)
+    t = 2 * np.pi * np.random.rand(1000)
+    np.random.seed(0)
+    u = np.random.power(2, 1000)
+    assert np.allclose(b.s0[0], 5e-3 * u * np.cos(t)) and np.allclose(b.s0[1], 5e-3 * u * np.sin(t))
+    for pd, row in (("x", 0), ("y", 1), ("z", 2)):
+        bb = B.Beam(64, 1e-3, 1e-4, 2e-3, probing_direction=pd)
+        assert np.all(bb.s0[row] == -2e-3) and np.allclose(np.linalg.norm(bb.s0[3:6], axis=0), 299792458.0)
+    np.random.seed(3)
+    s0 = legacy.init_beam(50, (1e-3, 2e-3), 1e-4, 5e-3, "rectangular", "z")
+    assert np.abs(s0[0]).max() <= 1e-3 and np.abs(s0[1]).max() <= 2e-3
+    d = B.Beam(10, 5e-3, 5e-5, 10e-3, device=True, seed=3)
+    assert d.s0 is None and d.spec.start == -10e-3
+
+
+def test_domain_api_shapes():
+    from synthpy_b200 import domain as D
+    dom = D.ScalarDomain([10e-3, 10e-3, 20e-3], [16, 12, 20], ne_type="test_exponential_cos")
+    assert dom.ne.shape == (16, 12, 20) and dom.x.dtype == np.float32 and dom.region_count == 1
+    assert np.array_equal(dom.z, np.float32(np.linspace(-10e-3, 10e-3, 20)))
+    assert abs(dom.cell_size() - 20e-3 / 19) < 1e-18
+    dom2 = D.ScalarDomain(1e-2, 8)
+    dom2.test_slab(s=2)
+    assert dom2.ne.shape == (8, 8, 8) and np.all(np.diff(dom2.ne[:, 0, 0]) > 0)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` prints one JSON line with the agreed keys (tiny grid so it runs in seconds)."""
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--grid", "32", "--steps", "1",
+                          "--warmup", "1", "--cpu-rays-per-worker", "40"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "rays*steps/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
