@@ -725,8 +725,18 @@ __global__ void k_joint_finish(JointBuf B, uint64_t n, int use_new, int p0, int 
 }
 
 // ------------------------------------------------------------------------------------ stand-alone kernels
+// SMEM_HIST: the image is small enough (<= 12 Ki bins) for a CTA-private uint32 histogram in shared memory:
+// lanes that hit the same pixel are aggregated in the warp (__match_any_sync), one shared-memory atomic per
+// distinct pixel, and each CTA flushes its non-zero bins to the global uint64 image once at the end.
+template <bool SMEM_HIST>
 __global__ void k_optics_image(const double* __restrict__ rf, const double* __restrict__ jf, uint64_t n,
                                const ChannelDev ch, double* __restrict__ rf_out, double* __restrict__ jf_out) {
+    extern __shared__ unsigned int s_hist[];
+    const int nbins = ch.nx * ch.ny;
+    if (SMEM_HIST) {
+        for (int i = threadIdx.x; i < nbins; i += blockDim.x) s_hist[i] = 0u;
+        __syncthreads();
+    }
     const uint64_t i0 = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
     const uint64_t n_round = (n + 31) / 32 * 32;      // keep warps converged for __match_any_sync
@@ -752,7 +762,26 @@ __global__ void k_optics_image(const double* __restrict__ rf, const double* __re
                 jf_out[2 * (n + i)] = d.alive ? d.ey_re : nanv; jf_out[2 * (n + i) + 1] = d.alive ? d.ey_im : nanv;
             }
         }
-        if (ch.nx > 0) bin_ray(ch, d, valid);
+        if (ch.nx > 0) {
+            if (SMEM_HIST) {
+                int pix = -1;
+                if (valid && d.alive) {
+                    const int ix = bin_index(d.x, ch.x_lo, ch.x_hi, ch.nx, true), iy = bin_index(d.y, ch.y_lo, ch.y_hi, ch.ny, true);
+                    if (ix >= 0 && iy >= 0) pix = iy * ch.nx + ix;
+                }
+                const unsigned peers = __match_any_sync(__activemask(), pix);
+                if (pix >= 0 && (__ffs(peers) - 1) == (int)(threadIdx.x & 31)) atomicAdd(s_hist + pix, (unsigned)__popc(peers));
+            } else {
+                bin_ray(ch, d, valid);
+            }
+        }
+    }
+    if (SMEM_HIST) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nbins; i += blockDim.x) {
+            const unsigned c = s_hist[i];
+            if (c) atomicAdd(ch.counts + i, (unsigned long long)c);
+        }
     }
 }
 
@@ -1162,8 +1191,15 @@ extern "C" int sp_optics_image(const double* rf_dev, const double* jf_dev, uint6
     if (rc) return rc;
     if (ch.kind == SP_IMG_INTERFEROGRAM && ch.nx > 0 && !jf_dev) return fail(SP_EINVAL, "interferogram needs Jones vectors");
     uint64_t blocks = (n + 255) / 256;
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    k_optics_image<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rf_dev, jf_dev, n, ch, rf_out_dev, jf_out_dev);
+    const size_t nbins = (size_t)ch.nx * ch.ny;
+    if (ch.kind == SP_IMG_HISTOGRAM && nbins > 0 && nbins <= 12288) {
+        if (blocks > 148 * 4) blocks = 148 * 4;           // few, fat CTAs: each flushes its private image once
+        k_optics_image<true><<<(unsigned)blocks, 256, nbins * sizeof(unsigned), (cudaStream_t)stream>>>(rf_dev, jf_dev, n, ch,
+                                                                                                     rf_out_dev, jf_out_dev);
+    } else {
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        k_optics_image<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rf_dev, jf_dev, n, ch, rf_out_dev, jf_out_dev);
+    }
     LAUNCH_CHECK();
     return SP_OK;
 }

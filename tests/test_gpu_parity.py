@@ -188,6 +188,9 @@ def test_optics_and_histograms(sp, golden):
             assert o.H.shape == ref.shape and o.H.sum() == ref.sum()           # total counts exact
             assert np.abs(o.H - ref).sum() <= 1e-3 * ref.sum()                 # L1 per image
             assert np.array_equal(o.H, ref)                                    # in fact identical here
+        # coarse image: shared-memory privatised histogram path (<= 12 Ki bins)
+        o.histogram(bin_scale=32)
+        assert np.array_equal(o.H, O.histogram(g[tag + "_rf"], bin_scale=32)), tag
 
 
 def test_element_functions(sp, golden):
