@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--no-sort", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-rays-per-worker", type=int, default=1000)
+    ap.add_argument("--cpu-rays-per-worker", type=int, default=6000)
     ap.add_argument("--fp32", action="store_true")
     ap.add_argument("--ds-frac", type=float, default=0.5, help="RK4 step as a fraction of the cell size along the probing axis")
     return ap.parse_args()
@@ -120,6 +120,17 @@ def _cpu_worker(args):
     return n * (sol.nfev - 2) / 6.0, time.perf_counter() - t0
 
 
+def _pool_init():
+    """One BLAS/OpenMP thread per worker process: the pool already uses every core (the reference's own
+    config pins threads to 1 as well, src/simulator/config.py:80-122); without this np.dot inside solve_ivp
+    oversubscribes the box and timings become erratic."""
+    try:
+        from threadpoolctl import threadpool_limits
+        _CPU["tp"] = threadpool_limits(1)
+    except Exception:
+        pass
+
+
 def cpu_setup(ne_host, grid):
     from oracle import synthpy_oracle as O
     x, y, z = (np.linspace(-L / 2, L / 2, grid) for L in LENGTHS)
@@ -152,7 +163,7 @@ def run_reference(a):
     cpu_setup(ne, a.grid)
     del ne
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
+    with ctx.Pool(cores, initializer=_pool_init) as pool:
         for w in range(a.warmup):
             cpu_pass(pool, cores, max(8, a.cpu_rays_per_worker // 8), 1000 + 100 * w)
         t0 = time.perf_counter()
@@ -318,7 +329,7 @@ def cpu_baseline(a, dom):
     cpu_setup(ne, a.grid)
     del ne
     ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
+    with ctx.Pool(cores, initializer=_pool_init) as pool:
         cpu_pass(pool, cores, 8, 100)
         units, wall = cpu_pass(pool, cores, a.cpu_rays_per_worker, 200)
     return {"value": units / wall, "unit": "rays*steps/s", "cores": cores, "kind": "port",

@@ -196,6 +196,8 @@ template <typename T, bool PHASE> struct CellCache {
     bool valid;
     SP_HD CellCache() : valid(false) {
         for (int k = 0; k < 3; ++k) { lo[k] = rinv[k] = (T)0; idx[k] = 0; }
+        for (int c = 0; c < (PHASE ? 4 : 3); ++c)
+            for (int k = 0; k < 8; ++k) a[c][k] = (T)0;
     }
 };
 
