@@ -47,6 +47,11 @@ def parse():
     ap.add_argument("--cpu-rays-per-worker", type=int, default=6000)
     ap.add_argument("--fp32", action="store_true")
     ap.add_argument("--ds-frac", type=float, default=0.5, help="RK4 step as a fraction of the cell size along the probing axis")
+    ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4"],
+                    help="C2 shadowgraphy+schlieren (default, the headline); C3 interferometry with phase accumulation; "
+                         "C4 refractometry + knife-edge schlieren with adaptive RK45")
+    ap.add_argument("--rtol", type=float, default=1e-3)
+    ap.add_argument("--atol", type=float, default=1e-6)
     return ap.parse_args()
 
 
@@ -185,9 +190,13 @@ def run_reference(a):
 
 
 def workload_config(a):
-    return {"workload": f"C2: {int(a.rays):d} rays/GPU through a {a.grid}^3 turbulent (k^-11/3) n_e field, "
-                        f"shadowgraphy(two-lens) + schlieren(DF) at bin_scale {a.bin_scale}",
-            "grid": a.grid, "rays_per_gpu": int(a.rays), "integrator": f"rk4, ds = {a.ds_frac:g} cell, early exit",
+    diag = {"C2": "shadowgraphy(two-lens) + schlieren(DF)", "C3": "interferometry(two-lens, phase accumulation, reference beam)",
+            "C4": "refractometry(incoherent) + knife-edge schlieren"}[a.workload]
+    integ = (f"rk4, ds = {a.ds_frac:g} cell, early exit" if a.workload != "C4" else
+             f"rk45 per ray (SciPy controller), rtol {a.rtol:g} atol {a.atol:g}, early exit")
+    return {"workload": f"{a.workload}: {int(a.rays):d} rays/GPU through a {a.grid}^3 turbulent (k^-11/3) n_e field, "
+                        f"{diag} at bin_scale {a.bin_scale}",
+            "grid": a.grid, "rays_per_gpu": int(a.rays), "integrator": integ,
             "precision": "fp32" if a.fp32 else "fp64", "field_bytes": 16 * a.grid ** 3,
             "l2_policy": "inputs larger than L2 (packed field 2.1 GB at 512^3 vs 126 MB L2)",
             "rays": "generated on device (Philox4x32-10), sorted into cell-column bundles" if not a.no_sort else
@@ -213,10 +222,18 @@ def run_ours(a):
     dom.device_field(LWL)
     del ne
     torch.cuda.empty_cache()
-    specs = [D.spec("shadow_two", bin_scale=a.bin_scale), D.spec("schlieren_DF", bin_scale=a.bin_scale, R_stop=1)]
-    beam = B.Beam(n_rays, BEAM_R, BEAM_DIV, EXTENT, device=True, seed=2, beam_type="circular")
     kw = dict(lwl=LWL, method="rk4", precision="fp32" if a.fp32 else "fp64", sort=not a.no_sort,
               ds=a.ds_frac * dom.cell_size())
+    if a.workload == "C2":
+        specs = [D.spec("shadow_two", bin_scale=a.bin_scale), D.spec("schlieren_DF", bin_scale=a.bin_scale, R_stop=1)]
+    elif a.workload == "C3":       # BASELINE configs[2]: phase accumulation + 2-D interferogram (reference beam 10 fringes, 20 deg)
+        specs = [D.spec("interf_two", bin_scale=a.bin_scale, interferogram=True, wavelength=LWL, ref_beam=(10, 20))]
+    else:                          # BASELINE configs[3]: refractometry + knife-edge schlieren, adaptive RK45 (SciPy controller)
+        specs = [D.spec("refracto_incoherent", bin_scale=a.bin_scale),
+                 D.spec("schlieren_knife", bin_scale=a.bin_scale, offset=0.1, axis=2, direction=1)]
+        kw.update(method="rk45", rtol=a.rtol, atol=a.atol, max_steps=1000000)
+        kw.pop("ds")
+    beam = B.Beam(n_rays, BEAM_R, BEAM_DIV, EXTENT, device=True, seed=2, beam_type="circular")
 
     def one_pass(rays, sync=False):
         for s in specs:
@@ -224,7 +241,8 @@ def run_ours(a):
         st, _ = P.solve_and_image(dom, rays, EXTENT, specs, n_rays=n_rays, ray_offset=rank * n_rays, sync=False, **kw)
         if world > 1:                         # the path's one exchange: sum of detector images
             for s in specs:
-                dist.all_reduce(s.image.counts, op=dist.ReduceOp.SUM)
+                for t_ in s.image.tensors():
+                    dist.all_reduce(t_, op=dist.ReduceOp.SUM)
         return st
 
     def barrier():
@@ -263,13 +281,13 @@ def run_ours(a):
     if not a.no_e2e:
         s0_host = beam.materialise(n_rays, rank * n_rays).cpu().pin_memory()
         s0_dev = torch.empty_like(s0_host, device="cuda")
-        outs = [torch.empty(s.image.counts.shape, dtype=torch.int64).pin_memory() for s in specs]
+        outs = [torch.empty(s.image.tensors()[0].shape, dtype=s.image.tensors()[0].dtype).pin_memory() for s in specs]
 
         def e2e_pass():
             s0_dev.copy_(s0_host, non_blocking=True)
             st_ = one_pass(s0_dev)
             for o, s in zip(outs, specs):
-                o.copy_(s.image.counts, non_blocking=True)
+                o.copy_(s.image.tensors()[0], non_blocking=True)
             return st_
         e2e_pass()
         barrier()
@@ -295,13 +313,17 @@ def run_ours(a):
     per_launch_steps = steps_per_pass * a.steps / max(1, klaunch)
     achieved = per_launch_steps * BYTES_PER_RAY_STEP / (kms / max(1, klaunch) * 1e-3) / 1e9 if kms > 0 else None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
-            "traffic": None, "kernel": "k_propagate<double, RK4>", "kernel_ms_per_launch": kms / max(1, klaunch),
+            "traffic": None, "kernel": "k_propagate<%s, %s>" % ("float" if a.fp32 else "double", "RK45" if a.workload == "C4" else "RK4"), "kernel_ms_per_launch": kms / max(1, klaunch),
             "kernel_share_of_step": kms / ms if ms > 0 else None, "peak_source": peak_src,
             "note": "achieved = algorithmic gather bytes (512 B per ray-step) / event-timed kernel duration; "
                     "gathers are served mostly by L1/L2 (rays are bundled per cell column), so frac may exceed 1; "
                     "see profiles/ for dram__bytes and L2 hit rate"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
-    if os.path.exists(traffic_file):
+    roof["bytes_per_ray_step"] = 768 if a.workload == "C4" else 512
+    if a.workload == "C4" and achieved:
+        roof["achieved"] = achieved * 768 / 512
+        roof["frac"] = roof["achieved"] / peak
+    if os.path.exists(traffic_file) and a.workload == "C2" and a.grid == 512 and n_rays == int(1e7) and not a.fp32:
         try:
             roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
         except Exception:
