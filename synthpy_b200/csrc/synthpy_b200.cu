@@ -282,6 +282,9 @@ extern "C" int sp_field_export_gradients(const sp_field* f, float* gx_dev, float
 }
 
 // -------------------------------------------------------------------------------------- detector channels
+#ifndef SP_RK45_MIN_BLOCKS
+#define SP_RK45_MIN_BLOCKS 3
+#endif
 #ifndef SP_RK4_MIN_BLOCKS
 #define SP_RK4_MIN_BLOCKS 4
 #endif
@@ -436,7 +439,7 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 }
 
 template <typename T, int METHOD, bool PHASE, bool AUX64>
-__global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 8) ? SP_RK4_MIN_BLOCKS : 1) k_propagate(const PropArgs<T> A, const Epilogue E) {
+__global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 8) ? SP_RK4_MIN_BLOCKS : ((METHOD == SP_METHOD_RK45 && sizeof(T) == 8) ? SP_RK45_MIN_BLOCKS : 1)) k_propagate(const PropArgs<T> A, const Epilogue E) {
     const int lane = threadIdx.x & 31;
     const bool early = (A.flags & SP_FLAG_EARLY_EXIT) != 0;
     for (;;) {
