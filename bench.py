@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--no-sort", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--cpu-rays-per-worker", type=int, default=6000)
+    ap.add_argument("--cpu-rays-per-worker", type=int, default=4000)
     ap.add_argument("--fp32", action="store_true")
     ap.add_argument("--ds-frac", type=float, default=0.5, help="RK4 step as a fraction of the cell size along the probing axis")
     ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4"],

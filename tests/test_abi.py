@@ -58,3 +58,30 @@ def test_no_cpu_fallback():
         dom = domain.ScalarDomain([1e-2, 1e-2, 2e-2], 8, ne_type="test_null")
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             propagator.solve(np.zeros((9, 4)), dom, 1e-2)
+
+
+def test_error_codes_without_touching_the_gpu():
+    """Argument validation happens before any CUDA call: every entry point returns a negative code and
+    sp_last_error() explains it (no exceptions across the boundary)."""
+    import ctypes as C
+    from synthpy_b200 import _lib as L
+    lib = L.lib
+    P = L.Params(method=0, n_steps=10, h=1e-12, probing_axis=2, out_axis_a=0, out_axis_b=1)
+    assert lib.sp_propagate(None, C.byref(P), None, None, None, 10, 0, None, None, None, None, None, 0, None, None) == -1
+    assert b"null" in lib.sp_last_error()
+    h = C.c_void_p()
+    ax = (C.c_float * 2)(0.0, 1.0)
+    bad = (C.c_float * 1)(0.0)
+    assert lib.sp_field_create(C.byref(h), C.c_void_p(8), 1, ax, ax, bad, 2, 2, 1, 1.0, 2, 0, None) == -1
+    assert b"at least 2" in lib.sp_last_error()
+    assert lib.sp_field_create(C.byref(h), None, 1, ax, ax, ax, 2, 2, 2, 1.0, 2, 0, None) == -1
+    assert lib.sp_field_create(C.byref(h), C.c_void_p(8), 1, ax, ax, ax, 2, 2, 2, 1.0, 7, 0, None) == -1
+    assert b"march_axis" in lib.sp_last_error()
+    assert lib.sp_rhs(None, None, None, 0, None, None) == -1
+    assert lib.sp_optics_image(None, None, 0, None, None, None, None) == -1
+    assert lib.sp_beam_generate(None, 0, 0, None, None) == -1
+    assert lib.sp_image_finalize(None, None, None) == -1
+    assert lib.sp_field_destroy(None) == 0 and lib.sp_workspace_destroy(None) == 0
+    import pytest
+    with pytest.raises(L.SynthpyB200Error, match="synthpy_b200 error -1"):
+        L.check(lib.sp_rhs(None, None, None, 0, None, None))
