@@ -268,15 +268,6 @@ SP_HD bool rhs(const FieldView<T>& F, CellCache<T, PHASE>& cc, T pu, T pv, T pw,
             // prepared field: the cell's polynomial was built once per cell at field creation (same tri_coef
             // arithmetic, so the coefficients are bit-identical to the on-the-fly path): 192 contiguous bytes
             const d2* q = reinterpret_cast<const d2*>(F.coef + base * F.coef_stride);
-#if defined(__CUDA_ARCH__)
-            // the ray will enter the next cell along the march axis ~8 evaluations from now: pull its
-            // coefficients into L1 so that reload is an L1 hit instead of an L2 round trip
-            {
-                const char* nxt = reinterpret_cast<const char*>(q) + (size_t)F.coef_stride * 8;
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(nxt + 128));
-            }
-#endif
 #pragma unroll
             for (int c = 0; c < (PHASE ? 4 : 3); ++c) {
 #pragma unroll
