@@ -47,7 +47,6 @@ def parse():
     ap.add_argument("--cpu-rays-per-worker", type=int, default=4000)
     ap.add_argument("--fp32", action="store_true")
     ap.add_argument("--ds-frac", type=float, default=0.5, help="RK4 step as a fraction of the cell size along the probing axis")
-    ap.add_argument("--no-prepare", action="store_true", help="do not precompute per-cell coefficients (SP_FIELD_COEF)")
     ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4"],
                     help="C2 shadowgraphy+schlieren (default, the headline); C3 interferometry with phase accumulation; "
                          "C4 refractometry + knife-edge schlieren with adaptive RK45")
@@ -199,7 +198,6 @@ def workload_config(a):
                         f"{diag} at bin_scale {a.bin_scale}",
             "grid": a.grid, "rays_per_gpu": int(a.rays), "integrator": integ,
             "precision": "fp32" if a.fp32 else "fp64", "field_bytes": 16 * a.grid ** 3,
-            "prepared_cells": getattr(a, "prepared", None),
             "l2_policy": "inputs larger than L2 (packed field 2.1 GB at 512^3 vs 126 MB L2)",
             "rays": "generated on device (Philox4x32-10), sorted into cell-column bundles" if not a.no_sort else
                     "generated on device, unsorted"}
@@ -221,10 +219,7 @@ def run_ours(a):
     ne = build_ne(a.grid, "cuda")
     dom = Dm.ScalarDomain(LENGTHS, a.grid)
     dom.external_ne(ne)
-    need_phase = a.workload == "C3"
-    fld = dom.device_field(LWL, phase=need_phase, prepare_cells=False if a.no_prepare else "auto")
-    a.prepared = bool(fld.prepare_cells(False if a.no_prepare else "auto"))
-    a.field_bytes_total = fld.nbytes
+    dom.device_field(LWL)
     del ne
     torch.cuda.empty_cache()
     kw = dict(lwl=LWL, method="rk4", precision="fp32" if a.fp32 else "fp64", sort=not a.no_sort,

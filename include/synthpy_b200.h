@@ -45,9 +45,6 @@ typedef struct sp_field sp_field; /* opaque: packed float4 {g_u, g_v, g_w, aux} 
 /* sp_field_create flags */
 #define SP_FIELD_PHASE 1     /* aux lane = float32(n - 1), n = sqrt(1 - (5.64e4 sqrt(ne 1e-6)/omega)^2)           */
 #define SP_FIELD_PHASE_F64 2 /* additionally keep n - 1 as a separate float64 grid (exact phase parity, +64 B/eval) */
-#define SP_FIELD_COEF 4      /* additionally precompute, per CELL, the trilinear polynomial the float64 kernels cache
-                                (192 B/cell, 256 B with phase): 12x the field's footprint, ~1.4x faster propagation.
-                                Results are bit-identical with and without it.  SP_ENOMEM if it does not fit.        */
 
 /*
  * Builds the device field from an electron-density grid.  Replaces ScalarDomain.calc_dndr
@@ -73,11 +70,6 @@ int sp_field_create_from_gradients(sp_field** out, const float* gx_dev, const fl
                                    const float* gz_dev, const float* aux_f32_dev, const double* aux_f64_dev,
                                    const float* ax_x_host, const float* ax_y_host, const float* ax_z_host,
                                    int nx, int ny, int nz, int march_axis, void* stream);
-
-/* Builds the SP_FIELD_COEF coefficient field for an existing handle (no-op if present); sp_field_coef_bytes tells
- * what it will cost so the caller can decide whether it fits. */
-int sp_field_build_coef(sp_field* f, void* stream);
-uint64_t sp_field_coef_bytes(int nx, int ny, int nz, int with_phase);
 
 int sp_field_destroy(sp_field* f);
 

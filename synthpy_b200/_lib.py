@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("SYNTHPY_B200_LIB") or os.path.join(_HERE, "csrc", "libsynthpy_b200.so")   # override: A/B builds
 
 # ---- constants (mirror the header) ---------------------------------------------------------------
-FIELD_PHASE, FIELD_PHASE_F64, FIELD_COEF = 1, 2, 4
+FIELD_PHASE, FIELD_PHASE_F64 = 1, 2
 BEAM_CIRCULAR_FOLD, BEAM_CIRCULAR_POW2, BEAM_SQUARE, BEAM_RECTANGULAR, BEAM_LINEAR = range(5)
 OP_TRAVEL, OP_TRAVEL_NOE, OP_LENS, OP_CIRC_AP, OP_CIRC_STOP, OP_RECT_AP, OP_KNIFE, OP_REF_BEAM = range(8)
 IMG_HISTOGRAM, IMG_INTERFEROGRAM = 0, 1
@@ -63,8 +63,6 @@ EXPORTS = {
     "sp_field_create_from_gradients": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
-    "sp_field_build_coef": (C.c_int, [C.c_void_p, C.c_void_p]),
-    "sp_field_coef_bytes": (C.c_uint64, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "sp_field_destroy": (C.c_int, [C.c_void_p]),
     "sp_field_export_gradients": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sp_field_bytes": (C.c_uint64, [C.c_void_p]),

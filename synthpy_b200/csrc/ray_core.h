@@ -161,8 +161,6 @@ template <typename T> struct AxisTab {
 template <typename T> struct FieldView {
     const f4* data;       // [nu][nv][nw] {g_u, g_v, g_w, aux}
     const double* aux64;  // [nu][nv][nw] n-1 in float64, or nullptr
-    const double* coef;   // optional per-CELL polynomial coefficients [nu][nv][nw][coef_stride] (float64 mode), or nullptr
-    int coef_stride;      // 24 (3 components) or 32 (with the n-1 component) doubles per cell
     AxisTab<T> ax[3];
     long long su;         // element stride of u  (= nv*nw)
     int sv;               // element stride of v  (= nw)
@@ -264,36 +262,22 @@ SP_HD bool rhs(const FieldView<T>& F, CellCache<T, PHASE>& cc, T pu, T pv, T pw,
         if (!relocate_axis(F.ax[1], pv, okv, v, cc.idx[1], cc.lo[1], cc.rinv[1])) return false;
         if (!relocate_axis(F.ax[2], pw, okw, v, cc.idx[2], cc.lo[2], cc.rinv[2])) return false;
         const long long base = (long long)cc.idx[0] * F.su + (long long)cc.idx[1] * F.sv + cc.idx[2];
-        if (sizeof(T) == 8 && F.coef != nullptr) {
-            // prepared field: the cell's polynomial was built once per cell at field creation (same tri_coef
-            // arithmetic, so the coefficients are bit-identical to the on-the-fly path): 192 contiguous bytes
-            const d2* q = reinterpret_cast<const d2*>(F.coef + base * F.coef_stride);
-#pragma unroll
-            for (int c = 0; c < (PHASE ? 4 : 3); ++c) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const d2 e = ldg(q + c * 4 + j);
-                    cc.a[c][2 * j] = (T)e.x; cc.a[c][2 * j + 1] = (T)e.y;
-                }
-            }
-        } else {
-            const f4* p = F.data + base;
-            const f4 c000 = ldg(p), c001 = ldg(p + 1);
-            const f4 c010 = ldg(p + F.sv), c011 = ldg(p + F.sv + 1);
-            const f4 c100 = ldg(p + F.su), c101 = ldg(p + F.su + 1);
-            const f4 c110 = ldg(p + F.su + F.sv), c111 = ldg(p + F.su + F.sv + 1);
-            tri_coef<T>(cvt<T>(c000.x), cvt<T>(c001.x), cvt<T>(c010.x), cvt<T>(c011.x), cvt<T>(c100.x), cvt<T>(c101.x), cvt<T>(c110.x), cvt<T>(c111.x), cc.a[0]);
-            tri_coef<T>(cvt<T>(c000.y), cvt<T>(c001.y), cvt<T>(c010.y), cvt<T>(c011.y), cvt<T>(c100.y), cvt<T>(c101.y), cvt<T>(c110.y), cvt<T>(c111.y), cc.a[1]);
-            tri_coef<T>(cvt<T>(c000.z), cvt<T>(c001.z), cvt<T>(c010.z), cvt<T>(c011.z), cvt<T>(c100.z), cvt<T>(c101.z), cvt<T>(c110.z), cvt<T>(c111.z), cc.a[2]);
-            if (PHASE) {
-                if (AUX64) {
-                    const double* q = F.aux64 + base;
-                    tri_coef<T>((T)ldg(q), (T)ldg(q + 1), (T)ldg(q + F.sv), (T)ldg(q + F.sv + 1), (T)ldg(q + F.su),
-                                (T)ldg(q + F.su + 1), (T)ldg(q + F.su + F.sv), (T)ldg(q + F.su + F.sv + 1), cc.a[PHASE ? 3 : 0]);
-                } else {
-                    tri_coef<T>(cvt<T>(c000.w), cvt<T>(c001.w), cvt<T>(c010.w), cvt<T>(c011.w), cvt<T>(c100.w), cvt<T>(c101.w), cvt<T>(c110.w), cvt<T>(c111.w),
-                                cc.a[PHASE ? 3 : 0]);
-                }
+        const f4* p = F.data + base;
+        const f4 c000 = ldg(p), c001 = ldg(p + 1);
+        const f4 c010 = ldg(p + F.sv), c011 = ldg(p + F.sv + 1);
+        const f4 c100 = ldg(p + F.su), c101 = ldg(p + F.su + 1);
+        const f4 c110 = ldg(p + F.su + F.sv), c111 = ldg(p + F.su + F.sv + 1);
+        tri_coef<T>(cvt<T>(c000.x), cvt<T>(c001.x), cvt<T>(c010.x), cvt<T>(c011.x), cvt<T>(c100.x), cvt<T>(c101.x), cvt<T>(c110.x), cvt<T>(c111.x), cc.a[0]);
+        tri_coef<T>(cvt<T>(c000.y), cvt<T>(c001.y), cvt<T>(c010.y), cvt<T>(c011.y), cvt<T>(c100.y), cvt<T>(c101.y), cvt<T>(c110.y), cvt<T>(c111.y), cc.a[1]);
+        tri_coef<T>(cvt<T>(c000.z), cvt<T>(c001.z), cvt<T>(c010.z), cvt<T>(c011.z), cvt<T>(c100.z), cvt<T>(c101.z), cvt<T>(c110.z), cvt<T>(c111.z), cc.a[2]);
+        if (PHASE) {
+            if (AUX64) {
+                const double* q = F.aux64 + base;
+                tri_coef<T>((T)ldg(q), (T)ldg(q + 1), (T)ldg(q + F.sv), (T)ldg(q + F.sv + 1), (T)ldg(q + F.su),
+                            (T)ldg(q + F.su + 1), (T)ldg(q + F.su + F.sv), (T)ldg(q + F.su + F.sv + 1), cc.a[PHASE ? 3 : 0]);
+            } else {
+                tri_coef<T>(cvt<T>(c000.w), cvt<T>(c001.w), cvt<T>(c010.w), cvt<T>(c011.w), cvt<T>(c100.w), cvt<T>(c101.w), cvt<T>(c110.w), cvt<T>(c111.w),
+                            cc.a[PHASE ? 3 : 0]);
             }
         }
         cc.valid = true;

@@ -51,9 +51,6 @@ struct sp_field {
     int nk[3];         // kernel-frame dims nu, nv, nw
     f4* data = nullptr;
     double* aux64 = nullptr;
-    double* coef = nullptr;    // optional per-cell polynomial coefficients (SP_FIELD_COEF)
-    int coef_ncomp = 0;        // 3, or 4 with the n-1 component
-    int has_aux = 0;           // the aux lane carries n-1
     d2* tab64[3] = {nullptr, nullptr, nullptr};   // kernel-frame axis tables
     f2* tab32[3] = {nullptr, nullptr, nullptr};
     double g0[3], inv_d[3], lo[3], hi[3];         // kernel frame
@@ -64,7 +61,7 @@ struct sp_field {
 template <typename T> static FieldView<T> make_view(const sp_field* f);
 template <> FieldView<double> make_view<double>(const sp_field* f) {
     FieldView<double> V;
-    V.data = f->data; V.aux64 = f->aux64; V.coef = f->coef; V.coef_stride = 8 * f->coef_ncomp;
+    V.data = f->data; V.aux64 = f->aux64;
     for (int k = 0; k < 3; ++k) {
         V.ax[k].tab = f->tab64[k]; V.ax[k].g0 = f->g0[k]; V.ax[k].inv_d = f->inv_d[k];
         V.ax[k].lo = f->lo[k]; V.ax[k].hi = f->hi[k]; V.ax[k].n = f->nk[k];
@@ -74,7 +71,7 @@ template <> FieldView<double> make_view<double>(const sp_field* f) {
 }
 template <> FieldView<float> make_view<float>(const sp_field* f) {
     FieldView<float> V;
-    V.data = f->data; V.aux64 = f->aux64; V.coef = nullptr; V.coef_stride = 0;
+    V.data = f->data; V.aux64 = f->aux64;
     for (int k = 0; k < 3; ++k) {
         V.ax[k].tab = f->tab32[k]; V.ax[k].g0 = (float)f->g0[k]; V.ax[k].inv_d = (float)f->inv_d[k];
         V.ax[k].lo = (float)f->lo[k]; V.ax[k].hi = (float)f->hi[k]; V.ax[k].n = f->nk[k];
@@ -176,69 +173,9 @@ static int pack_grid(long long total) {
     return (int)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b));
 }
 
-// Per-cell trilinear polynomial coefficients (the arithmetic of ray_core.h::tri_coef, so a ray gets bit-identical
-// coefficients whether it builds them on entering the cell or reads them here).  One thread per cell.
-__global__ void k_build_coef(const f4* __restrict__ data, const double* __restrict__ aux64, double* __restrict__ coef,
-                             int ncomp, int nu, int nv, int nw) {
-    const long long total = (long long)nu * nv * nw;
-    const long long su = (long long)nv * nw, sv = nw;
-    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long gstride = (long long)gridDim.x * blockDim.x;
-    for (; t < total; t += gstride) {
-        const int iw = (int)(t % nw);
-        const long long r = t / nw;
-        const int iv = (int)(r % nv), iu = (int)(r / nv);
-        if (iu >= nu - 1 || iv >= nv - 1 || iw >= nw - 1) continue;      // not the lower corner of a cell
-        const f4* p = data + t;
-        const f4 c000 = p[0], c001 = p[1], c010 = p[sv], c011 = p[sv + 1];
-        const f4 c100 = p[su], c101 = p[su + 1], c110 = p[su + sv], c111 = p[su + sv + 1];
-        double a[4][8];
-        tri_coef<double>(c000.x, c001.x, c010.x, c011.x, c100.x, c101.x, c110.x, c111.x, a[0]);
-        tri_coef<double>(c000.y, c001.y, c010.y, c011.y, c100.y, c101.y, c110.y, c111.y, a[1]);
-        tri_coef<double>(c000.z, c001.z, c010.z, c011.z, c100.z, c101.z, c110.z, c111.z, a[2]);
-        if (ncomp == 4) {
-            if (aux64) {
-                const double* q = aux64 + t;
-                tri_coef<double>(q[0], q[1], q[sv], q[sv + 1], q[su], q[su + 1], q[su + sv], q[su + sv + 1], a[3]);
-            } else {
-                tri_coef<double>(c000.w, c001.w, c010.w, c011.w, c100.w, c101.w, c110.w, c111.w, a[3]);
-            }
-        }
-        double2* out = reinterpret_cast<double2*>(coef + t * (8 * ncomp));
-        for (int c = 0; c < ncomp; ++c)
-#pragma unroll
-            for (int j = 0; j < 4; ++j) out[c * 4 + j] = make_double2(a[c][2 * j], a[c][2 * j + 1]);
-    }
-}
-
-static int build_coef(sp_field* f, int with_aux, cudaStream_t st) {
-    const long long cells = (long long)f->nk[0] * f->nk[1] * f->nk[2];
-    f->coef_ncomp = with_aux ? 4 : 3;
-    const size_t bytes = (size_t)cells * 8 * f->coef_ncomp * sizeof(double);
-    if (cudaMalloc(&f->coef, bytes) != cudaSuccess) {
-        cudaGetLastError();
-        f->coef = nullptr; f->coef_ncomp = 0;
-        return fail(SP_ENOMEM, "not enough device memory for the per-cell coefficient field (SP_FIELD_COEF)");
-    }
-    f->bytes += bytes;
-    k_build_coef<<<pack_grid(cells), 256, 0, st>>>(f->data, f->aux64, f->coef, f->coef_ncomp, f->nk[0], f->nk[1], f->nk[2]);
-    LAUNCH_CHECK();
-    return SP_OK;
-}
-
-extern "C" int sp_field_build_coef(sp_field* f, void* stream) {
-    if (!f) return fail(SP_EINVAL, "null field");
-    if (f->coef) return SP_OK;
-    return build_coef(f, f->has_aux, (cudaStream_t)stream);
-}
-
-extern "C" uint64_t sp_field_coef_bytes(int nx, int ny, int nz, int with_phase) {
-    return (uint64_t)nx * ny * nz * 8ull * (with_phase ? 4 : 3) * sizeof(double);
-}
-
 extern "C" int sp_field_destroy(sp_field* f) {
     if (!f) return SP_OK;
-    cudaFree(f->data); cudaFree(f->aux64); cudaFree(f->coef);
+    cudaFree(f->data); cudaFree(f->aux64);
     for (int k = 0; k < 3; ++k) { cudaFree(f->tab64[k]); cudaFree(f->tab32[k]); }
     delete f;
     return SP_OK;
@@ -303,11 +240,6 @@ extern "C" int sp_field_create(sp_field** out, const void* ne_dev, int ne_is_f64
     CUF(cudaStreamSynchronize(st));   // temporaries are freed below; creation is a one-off
 #undef CUF
     cleanup();
-    f->has_aux = (flags & (SP_FIELD_PHASE | SP_FIELD_PHASE_F64)) != 0;
-    if (flags & SP_FIELD_COEF) {
-        rc = build_coef(f, f->has_aux, st);
-        if (rc) { sp_field_destroy(f); return rc; }
-    }
     *out = f;
     return SP_OK;
 }
@@ -329,7 +261,6 @@ extern "C" int sp_field_create_from_gradients(sp_field** out, const float* gx_de
         if (cudaMalloc(&f->aux64, cells * sizeof(double)) != cudaSuccess) { sp_field_destroy(f); return fail(SP_ENOMEM, "aux64"); }
         f->bytes += cells * sizeof(double);
     }
-    f->has_aux = (aux_f32_dev != nullptr || aux_f64_dev != nullptr);
     PackArgs P = pack_args(f);
     k_pack_from_grads<<<pack_grid(cells), 256, 0, st>>>(gx_dev, gy_dev, gz_dev, aux_f32_dev, aux_f64_dev, f->data,
                                                         f->aux64, P);
@@ -984,9 +915,7 @@ static int kernel_index_of(const sp_field* f, int caller_axis) {
 }
 
 template <typename T, int METHOD>
-static int launch_propagate(const PropArgs<T>& A_in, const Epilogue& E, int grid, cudaStream_t st) {
-    PropArgs<T> A = A_in;
-    if ((A.flags & SP_FLAG_PHASE) && A.F.coef_stride < 32) A.F.coef = nullptr;
+static int launch_propagate(const PropArgs<T>& A, const Epilogue& E, int grid, cudaStream_t st) {
     const bool phase = (A.flags & SP_FLAG_PHASE) != 0, aux64 = phase && (A.flags & SP_FLAG_PHASE_F64) != 0;
     if (!phase) k_propagate<T, METHOD, false, false><<<grid, 128, 0, st>>>(A, E);
     else if (!aux64) k_propagate<T, METHOD, true, false><<<grid, 128, 0, st>>>(A, E);
@@ -1137,7 +1066,6 @@ static int joint_solve(const sp_field* field, const sp_params* P, sp_workspace* 
 
     FieldView<double> F = make_view<double>(field);
     const bool phase = (P->flags & SP_FLAG_PHASE) != 0, aux64 = phase && (P->flags & SP_FLAG_PHASE_F64) != 0;
-    if (phase && F.coef_stride < 32) F.coef = nullptr;
     const int p0 = field->perm[0], p1 = field->perm[1], p2 = field->perm[2];
     const double rtol = P->rtol, atol = P->atol, omega = P->omega, t_end = P->t_end;
     const int n_state = P->n_state > 0 ? P->n_state : 9;
@@ -1239,7 +1167,6 @@ extern "C" int sp_rhs(const sp_field* field, const sp_params* P, const double* s
     if (n == 0) return SP_OK;
     FieldView<double> F = make_view<double>(field);
     const bool phase = (P->flags & SP_FLAG_PHASE) != 0, aux64 = phase && (P->flags & SP_FLAG_PHASE_F64) != 0;
-    if (phase && F.coef_stride < 32) F.coef = nullptr;
     const int blocks = (int)((n + 127) / 128);
     cudaStream_t st = (cudaStream_t)stream;
     const int p0 = field->perm[0], p1 = field->perm[1], p2 = field->perm[2];

@@ -85,9 +85,8 @@ class ScalarDomain:
         self.Z = Z
 
     # -- device side
-    def device_field(self, lwl, *, phase=None, phase_f64=False, prepare_cells="auto"):
-        """Packed float4 {grad, n-1} grid for wavelength ``lwl`` (cached).  ``prepare_cells`` ("auto" | True | False):
-        also build the per-cell coefficient field when it fits (see ``engine.DeviceField.prepare_cells``)."""
+    def device_field(self, lwl, *, phase=None, phase_f64=False):
+        """Packed float4 {grad, n-1} grid for wavelength ``lwl`` (cached)."""
         if self.ne is None:
             raise RuntimeError("no electron density loaded (call a test_* profile or external_ne)")
         phase = self.phaseshift if phase is None else phase
@@ -96,7 +95,6 @@ class ScalarDomain:
             self._fields[key] = engine.DeviceField.from_ne(
                 self.ne, self.x, self.y, self.z, engine.omega_of(lwl),
                 march_axis=engine.AXIS[self.probing_direction], phase=phase, phase_f64=phase_f64)
-            self._fields[key].prepare_cells(prepare_cells)
         return self._fields[key]
 
     def cell_size(self, axis=None):

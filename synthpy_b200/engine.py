@@ -54,18 +54,6 @@ class DeviceField:
         self._h = handle
         self.shape, self.march_axis, self.has_phase, self.has_f64 = tuple(shape), march_axis, has_phase, has_f64
 
-    def prepare_cells(self, mode="auto", budget_frac=0.4):
-        """Per-cell polynomial coefficients (SP_FIELD_COEF): 192 B per cell (256 B with phase) of extra HBM for
-        ~1.4x faster float64 propagation; results are bit-identical either way.  mode: True | False | "auto"
-        (build it if it fits in ``budget_frac`` of the currently free device memory).  Returns whether present."""
-        if mode is False or mode is None:
-            return False
-        need = int(L.lib.sp_field_coef_bytes(*[int(v) for v in self.shape], int(self.has_phase)))
-        if mode == "auto" and need > budget_frac * torch.cuda.mem_get_info()[0]:
-            return False
-        L.check(L.lib.sp_field_build_coef(self._h, _stream()))
-        return True
-
     @classmethod
     def from_ne(cls, ne, x, y, z, omega, march_axis=2, phase=False, phase_f64=False):
         """ne: (nx,ny,nz) numpy/torch, float64 or float32; x,y,z: coordinate axes (rounded to float32 here,

@@ -21,7 +21,7 @@ struct HostField {
     AxisTables tabs[3];
     FieldView<double> view64() const {
         FieldView<double> V;
-        V.data = data.data(); V.aux64 = aux64.empty() ? nullptr : aux64.data(); V.coef = nullptr; V.coef_stride = 0;
+        V.data = data.data(); V.aux64 = aux64.empty() ? nullptr : aux64.data();
         for (int k = 0; k < 3; ++k) {
             V.ax[k].tab = tabs[k].t64.data(); V.ax[k].g0 = tabs[k].g0; V.ax[k].inv_d = tabs[k].inv_d;
             V.ax[k].lo = tabs[k].lo; V.ax[k].hi = tabs[k].hi; V.ax[k].n = nk[k];
@@ -31,7 +31,7 @@ struct HostField {
     }
     FieldView<float> view32() const {
         FieldView<float> V;
-        V.data = data.data(); V.aux64 = aux64.empty() ? nullptr : aux64.data(); V.coef = nullptr; V.coef_stride = 0;
+        V.data = data.data(); V.aux64 = aux64.empty() ? nullptr : aux64.data();
         for (int k = 0; k < 3; ++k) {
             V.ax[k].tab = tabs[k].t32.data(); V.ax[k].g0 = (float)tabs[k].g0; V.ax[k].inv_d = (float)tabs[k].inv_d;
             V.ax[k].lo = (float)tabs[k].lo; V.ax[k].hi = (float)tabs[k].hi; V.ax[k].n = nk[k];

@@ -264,28 +264,6 @@ def test_fused_path_equals_two_stage(sp, golden):
     assert np.array_equal(sh.H, specs[0].image.result().cpu().numpy())
 
 
-def test_prepared_cells_are_bit_identical(sp, golden):
-    """SP_FIELD_COEF (per-cell polynomial coefficients precomputed in HBM) must not change a single bit."""
-    from synthpy_b200 import engine
-    for name, ph in (("g3_turb", False), ("g2_expcos", True)):
-        g = golden(name)
-        ext, n = float(g["extent"]), int(g["rk4_nsteps"])
-        h = np.sqrt(8.0) * ext / C_LIGHT / n
-        d = _legacy_dom(sp, g, phaseshift=ph)
-        d.solve(g["s0"], return_E=True, method="rk4", n_steps=n, h=h)
-        sf0, rf0, J0 = d.sf.copy(), d.rf.copy(), d.Jf.copy()
-        sf45 = None
-        d.solve(g["s0"][:, :32], method="rk45")
-        sf45 = d.sf.copy()
-        assert d.field.prepare_cells(True) and d.field.nbytes > 12 * 16 * g["ne"].size
-        d.solve(g["s0"], return_E=True, method="rk4", n_steps=n, h=h)
-        assert np.array_equal(d.sf, sf0) and np.array_equal(d.rf, rf0) and np.array_equal(d.Jf, J0)
-        d.solve(g["s0"][:, :32], method="rk45")
-        assert np.array_equal(d.sf, sf45)
-        d.solve(g["s0"])                                   # joint mode reads the same coefficients
-        assert np.max(np.abs(d.rf - g["rf"])) < (1e-9 if ph else 1e-3 * ext)
-
-
 def test_device_beam_partition_invariance_and_statistics(sp):
     from synthpy_b200 import beam as B, engine
     b = B.Beam(100000, 4e-3, 5e-5, 10e-3, device=True, seed=11)
