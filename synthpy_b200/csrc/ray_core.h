@@ -506,13 +506,19 @@ SP_HD T dp5_initial_step(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega
 // ---- exit plane ------------------------------------------------------------------------------------------
 // ray_to_Jonesvector (full_solver.py:838-894): back-project to the plane coord[p] = extent; angles atan(v_a/v_p).
 // kp/ka/kb are kernel-frame indices of the probing axis and of the axes that land in rf rows (0,1) / (2,3).
+// (components are picked with selects, not r.p[k]: a dynamically indexed member would force the whole ray
+// state into local memory and cost six local stores per integration step)
+template <typename T> SP_HD T pick3(const T* a, int k) { return k == 0 ? a[0] : (k == 1 ? a[1] : a[2]); }
+
 template <typename T>
 SP_HD void exit_project(const Ray<T>& r, int kp, int ka, int kb, T extent, T& xa, T& tha, T& xb, T& thb) {
-    const T tbp = (r.p[kp] - extent) / r.v[kp];
-    xa = r.p[ka] - r.v[ka] * tbp;
-    xb = r.p[kb] - r.v[kb] * tbp;
-    tha = atan(r.v[ka] / r.v[kp]);
-    thb = atan(r.v[kb] / r.v[kp]);
+    const T pp = pick3(r.p, kp), vp = pick3(r.v, kp);
+    const T pa = pick3(r.p, ka), va = pick3(r.v, ka), pb = pick3(r.p, kb), vb = pick3(r.v, kb);
+    const T tbp = (pp - extent) / vp;
+    xa = pa - va * tbp;
+    xb = pb - vb * tbp;
+    tha = atan(va / vp);
+    thb = atan(vb / vp);
 }
 
 // ---- optics ------------------------------------------------------------------------------------------------
