@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SP_ABI_VERSION 1
+#define SP_ABI_VERSION 2
 
 /* error codes */
 #define SP_OK 0
@@ -70,6 +70,15 @@ int sp_field_create_from_gradients(sp_field** out, const float* gx_dev, const fl
                                    const float* gz_dev, const float* aux_f32_dev, const double* aux_f64_dev,
                                    const float* ax_x_host, const float* ax_y_host, const float* ax_z_host,
                                    int nx, int ny, int nz, int march_axis, void* stream);
+
+/*
+ * Optional attenuation / Faraday channels (state rows 6 and 8): float64 grids [x][y][z] on the device, any may
+ * be NULL.  kappa = inverse-bremsstrahlung rate (ScalarDomain.kappa, full_solver.py:243-268), ne and B for
+ * pol' = V ne (B.v) (full_solver.py:356-374).  The grids are copied (re-ordered to the packed layout).
+ * Used by sp_propagate when SP_FLAG_ATTEN / SP_FLAG_FARADAY are set (SP_METHOD_RK4, float64 only) and by sp_rhs.
+ */
+int sp_field_attach_channels(sp_field* f, const double* kappa_dev, const double* ne_dev, const double* bx_dev,
+                             const double* by_dev, const double* bz_dev, void* stream);
 
 int sp_field_destroy(sp_field* f);
 
@@ -168,6 +177,8 @@ int sp_image_finalize(const sp_image* img, double* H_dev, void* stream);
 #define SP_FLAG_FP32 4       /* float32 state and arithmetic (the JAX generation's default, config.py:127)   */
 #define SP_FLAG_PHASE_F64 8  /* interpolate n-1 from the float64 aux grid                                    */
 #define SP_FLAG_NO_SORT 16   /* do not reorder rays into coherent bundles                                    */
+#define SP_FLAG_ATTEN 32     /* integrate amp' = kappa(r) amp            (full_solver.py:540)                */
+#define SP_FLAG_FARADAY 64   /* integrate pol' = verdet ne(r) (B(r).v)   (full_solver.py:542)                */
 
 typedef struct sp_params {
     int32_t method;
@@ -183,6 +194,7 @@ typedef struct sp_params {
     int32_t out_axis_a;    /* which spatial axis lands in rf rows 0,1 ...                                    */
     int32_t out_axis_b;    /* ... and rows 2,3  (legacy 'y': a=x,b=z; current API 'y': a=z,b=x)              */
     int32_t _pad;
+    double verdet;         /* Verdet constant 2.62e-13 lambda^2 (full_solver.py:223); SP_FLAG_FARADAY only  */
 } sp_params;
 
 typedef struct sp_stats {

@@ -179,6 +179,29 @@ def main():
         g3d.update({f"{pd}_x": xp, f"{pd}_y": yp, f"{pd}_z": zp, f"{pd}_s0": s0p, f"{pd}_sf": sfp, f"{pd}_rf": rfp})
     np.savez_compressed(os.path.join(OUT, "g3_turb.npz"), **g3d)
 
+    # ---------------------------------------------------------------- G6: attenuation + Faraday channels (9-vector ODE)
+    lengths, dims, extent = (10e-3, 10e-3, 20e-3), (24, 20, 28), 10e-3
+    x, y, z = axes(lengths, dims)
+    rng6 = np.random.default_rng(21)
+    ne6 = gaussian_column(x, y, z, ne0=4e25, LR=3e-3) * (1 + 0.3 * np.cos(2 * np.pi * z / 7e-3))[None, None, :] + 1e24
+    XX, YY, ZZ = np.meshgrid(x, y, z, indexing="ij")
+    Te6 = 50.0 + 150.0 * np.exp(-(XX ** 2 + YY ** 2) / (4e-3) ** 2)            # eV
+    Z6 = 3.0 + 2.0 * np.cos(2 * np.pi * ZZ / 9e-3) ** 2
+    B6 = np.stack([5.0 * YY / 5e-3, -5.0 * XX / 5e-3, 10.0 * np.exp(-(XX ** 2 + YY ** 2) / (3e-3) ** 2)], axis=-1)   # T
+    dom = fs.ScalarDomain(x, y, z, extent, B_on=True, inv_brems=True, phaseshift=True)
+    dom.external_ne(ne6); dom.external_B(B6); dom.external_Te(Te6); dom.external_Z(Z6)
+    dom.calc_dndr(lwl)
+    dom.set_up_interps()
+    s6 = probe_states(rng6, 2048, lengths)
+    g6 = dict(x=x, y=y, z=z, extent=extent, lwl=lwl, ne=ne6, Te=Te6, Z=Z6, B=B6, s=s6, kappa=dom.kappa(),
+              dsdt=fs.dsdt(0.0, s6.ravel().copy(), dom).reshape(9, -1))
+    np.random.seed(6)
+    s0 = fs.init_beam(128, 4e-3, 2e-3, extent, "circular", "z")
+    g6["s0"], g6["rk4_nsteps"] = s0, 120
+    g6["rk4_sf"] = rk4(dom, s0, 120)
+    g6["rk4_rf"], g6["rk4_Jf"] = fs.ray_to_Jonesvector(g6["rk4_sf"], extent, probing_direction="z")
+    np.savez_compressed(os.path.join(OUT, "g6_channels.npz"), **g6)
+
     # ---------------------------------------------------------------- G4: optics + detector
     rng = np.random.default_rng(5)
     n = 5000

@@ -38,7 +38,7 @@ class Domain:
     """Restates ``full_solver.ScalarDomain`` (full_solver.py:96-403): float32 axes, float32 normalised
     density and gradients, float64 interpolation arithmetic, 9-component ray state."""
 
-    def __init__(self, x, y, z, extent, *, phaseshift=False, probing_direction="z"):
+    def __init__(self, x, y, z, extent, *, phaseshift=False, probing_direction="z", B_on=False, inv_brems=False):
         # full_solver.py:119 -- the axes are *rounded to float32*; the mesh (used by analytic profiles
         # only) is built from the caller's float64 axes (full_solver.py:120).
         self.x, self.y, self.z = (np.float32(a) for a in (x, y, z))
@@ -46,7 +46,8 @@ class Domain:
         self.extent = extent
         self.probing_direction = probing_direction
         self.phaseshift = phaseshift
-        self.ne = None
+        self.B_on, self.inv_brems = B_on, inv_brems
+        self.ne = self.B = self.Te = self.Z = None
 
     # -- analytic profiles (full_solver.py:130-175) -------------------------------------------------
     def _mesh(self):
@@ -69,8 +70,39 @@ class Domain:
     def external_ne(self, ne):                             # full_solver.py:169-175
         self.ne = ne
 
+    def external_B(self, B):                               # full_solver.py:177-183
+        self.B = B
+
+    def external_Te(self, Te, Te_min=1.0):                 # full_solver.py:185-191
+        self.Te = np.maximum(Te_min, Te)
+
+    def external_Z(self, Z):                               # full_solver.py:193-199
+        self.Z = Z
+
+    def kappa(self):
+        """Inverse-bremsstrahlung rate grid, full_solver.py:243-268 (NRL formulary)."""
+        e = 1.602176634e-19                                # scipy.constants.e
+        ne_cc = self.ne * 1e-6
+        o_pe = OMEGA_PE_COEFF * np.sqrt(ne_cc)
+        o_max = np.copy(o_pe)
+        o_max[o_pe < self.omega] = self.omega
+        L_max = np.maximum(self.Z * e / self.Te, 2.760428269727312e-10 / np.sqrt(self.Te))
+        CL = np.maximum(2.0, np.log(4.19e5 * np.sqrt(self.Te) / (o_max * L_max)))
+        return 3.1e-5 * self.Z * C_LIGHT * np.power(ne_cc / self.omega, 2) * CL * np.power(self.Te, -1.5)
+
+    def set_up_interps(self):
+        """full_solver.py:276-289 (the pieces the ray ODE uses)."""
+        axes = (self.x, self.y, self.z)
+        if self.B_on:
+            self.verdet = 2.62e-13 * self.lwl ** 2         # full_solver.py:222-223
+            self.ne_interp = RegularGridInterpolator(axes, self.ne, bounds_error=False, fill_value=0.0)
+            self.B_interp = [RegularGridInterpolator(axes, self.B[..., c], bounds_error=False, fill_value=0.0) for c in range(3)]
+        if self.inv_brems:
+            self.kappa_interp = RegularGridInterpolator(axes, self.kappa(), bounds_error=False, fill_value=0.0)
+
     # -- gradient precompute (full_solver.py:211-234) -----------------------------------------------
     def calc_dndr(self, lwl=1053e-9):
+        self.lwl = lwl
         self.omega = 2 * np.pi * (C_LIGHT / lwl)
         nc = NC_COEFF * self.omega ** 2
         self.ne_nc = np.array(self.ne / nc, dtype=np.float32)
@@ -93,14 +125,19 @@ class Domain:
         return np.stack([f(pts) for f in self.grad_interp])
 
     def dsdt(self, t, s):
-        """Flattened 9N -> 9N, full_solver.py:516-544 (attenuation / Faraday channels are off: 0)."""
+        """Flattened 9N -> 9N, full_solver.py:516-544."""
         n = s.size // 9
         s = s.reshape(9, n)
         out = np.zeros_like(s)
         out[3:6] = self.dndr(s[:3])
         out[:3] = s[3:6]
+        if self.inv_brems:
+            out[6] = self.kappa_interp(s[:3].T) * s[6]                # full_solver.py:335-339,540
         if self.phaseshift:
             out[7] = self.omega * (self.n_interp(s[:3].T) - 1.0)      # full_solver.py:342-345
+        if self.B_on:                                                 # full_solver.py:356-374,542
+            Bv = np.sum(np.array([f(s[:3].T) for f in self.B_interp]) * s[3:6], axis=0)
+            out[8] = self.verdet * self.ne_interp(s[:3].T) * Bv
         return out.ravel()
 
     # -- integrators ----------------------------------------------------------------------------------

@@ -15,7 +15,7 @@ BEAM_CIRCULAR_FOLD, BEAM_CIRCULAR_POW2, BEAM_SQUARE, BEAM_RECTANGULAR, BEAM_LINE
 OP_TRAVEL, OP_TRAVEL_NOE, OP_LENS, OP_CIRC_AP, OP_CIRC_STOP, OP_RECT_AP, OP_KNIFE, OP_REF_BEAM = range(8)
 IMG_HISTOGRAM, IMG_INTERFEROGRAM = 0, 1
 METHOD_RK4, METHOD_RK45, METHOD_RK45_JOINT = 0, 1, 2
-FLAG_PHASE, FLAG_EARLY_EXIT, FLAG_FP32, FLAG_PHASE_F64, FLAG_NO_SORT = 1, 2, 4, 8, 16
+FLAG_PHASE, FLAG_EARLY_EXIT, FLAG_FP32, FLAG_PHASE_F64, FLAG_NO_SORT, FLAG_ATTEN, FLAG_FARADAY = 1, 2, 4, 8, 16, 32, 64
 
 
 class Beam(C.Structure):
@@ -42,7 +42,7 @@ class Params(C.Structure):
     _fields_ = [("method", C.c_int32), ("flags", C.c_int32), ("n_steps", C.c_int32), ("n_state", C.c_int32),
                 ("h", C.c_double), ("t_end", C.c_double), ("rtol", C.c_double), ("atol", C.c_double),
                 ("omega", C.c_double), ("extent", C.c_double), ("probing_axis", C.c_int32),
-                ("out_axis_a", C.c_int32), ("out_axis_b", C.c_int32), ("_pad", C.c_int32)]
+                ("out_axis_a", C.c_int32), ("out_axis_b", C.c_int32), ("_pad", C.c_int32), ("verdet", C.c_double)]
 
 
 class Stats(C.Structure):
@@ -63,6 +63,7 @@ EXPORTS = {
     "sp_field_create_from_gradients": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_void_p, C.c_void_p,
                                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                  C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "sp_field_attach_channels": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sp_field_destroy": (C.c_int, [C.c_void_p]),
     "sp_field_export_gradients": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "sp_field_bytes": (C.c_uint64, [C.c_void_p]),

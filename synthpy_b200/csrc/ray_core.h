@@ -354,6 +354,81 @@ SP_HD int rk4_step(const FieldView<T>& F, CellCache<T, PHASE>& cc, T h, T omega,
     return touched;
 }
 
+// ---- attenuation and Faraday-rotation channels (slow path, float64, RK4 only) ---------------------------------
+// Reference: dsdt rows 6 and 8 (src/solvers-legacy/full_solver.py:540-542):
+//     amp' = kappa(r) amp          kappa_interp, fill 0     (full_solver.py:243-268,286,335-339)
+//     pol' = V ne(r) (B(r) . v)    ne_interp / B*_interp, fill 0, V = 2.62e-13 lambda^2  (full_solver.py:223,356-374)
+// The five grids stay float64 (the reference does not round them to float32) and are interpolated directly from
+// HBM with the weights of the cached cell; these channels are rare and not on the throughput path.
+struct ExtView {
+    const double* ch[5];   // kappa, ne, B_u, B_v, B_w in the kernel frame ([nu][nv][nw]); nullptr = channel off
+    double verdet;
+};
+
+template <bool PHASE>
+SP_HD void ext_eval(const FieldView<double>& F, const ExtView& X, const CellCache<double, PHASE>& cc, bool inside,
+                    const double* p, double out[5]) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) out[c] = 0.0;
+    if (!inside) return;
+    const double wu = (p[0] - cc.lo[0]) * cc.rinv[0], wv = (p[1] - cc.lo[1]) * cc.rinv[1], ww = (p[2] - cc.lo[2]) * cc.rinv[2];
+    const double mu = 1.0 - wu, mv = 1.0 - wv, mw = 1.0 - ww;
+    const double k[8] = {mu * mv * mw, mu * mv * ww, mu * wv * mw, mu * wv * ww, wu * mv * mw, wu * mv * ww, wu * wv * mw, wu * wv * ww};
+    const long long base = (long long)cc.idx[0] * F.su + (long long)cc.idx[1] * F.sv + cc.idx[2];
+    const long long off[8] = {0, 1, F.sv, F.sv + 1, F.su, F.su + 1, F.su + F.sv, F.su + F.sv + 1};
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+        if (!X.ch[c]) continue;
+        const double* q = X.ch[c] + base;
+        double acc = ldg(q) * k[0];
+#pragma unroll
+        for (int j = 1; j < 8; ++j) acc = sp_fma(ldg(q + off[j]), k[j], acc);
+        out[c] = acc;
+    }
+}
+
+struct ExtState { double amp, pol; };
+
+// Classical RK4 on the full 9-component state (explicit stage velocities: pol' depends on them).
+template <bool PHASE, bool AUX64>
+SP_HD int rk4_step_ext(const FieldView<double>& F, const ExtView& X, CellCache<double, PHASE>& cc, double h, double omega,
+                       bool with_phase, Ray<double>& r, ExtState& e, bool early = false) {
+    const double hh = 0.5 * h, h6 = h / 6.0;
+    double p[3], v[3], a[3], n, x[5];
+    double sp[3] = {0, 0, 0}, sv[3] = {0, 0, 0}, sn = 0, sA = 0, sR = 0;
+    double A = e.amp, kA = 0;
+    int touched = 0;
+    const double wgt[4] = {1.0, 2.0, 2.0, 1.0}, adv[4] = {0.0, hh, hh, h};
+    double kv_prev[3] = {0, 0, 0}, kp_prev[3] = {0, 0, 0};
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { p[k] = sp_fma(adv[s], kp_prev[k], r.p[k]); v[k] = sp_fma(adv[s], kv_prev[k], r.v[k]); }
+        A = sp_fma(adv[s], kA, e.amp);
+        const bool in = rhs<double, PHASE, AUX64>(F, cc, p[0], p[1], p[2], a[0], a[1], a[2], n);
+        if (s == 0 && early && !in && escaped(F, r)) return -1;
+        touched += in;
+        ext_eval<PHASE>(F, X, cc, in, p, x);
+        kA = x[0] * A;                                                        // kappa(r) * amp
+        const double kR = X.verdet * x[1] * (x[2] * v[0] + x[3] * v[1] + x[4] * v[2]);   // V ne (B . v)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            sp[k] = (s == 0) ? v[k] : sp_fma(wgt[s], v[k], sp[k]);
+            sv[k] = (s == 0) ? a[k] : sp_fma(wgt[s], a[k], sv[k]);
+            kp_prev[k] = v[k]; kv_prev[k] = a[k];
+        }
+        sn = (s == 0) ? n : sp_fma(wgt[s], n, sn);
+        sA = (s == 0) ? kA : sp_fma(wgt[s], kA, sA);
+        sR = (s == 0) ? kR : sp_fma(wgt[s], kR, sR);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { r.p[k] = sp_fma(h6, sp[k], r.p[k]); r.v[k] = sp_fma(h6, sv[k], r.v[k]); }
+    if (PHASE && with_phase) r.ph = sp_fma(h6, omega * sn, r.ph);
+    e.amp = sp_fma(h6, sA, e.amp);
+    e.pol = sp_fma(h6, sR, e.pol);
+    return touched;
+}
+
 // ---- Dormand-Prince 5(4) with SciPy's controller -------------------------------------------------------
 // Tableau of scipy/integrate/_ivp/rk.py::RK45 (Dormand & Prince 1980).
 struct DP {

@@ -51,6 +51,7 @@ struct sp_field {
     int nk[3];         // kernel-frame dims nu, nv, nw
     f4* data = nullptr;
     double* aux64 = nullptr;
+    double* ext[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};   // kappa, ne, B_u, B_v, B_w (kernel frame)
     d2* tab64[3] = {nullptr, nullptr, nullptr};   // kernel-frame axis tables
     f2* tab32[3] = {nullptr, nullptr, nullptr};
     double g0[3], inv_d[3], lo[3], hi[3];         // kernel frame
@@ -173,9 +174,46 @@ static int pack_grid(long long total) {
     return (int)(b > 148 * 32 ? 148 * 32 : (b < 1 ? 1 : b));
 }
 
+__global__ void k_repack_f64(const double* __restrict__ in, double* __restrict__ out, PackArgs P) {
+    const long long total = (long long)P.nk[0] * P.nk[1] * P.nk[2];
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long gstride = (long long)gridDim.x * blockDim.x;
+    for (; t < total; t += gstride) {
+        int ic[3];
+        out[t] = in[unpack_index(t, P, ic)];
+    }
+}
+
+extern "C" int sp_field_attach_channels(sp_field* f, const double* kappa_dev, const double* ne_dev, const double* bx_dev,
+                                        const double* by_dev, const double* bz_dev, void* stream) {
+    if (!f) return fail(SP_EINVAL, "null field");
+    const long long cells = (long long)f->n[0] * f->n[1] * f->n[2];
+    const double* b_caller[3] = {bx_dev, by_dev, bz_dev};
+    const double* src[5] = {kappa_dev, ne_dev, b_caller[f->perm[0]], b_caller[f->perm[1]], b_caller[f->perm[2]]};
+    PackArgs P = pack_args(f);
+    for (int c = 0; c < 5; ++c) {
+        cudaFree(f->ext[c]); f->ext[c] = nullptr;
+        if (!src[c]) continue;
+        CU(cudaMalloc(&f->ext[c], cells * sizeof(double)));
+        f->bytes += cells * sizeof(double);
+        k_repack_f64<<<pack_grid(cells), 256, 0, (cudaStream_t)stream>>>(src[c], f->ext[c], P);
+        LAUNCH_CHECK();
+    }
+    return SP_OK;
+}
+
+static ExtView make_ext(const sp_field* f, double verdet, int flags) {
+    ExtView X;
+    X.verdet = verdet;
+    X.ch[0] = (flags & SP_FLAG_ATTEN) ? f->ext[0] : nullptr;
+    for (int c = 1; c < 5; ++c) X.ch[c] = (flags & SP_FLAG_FARADAY) ? f->ext[c] : nullptr;
+    return X;
+}
+
 extern "C" int sp_field_destroy(sp_field* f) {
     if (!f) return SP_OK;
     cudaFree(f->data); cudaFree(f->aux64);
+    for (int c = 0; c < 5; ++c) cudaFree(f->ext[c]);
     for (int k = 0; k < 3; ++k) { cudaFree(f->tab64[k]); cudaFree(f->tab32[k]); }
     delete f;
     return SP_OK;
@@ -288,6 +326,7 @@ extern "C" int sp_field_export_gradients(const sp_field* f, float* gx_dev, float
 #ifndef SP_RK4_MIN_BLOCKS
 #define SP_RK4_MIN_BLOCKS 4
 #endif
+#define SP_METHOD_RK4X 3      // internal: RK4 with the attenuation / Faraday channels (float64)
 #define SP_MAX_OPS 16
 #define SP_MAX_CHANNELS 4
 
@@ -428,6 +467,7 @@ template <typename T> struct PropArgs {
     int method, flags, n_steps, n_state;
     T h, t_end, rtol, atol, omega, extent;
     sp_stats* stats;
+    ExtView X;                                // attenuation / Faraday channels (METHOD == SP_METHOD_RK4X only)
 };
 
 struct LaneStats { unsigned long long steps, acc, capped, binned, rejected, evals; };
@@ -436,6 +476,26 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+// RK4 over the full 9-component state (attenuation and Faraday rotation on): float64 only.
+template <bool PHASE, bool AUX64, typename T>
+__device__ __forceinline__ void rk4x_integrate(const PropArgs<T>& A, Ray<T>& r, CellCache<T, PHASE>& cc, bool early, uint64_t gi,
+                                               unsigned& n_att, LaneStats& ls, double& amp, double& pol) {}
+template <bool PHASE, bool AUX64>
+__device__ __forceinline__ void rk4x_integrate(const PropArgs<double>& A, Ray<double>& r, CellCache<double, PHASE>& cc, bool early,
+                                               uint64_t gi, unsigned& n_att, LaneStats& ls, double& amp, double& pol) {
+    ExtState e;
+    e.amp = A.use_beam ? 1.0 : A.s0[6 * A.n_total + gi];
+    e.pol = A.use_beam ? 0.0 : A.s0[8 * A.n_total + gi];
+    for (int it = 0; it < A.n_steps; ++it) {
+        const int t = rk4_step_ext<PHASE, AUX64>(A.F, A.X, cc, A.h, A.omega, (A.flags & SP_FLAG_PHASE) != 0, r, e, early);
+        if (t < 0) break;
+        ls.evals += t;
+        ++n_att;
+    }
+    ls.acc += n_att;
+    amp = e.amp; pol = e.pol;
 }
 
 template <typename T, int METHOD, bool PHASE, bool AUX64>
@@ -467,8 +527,11 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
         r.ph = (T)ph0;
         unsigned n_att = 0;
         CellCache<T, PHASE> cc;
+        double amp_x = 1.0, pol_x = 0.0;
         if (valid) {
-            if (METHOD == SP_METHOD_RK4) {
+            if (METHOD == SP_METHOD_RK4X) {
+                rk4x_integrate<PHASE, AUX64>(A, r, cc, early, gi, n_att, ls, amp_x, pol_x);
+            } else if (METHOD == SP_METHOD_RK4) {
                 const T h = A.h;
                 for (int it = 0; it < A.n_steps; ++it) {
                     const int t = rk4_step<T, PHASE, AUX64>(A.F, cc, h, A.omega, r, early);
@@ -523,6 +586,7 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
         const uint64_t N = A.n_total;
         double amp = 1.0, pol = 0.0;              // constant along the ray (zero derivative): re-read instead of kept live
         if (valid && !A.use_beam) { amp = A.s0[6 * N + gi]; pol = A.s0[8 * N + gi]; }
+        if (METHOD == SP_METHOD_RK4X) { amp = amp_x; pol = pol_x; }
         if (valid) {
             if (E.sf) {
 #pragma unroll
@@ -796,7 +860,7 @@ __global__ void k_finalize(const double* __restrict__ planes, double* __restrict
 }
 
 template <bool PHASE, bool AUX64>
-__global__ void k_rhs(FieldView<double> F, const double* __restrict__ s, uint64_t n, double* __restrict__ out,
+__global__ void k_rhs(FieldView<double> F, ExtView X, const double* __restrict__ s, uint64_t n, double* __restrict__ out,
                       int p0, int p1, int p2, double omega) {
     const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -805,9 +869,13 @@ __global__ void k_rhs(FieldView<double> F, const double* __restrict__ s, uint64_
     for (int k = 0; k < 3; ++k) { p[k] = s[(uint64_t)perm[k] * n + i]; v[k] = s[(uint64_t)(3 + perm[k]) * n + i]; }
     Deriv<double> f;
     CellCache<double, PHASE> cc;
-    deriv<double, PHASE, AUX64>(F, cc, omega, p, v, f);
+    const int inside = deriv<double, PHASE, AUX64>(F, cc, omega, p, v, f);
     for (int k = 0; k < 3; ++k) { out[(uint64_t)perm[k] * n + i] = f.dp[k]; out[(uint64_t)(3 + perm[k]) * n + i] = f.dv[k]; }
-    out[6 * n + i] = 0.0; out[7 * n + i] = f.dph; out[8 * n + i] = 0.0;
+    double x[5];
+    ext_eval<PHASE>(F, X, cc, inside != 0, p, x);
+    out[6 * n + i] = X.ch[0] ? x[0] * s[6 * n + i] : 0.0;
+    out[7 * n + i] = f.dph;
+    out[8 * n + i] = X.ch[1] ? X.verdet * x[1] * (x[2] * v[0] + x[3] * v[1] + x[4] * v[2]) : 0.0;
 }
 
 __global__ void k_beam(BeamSpec B, uint64_t off, uint64_t n, double* __restrict__ s0) {
@@ -938,6 +1006,21 @@ template <typename T, int METHOD> static int occupancy_grid(int sm_count, int fl
 static int joint_solve(const sp_field* field, const sp_params* P, sp_workspace* ws, const double* s0_dev, uint64_t n,
                        const Epilogue& E, sp_stats* stats_dev, cudaStream_t st);
 
+// attenuation / Faraday variant: float64, PHASE lane always compiled in (its integration is a run-time flag)
+static int ext_grid(int sm_count, bool aux64, int& grid) {
+    int per_sm = 0;
+    if (aux64) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<double, SP_METHOD_RK4X, true, true>, 128, 0));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<double, SP_METHOD_RK4X, true, false>, 128, 0));
+    grid = sm_count * (per_sm < 1 ? 1 : per_sm);
+    return SP_OK;
+}
+static int launch_ext(const PropArgs<double>& A, const Epilogue& E, bool aux64, int grid, cudaStream_t st) {
+    if (aux64) k_propagate<double, SP_METHOD_RK4X, true, true><<<grid, 128, 0, st>>>(A, E);
+    else k_propagate<double, SP_METHOD_RK4X, true, false><<<grid, 128, 0, st>>>(A, E);
+    LAUNCH_CHECK();
+    return SP_OK;
+}
+
 extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_workspace* ws, const double* s0_dev,
                             const sp_beam* beam, uint64_t n, uint64_t ray_offset, double* sf_dev, double* rf_dev,
                             double* jf_dev, uint32_t* steps_dev, const sp_channel* channels_host, int n_channels,
@@ -964,6 +1047,15 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
         return joint_solve(field, P, ws, s0_dev, n, E, stats_dev, st);
     }
     if (P->method != SP_METHOD_RK4 && P->method != SP_METHOD_RK45) return fail(SP_EINVAL, "unknown method");
+    const bool ext = (P->flags & (SP_FLAG_ATTEN | SP_FLAG_FARADAY)) != 0;
+    if (ext) {
+        if (P->method != SP_METHOD_RK4 || (P->flags & SP_FLAG_FP32))
+            return fail(SP_EINVAL, "attenuation / Faraday channels are integrated by float64 RK4 only");
+        if ((P->flags & SP_FLAG_ATTEN) && !field->ext[0]) return fail(SP_ESTATE, "SP_FLAG_ATTEN without a kappa grid (sp_field_attach_channels)");
+        if ((P->flags & SP_FLAG_FARADAY) && !(field->ext[1] && field->ext[2] && field->ext[3] && field->ext[4]))
+            return fail(SP_ESTATE, "SP_FLAG_FARADAY without ne and B grids (sp_field_attach_channels)");
+    }
+    const bool ext_aux64 = ext && (P->flags & SP_FLAG_PHASE) && (P->flags & SP_FLAG_PHASE_F64);
 
     const bool fp32 = (P->flags & SP_FLAG_FP32) != 0;
     const bool sort = !(P->flags & SP_FLAG_NO_SORT);
@@ -975,7 +1067,8 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
     const uint32_t n_keys = 1u << (2 * bits - key_shift);
 
     int grid = 0, rc = 0;
-    if (fp32) rc = (P->method == SP_METHOD_RK4) ? occupancy_grid<float, SP_METHOD_RK4>(ws->sm_count, P->flags, grid)
+    if (ext) rc = ext_grid(ws->sm_count, ext_aux64, grid);
+    else if (fp32) rc = (P->method == SP_METHOD_RK4) ? occupancy_grid<float, SP_METHOD_RK4>(ws->sm_count, P->flags, grid)
                                                 : occupancy_grid<float, SP_METHOD_RK45>(ws->sm_count, P->flags, grid);
     else rc = (P->method == SP_METHOD_RK4) ? occupancy_grid<double, SP_METHOD_RK4>(ws->sm_count, P->flags, grid)
                                            : occupancy_grid<double, SP_METHOD_RK45>(ws->sm_count, P->flags, grid);
@@ -1024,6 +1117,10 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
             FILL(float)
             rc = (P->method == SP_METHOD_RK4) ? launch_propagate<float, SP_METHOD_RK4>(A, E, g, st)
                                               : launch_propagate<float, SP_METHOD_RK45>(A, E, g, st);
+        } else if (ext) {
+            FILL(double)
+            A.X = make_ext(field, P->verdet, P->flags);
+            rc = launch_ext(A, E, ext_aux64, g, st);
         } else {
             FILL(double)
             rc = (P->method == SP_METHOD_RK4) ? launch_propagate<double, SP_METHOD_RK4>(A, E, g, st)
@@ -1170,9 +1267,10 @@ extern "C" int sp_rhs(const sp_field* field, const sp_params* P, const double* s
     const int blocks = (int)((n + 127) / 128);
     cudaStream_t st = (cudaStream_t)stream;
     const int p0 = field->perm[0], p1 = field->perm[1], p2 = field->perm[2];
-    if (!phase) k_rhs<false, false><<<blocks, 128, 0, st>>>(F, s_dev, n, dsdt_dev, p0, p1, p2, P->omega);
-    else if (!aux64) k_rhs<true, false><<<blocks, 128, 0, st>>>(F, s_dev, n, dsdt_dev, p0, p1, p2, P->omega);
-    else k_rhs<true, true><<<blocks, 128, 0, st>>>(F, s_dev, n, dsdt_dev, p0, p1, p2, P->omega);
+    const ExtView X = make_ext(field, P->verdet, P->flags);
+    if (!phase) k_rhs<false, false><<<blocks, 128, 0, st>>>(F, X, s_dev, n, dsdt_dev, p0, p1, p2, P->omega);
+    else if (!aux64) k_rhs<true, false><<<blocks, 128, 0, st>>>(F, X, s_dev, n, dsdt_dev, p0, p1, p2, P->omega);
+    else k_rhs<true, true><<<blocks, 128, 0, st>>>(F, X, s_dev, n, dsdt_dev, p0, p1, p2, P->omega);
     LAUNCH_CHECK();
     return SP_OK;
 }

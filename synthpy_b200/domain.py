@@ -14,9 +14,6 @@ class ScalarDomain:
     def __init__(self, lengths, dims, *, ne_type=None, inv_brems=False, phaseshift=False, B_on=False,
                  probing_direction="z", auto_batching=True, iteration=1, region_count=1, leeway_factor=None,
                  coord_backup=None, future_dims=None, debug=False):
-        if inv_brems or B_on:
-            raise NotImplementedError("inverse-bremsstrahlung / Faraday channels are outside the accelerated "
-                                      "path (SURVEY.md 8f-3); phaseshift is supported")
         self.inv_brems, self.phaseshift, self.B_on = inv_brems, phaseshift, B_on
         self.probing_direction = probing_direction
         self.ne_type = ne_type
@@ -77,12 +74,21 @@ class ScalarDomain:
 
     def external_B(self, B):
         self.B = B
+        self._fields.clear()
 
     def external_Te(self, Te, Te_min=1.0):
         self.Te = np.maximum(Te_min, Te)
+        self._fields.clear()
 
     def external_Z(self, Z):
         self.Z = Z
+        self._fields.clear()
+
+    def test_B(self, Bmax=1.0):                       # domain.py:493-503
+        XX = self._mesh()[0]
+        self.B = np.zeros(XX.shape + (3,))
+        self.B[..., 2] = Bmax * XX / self.x_length
+        self._fields.clear()
 
     # -- device side
     def device_field(self, lwl, *, phase=None, phase_f64=False):
@@ -95,6 +101,10 @@ class ScalarDomain:
             self._fields[key] = engine.DeviceField.from_ne(
                 self.ne, self.x, self.y, self.z, engine.omega_of(lwl),
                 march_axis=engine.AXIS[self.probing_direction], phase=phase, phase_f64=phase_f64)
+            if self.inv_brems or self.B_on:
+                ne = self.ne.cpu().numpy() if hasattr(self.ne, "cpu") else self.ne
+                kappa = engine.kappa_grid(ne, self.Te, self.Z, engine.omega_of(lwl)) if self.inv_brems else None
+                self._fields[key].attach_channels(kappa=kappa, ne=ne if self.B_on else None, B=self.B if self.B_on else None)
         return self._fields[key]
 
     def cell_size(self, axis=None):

@@ -43,6 +43,21 @@ def to_device(a, dtype=torch.float64):
     return t.to(device="cuda", dtype=dtype).contiguous()
 
 
+def kappa_grid(ne, Te, Z, omega):
+    """Inverse-bremsstrahlung rate grid, NRL formulary as coded in the reference (ScalarDomain.kappa,
+    src/solvers-legacy/full_solver.py:243-268; src/simulator/propagator.py:27-58).  Host NumPy float64: field
+    preparation, evaluated once per domain like the analytic profiles."""
+    e = 1.602176634e-19
+    ne_cc = np.asarray(ne, dtype=np.float64) * 1e-6
+    Te, Z = np.asarray(Te, dtype=np.float64), np.asarray(Z, dtype=np.float64)
+    o_pe = 5.64e4 * np.sqrt(ne_cc)
+    o_max = np.copy(o_pe)
+    o_max[o_pe < omega] = omega
+    L_max = np.maximum(Z * e / Te, 2.760428269727312e-10 / np.sqrt(Te))
+    CL = np.maximum(2.0, np.log(4.19e5 * np.sqrt(Te) / (o_max * L_max)))
+    return 3.1e-5 * Z * C_LIGHT * np.power(ne_cc / omega, 2) * CL * np.power(Te, -1.5)
+
+
 def omega_of(lwl):
     return 2 * np.pi * (C_LIGHT / lwl)          # full_solver.py:218, propagator.py:357
 
@@ -85,6 +100,15 @@ class DeviceField:
                                                      int(march_axis), _stream()))
         torch.cuda.current_stream().synchronize()       # inputs may be temporaries
         return cls(h, g[0].shape, march_axis, a32 is not None or a64 is not None, a64 is not None)
+
+    def attach_channels(self, kappa=None, ne=None, B=None):
+        """Attenuation / Faraday grids (float64, (nx,ny,nz); B is (nx,ny,nz,3)): see sp_field_attach_channels."""
+        k = None if kappa is None else to_device(kappa)
+        n = None if ne is None else to_device(ne)
+        b = [None] * 3 if B is None else [to_device(B[..., c]) for c in range(3)]
+        L.check(L.lib.sp_field_attach_channels(self._h, _ptr(k), _ptr(n), _ptr(b[0]), _ptr(b[1]), _ptr(b[2]), _stream()))
+        torch.cuda.current_stream().synchronize()
+        self.has_kappa, self.has_faraday = k is not None, (n is not None and B is not None)
 
     def export_gradients(self):
         outs = [torch.empty(self.shape, dtype=torch.float32, device="cuda") for _ in range(4)]
@@ -138,18 +162,19 @@ def joint_log():
 
 def make_params(method="rk4", *, probing_direction="z", extent, omega, n_steps=0, h=0.0, t_end=None, rtol=1e-3,
                 atol=1e-6, phase=False, phase_f64=False, early_exit=True, fp32=False, sort=True, n_state=9,
-                out_axes=None):
+                out_axes=None, atten=False, faraday=False, verdet=0.0):
     p = AXIS[probing_direction]
     if out_axes is None:
         # legacy ray_to_Jonesvector conventions (full_solver.py:856-881): x->(y,z), y->(x,z), z->(x,y)
         out_axes = {0: (1, 2), 1: (0, 2), 2: (0, 1)}[p]
     flags = ((L.FLAG_PHASE if phase else 0) | (L.FLAG_PHASE_F64 if (phase and phase_f64) else 0) |
-             (L.FLAG_EARLY_EXIT if early_exit else 0) | (L.FLAG_FP32 if fp32 else 0) | (0 if sort else L.FLAG_NO_SORT))
+             (L.FLAG_EARLY_EXIT if early_exit else 0) | (L.FLAG_FP32 if fp32 else 0) | (0 if sort else L.FLAG_NO_SORT) |
+             (L.FLAG_ATTEN if atten else 0) | (L.FLAG_FARADAY if faraday else 0))
     if t_end is None:
         t_end = np.sqrt(8.0) * extent / C_LIGHT       # full_solver.py:381, propagator.py:454
     return L.Params(method=METHODS[method], flags=flags, n_steps=int(n_steps), n_state=int(n_state), h=float(h),
                     t_end=float(t_end), rtol=float(rtol), atol=float(atol), omega=float(omega), extent=float(extent),
-                    probing_axis=p, out_axis_a=out_axes[0], out_axis_b=out_axes[1])
+                    probing_axis=p, out_axis_a=out_axes[0], out_axis_b=out_axes[1], verdet=float(verdet))
 
 
 def make_beam(beam_type, size, divergence, ne_extent, probing_direction="z", seed=0):

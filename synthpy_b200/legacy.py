@@ -15,8 +15,8 @@ from .engine import C_LIGHT as c
 
 class ScalarDomain:
     def __init__(self, x, y, z, extent, B_on=False, inv_brems=False, phaseshift=False, probing_direction="z"):
-        if B_on or inv_brems:
-            raise NotImplementedError("Faraday / inverse-bremsstrahlung channels are outside the accelerated path")
+        self.B_on, self.inv_brems = B_on, inv_brems
+        self.B = self.Te = self.Z = None
         self.x, self.y, self.z = np.float32(x), np.float32(y), np.float32(z)       # full_solver.py:119
         self._axes64 = (np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64), np.asarray(z, dtype=np.float64))
         self.extent, self.probing_direction, self.phaseshift = extent, probing_direction, phaseshift
@@ -43,10 +43,30 @@ class ScalarDomain:
     def external_ne(self, ne):
         self.ne = ne
 
+    def external_B(self, B):                      # full_solver.py:177-183
+        self.B = B
+
+    def external_Te(self, Te, Te_min=1.0):        # full_solver.py:185-191
+        self.Te = np.maximum(Te_min, Te)
+
+    def external_Z(self, Z):                      # full_solver.py:193-199
+        self.Z = Z
+
+    def test_B(self, Bmax=1.0):                   # full_solver.py:201-209
+        XX = self._mesh()[0]
+        self.B = np.zeros(XX.shape + (3,))
+        self.B[..., 2] = Bmax * XX / self.extent
+
+    def set_up_interps(self):
+        """full_solver.py:276-289: attach the attenuation / Faraday grids to the device field."""
+        kappa = engine.kappa_grid(self.ne, self.Te, self.Z, self.omega) if self.inv_brems else None
+        self.field.attach_channels(kappa=kappa, ne=self.ne if self.B_on else None, B=self.B if self.B_on else None)
+
     def calc_dndr(self, lwl=1053e-9, phase_f64=True):
         """full_solver.py:211-234 on the device (float32 stencil identical to np.gradient)."""
         self.lwl = lwl
         self.omega = engine.omega_of(lwl)
+        self.VerdetConst = 2.62e-13 * lwl ** 2 if self.B_on else 0.0          # full_solver.py:222-223
         self.field = engine.DeviceField.from_ne(self.ne, self.x, self.y, self.z, self.omega,
                                                 march_axis=engine.AXIS[self.probing_direction],
                                                 phase=self.phaseshift, phase_f64=self.phaseshift and phase_f64)
@@ -54,6 +74,9 @@ class ScalarDomain:
     def params(self, method, **kw):
         kw.setdefault("phase", self.phaseshift)
         kw.setdefault("phase_f64", self.phaseshift and self.field.has_f64)
+        kw.setdefault("atten", self.inv_brems)
+        kw.setdefault("faraday", self.B_on)
+        kw.setdefault("verdet", self.VerdetConst)
         return engine.make_params(method, probing_direction=self.probing_direction, extent=self.extent,
                                   omega=self.omega, **kw)
 

@@ -45,7 +45,9 @@ def _params(domain, probing_depth, lwl, method, n_steps, ds, rtol, atol, precisi
     return engine.make_params(method, probing_direction=domain.probing_direction, extent=extent,
                               omega=engine.omega_of(lwl), n_steps=n, h=h, t_end=t_end, rtol=rtol, atol=atol,
                               phase=phase, phase_f64=phase_f64, early_exit=early_exit, fp32=(precision == "fp32"),
-                              sort=sort, out_axes=_out_axes(domain.probing_direction, convention))
+                              sort=sort, out_axes=_out_axes(domain.probing_direction, convention),
+                              atten=bool(domain.inv_brems), faraday=bool(domain.B_on),
+                              verdet=2.62e-13 * lwl ** 2 if domain.B_on else 0.0)      # propagator.py:353-355
 
 
 def solve(s0_import, ScalarDomain, probing_depth, *, return_E=False, parallelise=True, jitted=True, save_steps=2,

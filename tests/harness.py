@@ -86,6 +86,23 @@ class HField:
     def __del__(self):
         self.H.lib.hh_field_destroy(self.h)
 
+    def attach(self, kappa, ne, B):
+        self._ext = [np.ascontiguousarray(a, dtype=np.float64) for a in (kappa, ne, B[..., 0], B[..., 1], B[..., 2])]
+        self.H.lib.hh_attach(self.h, *[_p(a) for a in self._ext])
+
+    def rhs_ext(self, s, verdet):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        out = np.empty_like(s)
+        self.H.lib.hh_rhs_ext(self.h, _p(s), C.c_uint64(s.shape[1]), _p(out), C.c_double(self.omega), C.c_double(verdet))
+        return out
+
+    def rk4_ext(self, s0, n_steps, h, verdet, early=False):
+        s0 = np.ascontiguousarray(s0, dtype=np.float64)
+        sf = np.empty_like(s0)
+        self.H.lib.hh_rk4_ext(self.h, _p(s0), C.c_uint64(s0.shape[1]), C.c_int(n_steps), C.c_double(h), C.c_double(self.omega),
+                              C.c_double(verdet), C.c_int(int(early)), _p(sf))
+        return sf
+
     def export(self):
         outs = [np.empty(self.shape, dtype=np.float32) for _ in range(4)]
         self.H.lib.hh_field_export(self.h, *[_p(o) for o in outs])

@@ -18,7 +18,14 @@ struct HostField {
     int n[3], perm[3], nk[3];
     std::vector<f4> data;
     std::vector<double> aux64;
+    std::vector<double> ext[5];          // kappa, ne, B_u, B_v, B_w (kernel frame)
     AxisTables tabs[3];
+    ExtView ext_view(double verdet, bool atten, bool faraday) const {
+        ExtView X; X.verdet = verdet;
+        X.ch[0] = (atten && !ext[0].empty()) ? ext[0].data() : nullptr;
+        for (int c = 1; c < 5; ++c) X.ch[c] = (faraday && !ext[c].empty()) ? ext[c].data() : nullptr;
+        return X;
+    }
     FieldView<double> view64() const {
         FieldView<double> V;
         V.data = data.data(); V.aux64 = aux64.empty() ? nullptr : aux64.data();
@@ -269,5 +276,54 @@ extern "C" void hh_rhs_fp32(void* hnd, const double* s, uint64_t n, double* out)
         deriv<float, false, false>(F, cc, 0.f, p, v, d);
         for (int k = 0; k < 3; ++k) { out[(uint64_t)f->perm[k] * n + i] = d.dp[k]; out[(uint64_t)(3 + f->perm[k]) * n + i] = d.dv[k]; }
         out[6 * n + i] = out[7 * n + i] = out[8 * n + i] = 0;
+    }
+}
+
+// attenuation / Faraday channels: same repacking as sp_field_attach_channels (inputs [x][y][z], B as 3 grids)
+extern "C" void hh_attach(void* hnd, const double* kappa, const double* ne, const double* bx, const double* by, const double* bz) {
+    HostField* f = (HostField*)hnd;
+    PackArgs P; memset(&P, 0, sizeof(P));
+    for (int a = 0; a < 3; ++a) { P.n[a] = f->n[a]; P.perm[a] = f->perm[a]; P.nk[a] = f->nk[a]; }
+    const double* b[3] = {bx, by, bz};
+    const double* src[5] = {kappa, ne, b[f->perm[0]], b[f->perm[1]], b[f->perm[2]]};
+    const long long cells = (long long)f->n[0] * f->n[1] * f->n[2];
+    for (int c = 0; c < 5; ++c) {
+        f->ext[c].clear();
+        if (!src[c]) continue;
+        f->ext[c].resize(cells);
+        for (long long t = 0; t < cells; ++t) { int ic[3]; f->ext[c][t] = src[c][unpack_index(t, P, ic)]; }
+    }
+}
+
+extern "C" void hh_rhs_ext(void* hnd, const double* s, uint64_t n, double* out, double omega, double verdet) {
+    const HostField* f = (const HostField*)hnd;
+    FieldView<double> F = f->view64();
+    const ExtView X = f->ext_view(verdet, true, true);
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray<double> r; load(f, s, n, i, r);
+        Deriv<double> d; CellCache<double, true> cc;
+        const int inside = deriv<double, true, true>(F, cc, omega, r.p, r.v, d);
+        for (int k = 0; k < 3; ++k) { out[(uint64_t)f->perm[k] * n + i] = d.dp[k]; out[(uint64_t)(3 + f->perm[k]) * n + i] = d.dv[k]; }
+        double x[5];
+        ext_eval<true>(F, X, cc, inside != 0, r.p, x);
+        out[6 * n + i] = x[0] * s[6 * n + i];
+        out[7 * n + i] = d.dph;
+        out[8 * n + i] = verdet * x[1] * (x[2] * r.v[0] + x[3] * r.v[1] + x[4] * r.v[2]);
+    }
+}
+
+extern "C" void hh_rk4_ext(void* hnd, const double* s0, uint64_t n, int n_steps, double h, double omega, double verdet,
+                           int early, double* sf) {
+    const HostField* f = (const HostField*)hnd;
+    FieldView<double> F = f->view64();
+    const ExtView X = f->ext_view(verdet, true, true);
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray<double> r; load(f, s0, n, i, r);
+        ExtState e; e.amp = s0[6 * n + i]; e.pol = s0[8 * n + i];
+        CellCache<double, true> cc;
+        for (int it = 0; it < n_steps; ++it)
+            if (rk4_step_ext<true, true>(F, X, cc, h, omega, true, r, e, early != 0) < 0) break;
+        for (int k = 0; k < 3; ++k) { sf[(uint64_t)f->perm[k] * n + i] = r.p[k]; sf[(uint64_t)(3 + f->perm[k]) * n + i] = r.v[k]; }
+        sf[6 * n + i] = e.amp; sf[7 * n + i] = r.ph; sf[8 * n + i] = e.pol;
     }
 }

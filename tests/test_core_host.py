@@ -121,6 +121,26 @@ def test_rk45_per_ray_matches_solve_ivp(H, golden):
     assert np.all(err_ours <= 2 * err_scipy + 1e-12)
 
 
+def test_attenuation_and_faraday_channels(H, golden):
+    g = golden("g6_channels")
+    lwl, ext = float(g["lwl"]), float(g["extent"])
+    f = H.field(g["ne"], g["x"], g["y"], g["z"], omega_of(lwl), phase=True, f64=True)
+    f.attach(g["kappa"], g["ne"], g["B"])
+    verdet = 2.62e-13 * lwl ** 2
+    out = f.rhs_ext(g["s"], verdet)
+    ref = g["dsdt"]
+    assert np.array_equal(out[6] == 0, ref[6] == 0) and np.array_equal(out[8] == 0, ref[8] == 0)
+    assert np.max(np.abs(out[6] - ref[6])) < 1e-12 * np.abs(ref[6]).max()
+    assert np.max(np.abs(out[8] - ref[8])) < 1e-12 * np.abs(ref[8]).max()
+    n = int(g["rk4_nsteps"])
+    sf = f.rk4_ext(g["s0"], n, np.sqrt(8.0) * ext / C_LIGHT / n, verdet)
+    assert rel_err(sf[:6], g["rk4_sf"][:6], floor=1e-6) < 1e-10
+    assert np.max(np.abs(sf[6] - g["rk4_sf"][6])) < 1e-10 * np.abs(g["rk4_sf"][6]).max()       # amplitude
+    assert np.max(np.abs(sf[7] - g["rk4_sf"][7])) < 1e-10 * np.abs(g["rk4_sf"][7]).max()       # phase
+    assert np.max(np.abs(sf[8] - g["rk4_sf"][8])) < 1e-10 * np.abs(g["rk4_sf"][8]).max()       # polarisation
+    assert np.ptp(g["rk4_sf"][6]) > 1e-3 and np.abs(g["rk4_sf"][8]).max() > 1e-6                # channels are live
+
+
 def test_fp32_mode_within_1e4(H, golden):
     """FP32 state/arithmetic (the JAX generation's default precision) against the FP64 oracle.  The golden rays
     start at z = -extent, which is OUTSIDE the float32-rounded z[0] in float64 but ON it once rounded to

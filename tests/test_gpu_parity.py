@@ -264,6 +264,35 @@ def test_fused_path_equals_two_stage(sp, golden):
     assert np.array_equal(sh.H, specs[0].image.result().cpu().numpy())
 
 
+def test_attenuation_and_faraday_channels(sp, golden):
+    """All nine state rows: amp' = kappa amp (inverse bremsstrahlung), pol' = V ne B.v (Faraday), phase."""
+    g = golden("g6_channels")
+    lwl, ext = float(g["lwl"]), float(g["extent"])
+    d = sp.ScalarDomain(g["x"], g["y"], g["z"], ext, B_on=True, inv_brems=True, phaseshift=True)
+    d.external_ne(g["ne"]); d.external_B(g["B"]); d.external_Te(g["Te"]); d.external_Z(g["Z"])
+    d.calc_dndr(lwl)
+    d.set_up_interps()
+    out, ref = d.dsdt(g["s"]), g["dsdt"]
+    assert np.array_equal(out[:3], ref[:3]) and rel_err(out[3:6], ref[3:6], floor=1e3) < 1e-11
+    for row in (6, 8):
+        assert np.array_equal(out[row] == 0, ref[row] == 0)
+        assert np.max(np.abs(out[row] - ref[row])) < 1e-12 * np.abs(ref[row]).max()
+    n = int(g["rk4_nsteps"])
+    rf, Jf = d.solve(g["s0"], return_E=True, method="rk4", n_steps=n, h=np.sqrt(8.0) * ext / C_LIGHT / n)
+    assert rel_err(d.sf[:6], g["rk4_sf"][:6], floor=1e-6) < 1e-10
+    for row in (6, 7, 8):
+        assert np.max(np.abs(d.sf[row] - g["rk4_sf"][row])) < 1e-10 * np.abs(g["rk4_sf"][row]).max()
+    assert rel_err(rf, g["rk4_rf"], floor=1e-7) < 1e-9 and np.max(np.abs(Jf - g["rk4_Jf"])) < 1e-8
+    # current-API domain with the same channels
+    from synthpy_b200 import domain as Dm, propagator as P
+    dom = Dm.ScalarDomain([10e-3, 10e-3, 20e-3], [24, 20, 28], phaseshift=True, B_on=True, inv_brems=True)
+    dom.external_ne(g["ne"]); dom.external_B(g["B"]); dom.external_Te(g["Te"]); dom.external_Z(g["Z"])
+    rf2, Jf2, _ = P.solve(g["s0"], dom, ext, lwl=lwl, return_E=True, method="rk4", n_steps=n, early_exit=False, phase_f64=True)
+    assert rel_err(rf2, g["rk4_rf"], floor=1e-7) < 1e-9 and np.max(np.abs(Jf2 - g["rk4_Jf"])) < 1e-8
+    with pytest.raises(Exception, match="float64 RK4 only"):
+        P.solve(g["s0"], dom, ext, lwl=lwl, method="rk45")
+
+
 def test_device_beam_partition_invariance_and_statistics(sp):
     from synthpy_b200 import beam as B, engine
     b = B.Beam(100000, 4e-3, 5e-5, 10e-3, device=True, seed=11)

@@ -130,3 +130,20 @@ def test_docstring_kats(golden):
     d = O.Domain(xs, ys, zs, 5e-3)
     d.test_linear_cos(s1=-1, s2=1, n_e0=1e26, Ly=5e-3)
     assert np.array_equal(d.ne.sum(axis=2), g["linear_cos_integrated"])
+
+
+def test_attenuation_and_faraday_channels(golden):
+    """Rows 6 (inverse bremsstrahlung) and 8 (Faraday rotation) of the 9-vector ODE, full_solver.py:243-268,356-374."""
+    g = golden("g6_channels")
+    d = O.Domain(g["x"], g["y"], g["z"], float(g["extent"]), phaseshift=True, B_on=True, inv_brems=True)
+    d.external_ne(g["ne"]); d.external_B(g["B"]); d.external_Te(g["Te"]); d.external_Z(g["Z"])
+    d.calc_dndr(float(g["lwl"]))
+    d.set_up_interps()
+    assert np.array_equal(d.kappa(), g["kappa"])
+    out = d.dsdt(0.0, g["s"].ravel().copy()).reshape(9, -1)
+    assert np.array_equal(out, g["dsdt"])
+    assert np.abs(out[6]).max() > 0 and np.abs(out[8]).max() > 0
+    sf, _ = d.solve_rk4(g["s0"], int(g["rk4_nsteps"]))
+    assert np.array_equal(sf, g["rk4_sf"])
+    rf, Jf = O.ray_to_jones(sf, float(g["extent"]))
+    assert np.array_equal(rf, g["rk4_rf"]) and np.array_equal(Jf, g["rk4_Jf"])
