@@ -34,14 +34,14 @@ def test_every_declared_symbol_is_exported(lib):
 def test_binding_covers_header():
     from synthpy_b200 import _lib
     assert sorted(_lib.EXPORTS) == declared_symbols()
-    assert _lib.lib.sp_version() == 1
+    assert _lib.lib.sp_version() == 2
 
 
 def test_struct_sizes_match_header_layout():
     from synthpy_b200 import _lib as L
     assert ctypes.sizeof(L.OpticOp) == 32 and ctypes.sizeof(L.Beam) == 48
     assert ctypes.sizeof(L.Image) == 64 and ctypes.sizeof(L.Channel) == 88
-    assert ctypes.sizeof(L.Params) == 80 and ctypes.sizeof(L.Stats) == 48
+    assert ctypes.sizeof(L.Params) == 88 and ctypes.sizeof(L.Stats) == 48
 
 
 def test_no_cpu_fallback():
