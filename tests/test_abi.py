@@ -85,3 +85,13 @@ def test_error_codes_without_touching_the_gpu():
     import pytest
     with pytest.raises(L.SynthpyB200Error, match="synthpy_b200 error -1"):
         L.check(lib.sp_rhs(None, None, None, 0, None, None))
+
+
+def test_integration_stub_matches_binding():
+    """The ctypes stub printed in INTEGRATION.md declares sp_params exactly like the shipped binding."""
+    from synthpy_b200 import _lib as L
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = md[md.index("class Params(C.Structure)"):md.index("def check(rc)")]
+    names = re.findall(r'\("(\w+)", C\.c_(\w+)\)', block)
+    assert [n for n, _ in names] == [n for n, _ in L.Params._fields_]
+    assert [t for _, t in names] == [f[1].__name__.replace("c_", "") for f in L.Params._fields_]
