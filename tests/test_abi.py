@@ -94,4 +94,6 @@ def test_integration_stub_matches_binding():
     block = md[md.index("class Params(C.Structure)"):md.index("def check(rc)")]
     names = re.findall(r'\("(\w+)", C\.c_(\w+)\)', block)
     assert [n for n, _ in names] == [n for n, _ in L.Params._fields_]
-    assert [t for _, t in names] == [f[1].__name__.replace("c_", "") for f in L.Params._fields_]
+    stub = type("Stub", (ctypes.Structure,), {"_fields_": [(n, getattr(ctypes, "c_" + t)) for n, t in names]})
+    assert ctypes.sizeof(stub) == ctypes.sizeof(L.Params)
+    assert all(getattr(stub, n).offset == getattr(L.Params, n).offset for n, _ in names)
