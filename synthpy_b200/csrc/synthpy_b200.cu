@@ -1041,12 +1041,6 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
         int rc = channel_to_dev(channels_host + c, E.ch[c]);
         if (rc) return rc;
     }
-    if (P->method == SP_METHOD_RK45_JOINT) {
-        if (!s0_dev) return fail(SP_EINVAL, "joint RK45 needs explicit s0");
-        if (P->flags & SP_FLAG_FP32) return fail(SP_EINVAL, "joint RK45 is float64 only");
-        return joint_solve(field, P, ws, s0_dev, n, E, stats_dev, st);
-    }
-    if (P->method != SP_METHOD_RK4 && P->method != SP_METHOD_RK45) return fail(SP_EINVAL, "unknown method");
     const bool ext = (P->flags & (SP_FLAG_ATTEN | SP_FLAG_FARADAY)) != 0;
     if (ext) {
         if (P->method != SP_METHOD_RK4 || (P->flags & SP_FLAG_FP32))
@@ -1055,6 +1049,12 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
         if ((P->flags & SP_FLAG_FARADAY) && !(field->ext[1] && field->ext[2] && field->ext[3] && field->ext[4]))
             return fail(SP_ESTATE, "SP_FLAG_FARADAY without ne and B grids (sp_field_attach_channels)");
     }
+    if (P->method == SP_METHOD_RK45_JOINT) {
+        if (!s0_dev) return fail(SP_EINVAL, "joint RK45 needs explicit s0");
+        if (P->flags & SP_FLAG_FP32) return fail(SP_EINVAL, "joint RK45 is float64 only");
+        return joint_solve(field, P, ws, s0_dev, n, E, stats_dev, st);
+    }
+    if (P->method != SP_METHOD_RK4 && P->method != SP_METHOD_RK45) return fail(SP_EINVAL, "unknown method");
     const bool ext_aux64 = ext && (P->flags & SP_FLAG_PHASE) && (P->flags & SP_FLAG_PHASE_F64);
 
     const bool fp32 = (P->flags & SP_FLAG_FP32) != 0;

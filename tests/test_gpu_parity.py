@@ -291,6 +291,8 @@ def test_attenuation_and_faraday_channels(sp, golden):
     assert rel_err(rf2, g["rk4_rf"], floor=1e-7) < 1e-9 and np.max(np.abs(Jf2 - g["rk4_Jf"])) < 1e-8
     with pytest.raises(Exception, match="float64 RK4 only"):
         P.solve(g["s0"], dom, ext, lwl=lwl, method="rk45")
+    with pytest.raises(Exception, match="float64 RK4 only"):
+        d.solve(g["s0"])                                    # legacy default = joint RK45: refused, not silently wrong
 
 
 def test_device_beam_partition_invariance_and_statistics(sp):
