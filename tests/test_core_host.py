@@ -53,6 +53,28 @@ def test_rhs_matches_reference(H, golden):
     assert np.all(np.abs(out[7] - g["dsdt_phase1"][7]) <= 1e-15 * f.omega + 2e-7 * np.abs(g["dsdt_phase1"][7]))
 
 
+def test_non_uniform_axes(H):
+    """The legacy API takes arbitrary ascending axes (full_solver.py:102-120): the cell search walks the real table."""
+    rng = np.random.default_rng(8)
+    x = np.cumsum(rng.uniform(0.5, 2.0, 19)); x = (x - x.mean()) * 1e-3 / 3
+    y = np.sort(rng.uniform(-4e-3, 4e-3, 15)); z = np.linspace(-1, 1, 23) ** 3 * 8e-3
+    ne = 1e25 * (1 + 0.5 * rng.random((19, 15, 23)))
+    d = O.Domain(x, y, z, 8e-3)
+    d.external_ne(ne)
+    d.calc_dndr(1064e-9)
+    f = H.field(ne, x, y, z, omega_of(1064e-9))
+    gx, gy, gz, _ = f.export()
+    assert np.array_equal(gx, d.grads[0]) and np.array_equal(gy, d.grads[1]) and np.array_equal(gz, d.grads[2])
+    s = np.zeros((9, 3000))
+    s[0], s[1], s[2] = rng.uniform(x[0] * 1.1, x[-1] * 1.1, 3000), rng.uniform(-4.4e-3, 4.4e-3, 3000), rng.uniform(-8.5e-3, 8.5e-3, 3000)
+    s[0, :19], s[2, 19:42] = np.float64(np.float32(x)), np.float64(np.float32(z))         # exactly on nodes
+    s[3:6] = 1e8
+    ref = d.dsdt(0.0, s.ravel().copy()).reshape(9, -1)
+    out = f.rhs(s)
+    assert np.array_equal(out[3:6] == 0, ref[3:6] == 0)
+    assert np.max(np.abs(out[3:6] - ref[3:6])) < 1e-11 * np.abs(ref[3:6]).max()
+
+
 def test_rk4_matches_reference_rhs_loop(H, golden):
     for name, ph in (("g2_expcos", True), ("g3_turb", False)):
         g = golden(name)

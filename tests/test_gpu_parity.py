@@ -63,6 +63,37 @@ def test_rhs_L0(sp, golden):
             assert np.all(np.abs(out[7] - ref[7]) <= 1e-15 * d.omega + 1e-12 * np.abs(ref[7]))
 
 
+def test_non_uniform_axes(sp):
+    """Arbitrary ascending axes (legacy API): bit-equal stencil, identical bounds decisions, RHS and RK4 parity."""
+    rng = np.random.default_rng(8)
+    x = np.cumsum(rng.uniform(0.5, 2.0, 19)); x = (x - x.mean()) * 1e-3 / 3
+    y = np.sort(rng.uniform(-4e-3, 4e-3, 15)); z = np.linspace(-1, 1, 23) ** 3 * 8e-3
+    ne = 1e25 * (1 + 0.5 * rng.random((19, 15, 23)))
+    o = O.Domain(x, y, z, 8e-3)
+    o.external_ne(ne)
+    o.calc_dndr(1064e-9)
+    d = sp.ScalarDomain(x, y, z, 8e-3)
+    d.external_ne(ne)
+    d.calc_dndr(1064e-9)
+    got = [t.cpu().numpy() for t in d.field.export_gradients()[:3]]
+    assert all(np.array_equal(got[a], o.grads[a]) for a in range(3))
+    s = np.zeros((9, 3000))
+    s[0], s[1], s[2] = rng.uniform(x[0] * 1.1, x[-1] * 1.1, 3000), rng.uniform(-4.4e-3, 4.4e-3, 3000), rng.uniform(-8.5e-3, 8.5e-3, 3000)
+    s[0, :19], s[2, 19:42] = np.float64(np.float32(x)), np.float64(np.float32(z))
+    s[3:6] = 1e8
+    ref = o.dsdt(0.0, s.ravel().copy()).reshape(9, -1)
+    out = d.dsdt(s)
+    assert np.array_equal(out[3:6] == 0, ref[3:6] == 0)
+    assert np.max(np.abs(out[3:6] - ref[3:6])) < 1e-11 * np.abs(ref[3:6]).max()
+    s0 = np.zeros((9, 200))
+    s0[0], s0[1], s0[2] = rng.uniform(-2e-3, 2e-3, 200), rng.uniform(-3e-3, 3e-3, 200), -8e-3
+    s0[5], s0[6] = C_LIGHT, 1.0
+    h = np.sqrt(8.0) * 8e-3 / C_LIGHT / 150
+    rf = d.solve(s0, method="rk4", n_steps=150, h=h)
+    rf_o, _ = O.ray_to_jones(o.solve_rk4(s0, 150)[0], 8e-3)
+    assert rel_err(rf, rf_o, floor=1e-7) < 1e-9
+
+
 def test_rk4_L1(sp, golden):
     for name, ph in (("g2_expcos", True), ("g3_turb", False)):
         g = golden(name)
