@@ -188,3 +188,15 @@ def test_C2_null_field_is_identity_at_full_size(mods):
     assert torch.equal(rf[1], torch.atan(s0[3] / s0[5])) and torch.equal(rf[3], torch.atan(s0[4] / s0[5]))
     x_exit = s0[0] - s0[3] * ((s0[2] - EXT) / s0[5])
     assert torch.max(torch.abs(rf[0] - x_exit)) < 1e-14
+
+
+def test_quickstart_example_runs(mods):
+    """examples/quickstart.py = the reference notebook's walkthrough; must run unchanged on the GPU."""
+    import importlib.util
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples", "quickstart.py")
+    spec = importlib.util.spec_from_file_location("quickstart", path)
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    rf = m.main(20000)
+    assert rf.shape == (4, 20000) and np.isfinite(rf).all()
