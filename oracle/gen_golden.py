@@ -200,6 +200,16 @@ def main():
     g6["s0"], g6["rk4_nsteps"] = s0, 120
     g6["rk4_sf"] = rk4(dom, s0, 120)
     g6["rk4_rf"], g6["rk4_Jf"] = fs.ray_to_Jonesvector(g6["rk4_sf"], extent, probing_direction="z")
+    # the shipped solver (joint RK45 over all 9N rows) and the per-ray variant, channels on
+    rf6, Jf6 = quiet(dom.solve, s0.copy(), return_E=True)
+    g6.update(joint_sf=dom.sf, joint_rf=rf6, joint_Jf=Jf6, joint_log=joint_log(fs, dom, s0))
+    from scipy.integrate import solve_ivp as _ivp
+    tt = np.linspace(0.0, np.sqrt(8.0) * extent / fs.c, 2)
+    pr_sf, pr_nfev = np.empty((9, 16)), np.empty(16, dtype=np.int64)
+    for i in range(16):
+        sol = _ivp(lambda t, yy: fs.dsdt(t, yy, dom), [0, tt[-1]], s0[:, i].copy(), t_eval=tt)
+        pr_sf[:, i], pr_nfev[i] = sol.y[:, -1], sol.nfev
+    g6.update(perray_sf=pr_sf, perray_nfev=pr_nfev)
     np.savez_compressed(os.path.join(OUT, "g6_channels.npz"), **g6)
 
     # ---------------------------------------------------------------- G4: optics + detector

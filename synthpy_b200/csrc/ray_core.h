@@ -578,6 +578,85 @@ SP_HD T dp5_initial_step(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega
     return fmin(fmin((T)100 * h0, h1), t_end);
 }
 
+// ---- Dormand-Prince on the full 9-component state (attenuation / Faraday channels on; slow path) ----------------
+// State y = {p[3], v[3], amp, phase, pol} in the kernel frame; the same controller arithmetic as above, written
+// generically over the nine rows exactly as scipy does (rk.py: rk_step, _estimate_error_norm).
+template <bool PHASE, bool AUX64>
+SP_HD int deriv9(const FieldView<double>& F, const ExtView& X, CellCache<double, PHASE>& cc, double omega, bool with_phase,
+                 const double* y, double* f) {
+    double a[3], n, x[5];
+    const bool in = rhs<double, PHASE, AUX64>(F, cc, y[0], y[1], y[2], a[0], a[1], a[2], n);
+    ext_eval<PHASE>(F, X, cc, in, y, x);
+    f[0] = y[3]; f[1] = y[4]; f[2] = y[5];
+    f[3] = a[0]; f[4] = a[1]; f[5] = a[2];
+    f[6] = x[0] * y[6];
+    f[7] = (PHASE && with_phase) ? omega * n : 0.0;
+    f[8] = X.verdet * x[1] * (x[2] * y[3] + x[3] * y[4] + x[4] * y[5]);
+    return in;
+}
+
+template <bool PHASE, bool AUX64>
+SP_HD int dp5_attempt9(const FieldView<double>& F, const ExtView& X, CellCache<double, PHASE>& cc, double omega, bool with_phase,
+                       double h, double rtol, double atol, const double* y, const double* k1, double* yn, double* k7,
+                       double& err_sq) {
+    const double A[5][5] = {{DP::a21, 0, 0, 0, 0}, {DP::a31, DP::a32, 0, 0, 0}, {DP::a41, DP::a42, DP::a43, 0, 0},
+                            {DP::a51, DP::a52, DP::a53, DP::a54, 0}, {DP::a61, DP::a62, DP::a63, DP::a64, DP::a65}};
+    const double Bc[6] = {DP::b1, 0.0, DP::b3, DP::b4, DP::b5, DP::b6};
+    const double Ec[7] = {DP::e1, 0.0, DP::e3, DP::e4, DP::e5, DP::e6, DP::e7};
+    double K[7][9], ys[9];
+    int touched = 0;
+    for (int i = 0; i < 9; ++i) K[0][i] = k1[i];
+    for (int s = 1; s < 6; ++s) {
+        for (int i = 0; i < 9; ++i) {
+            double acc = A[s - 1][0] * K[0][i];
+            for (int j = 1; j < s; ++j) acc += A[s - 1][j] * K[j][i];
+            ys[i] = y[i] + acc * h;
+        }
+        touched += deriv9<PHASE, AUX64>(F, X, cc, omega, with_phase, ys, K[s]);
+    }
+    for (int i = 0; i < 9; ++i) {
+        double acc = Bc[0] * K[0][i];
+        for (int j = 2; j < 6; ++j) acc += Bc[j] * K[j][i];
+        yn[i] = y[i] + h * acc;
+    }
+    touched += deriv9<PHASE, AUX64>(F, X, cc, omega, with_phase, yn, K[6]);
+    double tot = 0.0;
+    for (int i = 0; i < 9; ++i) {
+        k7[i] = K[6][i];
+        double e = Ec[0] * K[0][i];
+        for (int j = 2; j < 7; ++j) e += Ec[j] * K[j][i];
+        e *= h;
+        const double a0 = fabs(y[i]), a1 = fabs(yn[i]);
+        const double q = e / (atol + (a0 > a1 ? a0 : a1) * rtol);
+        tot += q * q;
+    }
+    err_sq = tot;
+    return touched;
+}
+
+template <bool PHASE, bool AUX64>
+SP_HD double dp5_initial_step9(const FieldView<double>& F, const ExtView& X, CellCache<double, PHASE>& cc, double omega,
+                               bool with_phase, double t_end, double rtol, double atol, const double* y, const double* f0,
+                               int& touched) {
+    if (t_end == 0.0) return 0.0;
+    double s0 = 0, s1 = 0, sc[9], y1[9], f1[9];
+    for (int i = 0; i < 9; ++i) {
+        sc[i] = atol + fabs(y[i]) * rtol;
+        double q = y[i] / sc[i]; s0 += q * q;
+        q = f0[i] / sc[i]; s1 += q * q;
+    }
+    const double d0 = sqrt(s0 / 9.0), d1 = sqrt(s1 / 9.0);
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    h0 = fmin(h0, t_end);
+    for (int i = 0; i < 9; ++i) y1[i] = y[i] + h0 * f0[i];
+    touched += deriv9<PHASE, AUX64>(F, X, cc, omega, with_phase, y1, f1);
+    double s2 = 0;
+    for (int i = 0; i < 9; ++i) { const double q = (f1[i] - f0[i]) / sc[i]; s2 += q * q; }
+    const double d2 = sqrt(s2 / 9.0) / h0;
+    const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 0.2);
+    return fmin(fmin(100 * h0, h1), t_end);
+}
+
 // ---- exit plane ------------------------------------------------------------------------------------------
 // ray_to_Jonesvector (full_solver.py:838-894): back-project to the plane coord[p] = extent; angles atan(v_a/v_p).
 // kp/ka/kb are kernel-frame indices of the probing axis and of the axes that land in rf rows (0,1) / (2,3).

@@ -327,6 +327,7 @@ extern "C" int sp_field_export_gradients(const sp_field* f, float* gx_dev, float
 #define SP_RK4_MIN_BLOCKS 4
 #endif
 #define SP_METHOD_RK4X 3      // internal: RK4 with the attenuation / Faraday channels (float64)
+#define SP_METHOD_RK45X 4     // internal: per-ray Dormand-Prince over all nine rows (channels on, float64)
 #define SP_MAX_OPS 16
 #define SP_MAX_CHANNELS 4
 
@@ -498,6 +499,58 @@ __device__ __forceinline__ void rk4x_integrate(const PropArgs<double>& A, Ray<do
     amp = e.amp; pol = e.pol;
 }
 
+// Per-ray adaptive solve over the full 9-component state (same controller as the RK45 branch of k_propagate).
+template <bool PHASE, bool AUX64, typename T>
+__device__ __forceinline__ void rk45x_integrate(const PropArgs<T>& A, Ray<T>& r, CellCache<T, PHASE>& cc, bool early, uint64_t gi,
+                                                unsigned& n_att, LaneStats& ls, double& amp, double& pol) {}
+template <bool PHASE, bool AUX64>
+__device__ __noinline__ void rk45x_integrate(const PropArgs<double>& A, Ray<double>& r, CellCache<double, PHASE>& cc, bool early,
+                                             uint64_t gi, unsigned& n_att, LaneStats& ls, double& amp, double& pol) {
+    const bool with_phase = (A.flags & SP_FLAG_PHASE) != 0;
+    double y[9], f[9], yn[9], fn[9];
+    for (int k = 0; k < 3; ++k) { y[k] = r.p[k]; y[3 + k] = r.v[k]; }
+    y[6] = A.use_beam ? 1.0 : A.s0[6 * A.n_total + gi];
+    y[7] = r.ph;
+    y[8] = A.use_beam ? 0.0 : A.s0[8 * A.n_total + gi];
+    int touched = deriv9<PHASE, AUX64>(A.F, A.X, cc, A.omega, with_phase, y, f);
+    double h_abs = dp5_initial_step9<PHASE, AUX64>(A.F, A.X, cc, A.omega, with_phase, A.t_end, A.rtol, A.atol, y, f, touched);
+    double t = 0.0;
+    const unsigned cap = A.n_steps > 0 ? (unsigned)A.n_steps : (1u << 30);
+    bool failed = false;
+    while (t < A.t_end && !failed) {
+        if (early) {
+            Ray<double> q;
+            for (int k = 0; k < 3; ++k) { q.p[k] = y[k]; q.v[k] = y[3 + k]; }
+            if (escaped(A.F, q)) break;
+        }
+        const double min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);
+        if (h_abs < min_step) h_abs = min_step;
+        bool rejected = false;
+        for (;;) {
+            if (n_att >= cap || h_abs < min_step) { failed = true; ls.capped += 1; break; }
+            double t_new = t + h_abs;
+            if (t_new - A.t_end > 0.0) t_new = A.t_end;
+            const double h = t_new - t;
+            h_abs = fabs(h);
+            double esq;
+            touched += dp5_attempt9<PHASE, AUX64>(A.F, A.X, cc, A.omega, with_phase, h, A.rtol, A.atol, y, f, yn, fn, esq);
+            ++n_att;
+            const double en = sqrt(esq / 9.0);
+            if (en < 1.0) {
+                h_abs *= dp5_factor<double>(en, true, rejected);
+                t = t_new; ls.acc += 1;
+                for (int i = 0; i < 9; ++i) { y[i] = yn[i]; f[i] = fn[i]; }
+                break;
+            }
+            h_abs *= dp5_factor<double>(en, false, rejected);
+            rejected = true;
+        }
+    }
+    ls.evals += touched;
+    for (int k = 0; k < 3; ++k) { r.p[k] = y[k]; r.v[k] = y[3 + k]; }
+    r.ph = y[7]; amp = y[6]; pol = y[8];
+}
+
 template <typename T, int METHOD, bool PHASE, bool AUX64>
 __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 8) ? SP_RK4_MIN_BLOCKS : ((METHOD == SP_METHOD_RK45 && sizeof(T) == 8) ? SP_RK45_MIN_BLOCKS : 1)) k_propagate(const PropArgs<T> A, const Epilogue E) {
     const int lane = threadIdx.x & 31;
@@ -531,6 +584,8 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
         if (valid) {
             if (METHOD == SP_METHOD_RK4X) {
                 rk4x_integrate<PHASE, AUX64>(A, r, cc, early, gi, n_att, ls, amp_x, pol_x);
+            } else if (METHOD == SP_METHOD_RK45X) {
+                rk45x_integrate<PHASE, AUX64>(A, r, cc, early, gi, n_att, ls, amp_x, pol_x);
             } else if (METHOD == SP_METHOD_RK4) {
                 const T h = A.h;
                 for (int it = 0; it < A.n_steps; ++it) {
@@ -586,7 +641,7 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
         const uint64_t N = A.n_total;
         double amp = 1.0, pol = 0.0;              // constant along the ray (zero derivative): re-read instead of kept live
         if (valid && !A.use_beam) { amp = A.s0[6 * N + gi]; pol = A.s0[8 * N + gi]; }
-        if (METHOD == SP_METHOD_RK4X) { amp = amp_x; pol = pol_x; }
+        if (METHOD == SP_METHOD_RK4X || METHOD == SP_METHOD_RK45X) { amp = amp_x; pol = pol_x; }
         if (valid) {
             if (E.sf) {
 #pragma unroll
@@ -725,6 +780,67 @@ __global__ void k_joint_attempt(FieldView<double> F, JointBuf B, uint64_t n, dou
         __syncthreads();
     }
     if (threadIdx.x == 0) B.partial[2 * blockIdx.x] = sh0[0];
+}
+
+// Joint solve with the attenuation / Faraday channels: all nine rows, state as a [9][n] SoA (kernel-frame rows
+// p, v, amp, phase, pol).  pass 0 / 1 as in k_joint_init.
+template <bool PHASE, bool AUX64>
+__global__ void k_jointx_init(FieldView<double> F, ExtView X, double* __restrict__ Y, double* __restrict__ Fy,
+                              double* __restrict__ partial, const double* __restrict__ s0, uint64_t n, int p0, int p1, int p2,
+                              double omega, int with_phase, double rtol, double atol, int pass, double h0) {
+    __shared__ double sh0[128], sh1[128];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double s_a = 0.0, s_b = 0.0;
+    if (i < n) {
+        const int perm[3] = {p0, p1, p2};
+        double y[9], f[9];
+        CellCache<double, PHASE> cc;
+        if (pass == 0) {
+            for (int k = 0; k < 3; ++k) { y[k] = s0[(uint64_t)perm[k] * n + i]; y[3 + k] = s0[(uint64_t)(3 + perm[k]) * n + i]; }
+            for (int k = 6; k < 9; ++k) y[k] = s0[(uint64_t)k * n + i];
+            deriv9<PHASE, AUX64>(F, X, cc, omega, with_phase != 0, y, f);
+            for (int k = 0; k < 9; ++k) {
+                Y[(uint64_t)k * n + i] = y[k]; Fy[(uint64_t)k * n + i] = f[k];
+                const double sc = atol + fabs(y[k]) * rtol;
+                double q = y[k] / sc; s_a += q * q; q = f[k] / sc; s_b += q * q;
+            }
+        } else {
+            double y1[9], f1[9];
+            for (int k = 0; k < 9; ++k) { y[k] = Y[(uint64_t)k * n + i]; f[k] = Fy[(uint64_t)k * n + i]; y1[k] = y[k] + h0 * f[k]; }
+            deriv9<PHASE, AUX64>(F, X, cc, omega, with_phase != 0, y1, f1);
+            for (int k = 0; k < 9; ++k) { const double q = (f1[k] - f[k]) / (atol + fabs(y[k]) * rtol); s_a += q * q; }
+        }
+    }
+    sh0[threadIdx.x] = s_a; sh1[threadIdx.x] = s_b;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { sh0[threadIdx.x] += sh0[threadIdx.x + o]; sh1[threadIdx.x] += sh1[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { partial[2 * blockIdx.x] = sh0[0]; partial[2 * blockIdx.x + 1] = sh1[0]; }
+}
+
+template <bool PHASE, bool AUX64>
+__global__ void k_jointx_attempt(FieldView<double> F, ExtView X, const double* __restrict__ Y, const double* __restrict__ Fy,
+                                 double* __restrict__ Yn, double* __restrict__ Fn, double* __restrict__ partial, uint64_t n,
+                                 double omega, int with_phase, double h, double rtol, double atol) {
+    __shared__ double sh0[128];
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    double esq = 0.0;
+    if (i < n) {
+        double y[9], f[9], yn[9], fn[9];
+        CellCache<double, PHASE> cc;
+        for (int k = 0; k < 9; ++k) { y[k] = Y[(uint64_t)k * n + i]; f[k] = Fy[(uint64_t)k * n + i]; }
+        dp5_attempt9<PHASE, AUX64>(F, X, cc, omega, with_phase != 0, h, rtol, atol, y, f, yn, fn, esq);
+        for (int k = 0; k < 9; ++k) { Yn[(uint64_t)k * n + i] = yn[k]; Fn[(uint64_t)k * n + i] = fn[k]; }
+    }
+    sh0[threadIdx.x] = esq;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) sh0[threadIdx.x] += sh0[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[2 * blockIdx.x] = sh0[0];
 }
 
 // Deterministic (fixed-order) final reduction of the per-block partials -> out[0], out[1] (mapped host memory).
@@ -1007,16 +1123,26 @@ static int joint_solve(const sp_field* field, const sp_params* P, sp_workspace* 
                        const Epilogue& E, sp_stats* stats_dev, cudaStream_t st);
 
 // attenuation / Faraday variant: float64, PHASE lane always compiled in (its integration is a run-time flag)
-static int ext_grid(int sm_count, bool aux64, int& grid) {
+static int ext_grid(int sm_count, bool adaptive, bool aux64, int& grid) {
     int per_sm = 0;
-    if (aux64) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<double, SP_METHOD_RK4X, true, true>, 128, 0));
-    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<double, SP_METHOD_RK4X, true, false>, 128, 0));
+    if (adaptive) {
+        if (aux64) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<double, SP_METHOD_RK45X, true, true>, 128, 0));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<double, SP_METHOD_RK45X, true, false>, 128, 0));
+    } else {
+        if (aux64) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<double, SP_METHOD_RK4X, true, true>, 128, 0));
+        else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<double, SP_METHOD_RK4X, true, false>, 128, 0));
+    }
     grid = sm_count * (per_sm < 1 ? 1 : per_sm);
     return SP_OK;
 }
-static int launch_ext(const PropArgs<double>& A, const Epilogue& E, bool aux64, int grid, cudaStream_t st) {
-    if (aux64) k_propagate<double, SP_METHOD_RK4X, true, true><<<grid, 128, 0, st>>>(A, E);
-    else k_propagate<double, SP_METHOD_RK4X, true, false><<<grid, 128, 0, st>>>(A, E);
+static int launch_ext(const PropArgs<double>& A, const Epilogue& E, bool adaptive, bool aux64, int grid, cudaStream_t st) {
+    if (adaptive) {
+        if (aux64) k_propagate<double, SP_METHOD_RK45X, true, true><<<grid, 128, 0, st>>>(A, E);
+        else k_propagate<double, SP_METHOD_RK45X, true, false><<<grid, 128, 0, st>>>(A, E);
+    } else {
+        if (aux64) k_propagate<double, SP_METHOD_RK4X, true, true><<<grid, 128, 0, st>>>(A, E);
+        else k_propagate<double, SP_METHOD_RK4X, true, false><<<grid, 128, 0, st>>>(A, E);
+    }
     LAUNCH_CHECK();
     return SP_OK;
 }
@@ -1043,8 +1169,7 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
     }
     const bool ext = (P->flags & (SP_FLAG_ATTEN | SP_FLAG_FARADAY)) != 0;
     if (ext) {
-        if (P->method != SP_METHOD_RK4 || (P->flags & SP_FLAG_FP32))
-            return fail(SP_EINVAL, "attenuation / Faraday channels are integrated by float64 RK4 only");
+        if (P->flags & SP_FLAG_FP32) return fail(SP_EINVAL, "attenuation / Faraday channels are float64 only");
         if ((P->flags & SP_FLAG_ATTEN) && !field->ext[0]) return fail(SP_ESTATE, "SP_FLAG_ATTEN without a kappa grid (sp_field_attach_channels)");
         if ((P->flags & SP_FLAG_FARADAY) && !(field->ext[1] && field->ext[2] && field->ext[3] && field->ext[4]))
             return fail(SP_ESTATE, "SP_FLAG_FARADAY without ne and B grids (sp_field_attach_channels)");
@@ -1067,7 +1192,7 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
     const uint32_t n_keys = 1u << (2 * bits - key_shift);
 
     int grid = 0, rc = 0;
-    if (ext) rc = ext_grid(ws->sm_count, ext_aux64, grid);
+    if (ext) rc = ext_grid(ws->sm_count, P->method == SP_METHOD_RK45, ext_aux64, grid);
     else if (fp32) rc = (P->method == SP_METHOD_RK4) ? occupancy_grid<float, SP_METHOD_RK4>(ws->sm_count, P->flags, grid)
                                                 : occupancy_grid<float, SP_METHOD_RK45>(ws->sm_count, P->flags, grid);
     else rc = (P->method == SP_METHOD_RK4) ? occupancy_grid<double, SP_METHOD_RK4>(ws->sm_count, P->flags, grid)
@@ -1120,7 +1245,7 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
         } else if (ext) {
             FILL(double)
             A.X = make_ext(field, P->verdet, P->flags);
-            rc = launch_ext(A, E, ext_aux64, g, st);
+            rc = launch_ext(A, E, P->method == SP_METHOD_RK45, ext_aux64, g, st);
         } else {
             FILL(double)
             rc = (P->method == SP_METHOD_RK4) ? launch_propagate<double, SP_METHOD_RK4>(A, E, g, st)
@@ -1169,8 +1294,27 @@ static int joint_solve(const sp_field* field, const sp_params* P, sp_workspace* 
     const double size = (double)n_state * (double)n;     // x.size of the flattened state
     uint64_t evals = 0;
 
+    // attenuation / Faraday channels on: nine-row kernels over a second set of buffers (Y, F, Yn, Fn: [9][n] each)
+    const bool ext = (P->flags & (SP_FLAG_ATTEN | SP_FLAG_FARADAY)) != 0;
+    const ExtView X = make_ext(field, P->verdet, P->flags);
+    double *Yc = nullptr, *Fc = nullptr, *Yn = nullptr, *Fn = nullptr;
+    if (ext) {
+        const size_t need_x = need + 36 * per;
+        if (need_x > ws->joint_cap) {
+            cudaFree(ws->joint); ws->joint = nullptr; ws->joint_cap = 0;
+            CU(cudaMalloc(&ws->joint, need_x * sizeof(double)));
+            ws->joint_cap = need_x;
+        }
+        B.partial = ws->joint;                               // 2 * nblocks doubles, then the four state blocks
+        Yc = ws->joint + 2 * (size_t)nblocks; Fc = Yc + 9 * per; Yn = Fc + 9 * per; Fn = Yn + 9 * per;
+    }
+    const bool ext_aux64 = ext && aux64;
+
     auto init_pass = [&](int pass, double h0) -> int {
-        if (!phase) k_joint_init<false, false><<<nblocks, threads, 0, st>>>(F, B, s0_dev, n, p0, p1, p2, omega, rtol, atol, pass, h0);
+        if (ext) {
+            if (ext_aux64) k_jointx_init<true, true><<<nblocks, threads, 0, st>>>(F, X, Yc, Fc, B.partial, s0_dev, n, p0, p1, p2, omega, phase, rtol, atol, pass, h0);
+            else k_jointx_init<true, false><<<nblocks, threads, 0, st>>>(F, X, Yc, Fc, B.partial, s0_dev, n, p0, p1, p2, omega, phase, rtol, atol, pass, h0);
+        } else if (!phase) k_joint_init<false, false><<<nblocks, threads, 0, st>>>(F, B, s0_dev, n, p0, p1, p2, omega, rtol, atol, pass, h0);
         else if (!aux64) k_joint_init<true, false><<<nblocks, threads, 0, st>>>(F, B, s0_dev, n, p0, p1, p2, omega, rtol, atol, pass, h0);
         else k_joint_init<true, true><<<nblocks, threads, 0, st>>>(F, B, s0_dev, n, p0, p1, p2, omega, rtol, atol, pass, h0);
         LAUNCH_CHECK();
@@ -1210,7 +1354,10 @@ static int joint_solve(const sp_field* field, const sp_params* P, sp_workspace* 
             if (t_new - t_end > 0) t_new = t_end;
             const double h = t_new - t;
             h_abs = fabs(h);
-            if (!phase) k_joint_attempt<false, false><<<nblocks, threads, 0, st>>>(F, B, n, omega, h, rtol, atol);
+            if (ext) {
+                if (ext_aux64) k_jointx_attempt<true, true><<<nblocks, threads, 0, st>>>(F, X, Yc, Fc, Yn, Fn, B.partial, n, omega, phase, h, rtol, atol);
+                else k_jointx_attempt<true, false><<<nblocks, threads, 0, st>>>(F, X, Yc, Fc, Yn, Fn, B.partial, n, omega, phase, h, rtol, atol);
+            } else if (!phase) k_joint_attempt<false, false><<<nblocks, threads, 0, st>>>(F, B, n, omega, h, rtol, atol);
             else if (!aux64) k_joint_attempt<true, false><<<nblocks, threads, 0, st>>>(F, B, n, omega, h, rtol, atol);
             else k_joint_attempt<true, true><<<nblocks, threads, 0, st>>>(F, B, n, omega, h, rtol, atol);
             LAUNCH_CHECK();
@@ -1228,11 +1375,16 @@ static int joint_solve(const sp_field* field, const sp_params* P, sp_workspace* 
                 // accept: candidate becomes current (pointer swap)
                 for (int k = 0; k < 3; ++k) { std::swap(B.p[k], B.pn[k]); std::swap(B.v[k], B.vn[k]); std::swap(B.fv[k], B.fvn[k]); }
                 std::swap(B.ph, B.phn); std::swap(B.fph, B.fphn);
+                std::swap(Yc, Yn); std::swap(Fc, Fn);
                 break;
             }
             h_abs *= fmax(DP::MIN_FACTOR, DP::SAFETY * pow(en, -0.2));
             rejected = true;
         }
+    }
+    if (ext) {                                               // present the nine-row state through the JointBuf view
+        for (int k = 0; k < 3; ++k) { B.p[k] = Yc + (size_t)k * per; B.v[k] = Yc + (size_t)(3 + k) * per; }
+        B.amp = Yc + 6 * per; B.ph = Yc + 7 * per; B.pol = Yc + 8 * per;
     }
     k_joint_finish<<<nblocks, threads, 0, st>>>(B, n, 0, p0, p1, p2, kernel_index_of(field, P->probing_axis),
                                                 kernel_index_of(field, P->out_axis_a), kernel_index_of(field, P->out_axis_b),

@@ -103,6 +103,14 @@ class HField:
                               C.c_double(verdet), C.c_int(int(early)), _p(sf))
         return sf
 
+    def rk45_ext(self, s0, t_end, verdet, rtol=1e-3, atol=1e-6):
+        s0 = np.ascontiguousarray(s0, dtype=np.float64)
+        sf = np.empty_like(s0)
+        nfev = np.empty(s0.shape[1], dtype=np.uint32)
+        self.H.lib.hh_rk45_ext(self.h, _p(s0), C.c_uint64(s0.shape[1]), C.c_double(t_end), C.c_double(rtol), C.c_double(atol),
+                               C.c_double(self.omega), C.c_double(verdet), _p(sf), _p(nfev))
+        return sf, nfev
+
     def export(self):
         outs = [np.empty(self.shape, dtype=np.float32) for _ in range(4)]
         self.H.lib.hh_field_export(self.h, *[_p(o) for o in outs])

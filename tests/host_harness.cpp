@@ -327,3 +327,44 @@ extern "C" void hh_rk4_ext(void* hnd, const double* s0, uint64_t n, int n_steps,
         sf[6 * n + i] = e.amp; sf[7 * n + i] = r.ph; sf[8 * n + i] = e.pol;
     }
 }
+
+// per-ray adaptive solve over all nine rows (channels on): the loop of rk45x_integrate in synthpy_b200.cu
+extern "C" void hh_rk45_ext(void* hnd, const double* s0, uint64_t n, double t_end, double rtol, double atol, double omega,
+                            double verdet, double* sf, uint32_t* nfev) {
+    const HostField* f = (const HostField*)hnd;
+    FieldView<double> F = f->view64();
+    const ExtView X = f->ext_view(verdet, true, true);
+    for (uint64_t i = 0; i < n; ++i) {
+        double y[9], fy[9], yn[9], fn[9];
+        for (int k = 0; k < 3; ++k) { y[k] = s0[(uint64_t)f->perm[k] * n + i]; y[3 + k] = s0[(uint64_t)(3 + f->perm[k]) * n + i]; }
+        for (int k = 6; k < 9; ++k) y[k] = s0[(uint64_t)k * n + i];
+        CellCache<double, true> cc;
+        int touched = 0; uint32_t evals = 2;
+        deriv9<true, true>(F, X, cc, omega, true, y, fy);
+        double h_abs = dp5_initial_step9<true, true>(F, X, cc, omega, true, t_end, rtol, atol, y, fy, touched);
+        double t = 0;
+        while (t < t_end) {
+            const double min_step = 10 * (nextafter(t, INFINITY) - t);
+            if (h_abs < min_step) h_abs = min_step;
+            bool rejected = false, failed = false;
+            for (;;) {
+                if (h_abs < min_step) { failed = true; break; }
+                double t_new = t + h_abs;
+                if (t_new - t_end > 0) t_new = t_end;
+                const double h = t_new - t;
+                h_abs = fabs(h);
+                double esq;
+                dp5_attempt9<true, true>(F, X, cc, omega, true, h, rtol, atol, y, fy, yn, fn, esq);
+                evals += 6;
+                const double en = sqrt(esq / 9.0);
+                if (en < 1) { h_abs *= dp5_factor<double>(en, true, rejected); t = t_new; for (int k = 0; k < 9; ++k) { y[k] = yn[k]; fy[k] = fn[k]; } break; }
+                h_abs *= dp5_factor<double>(en, false, rejected);
+                rejected = true;
+            }
+            if (failed) break;
+        }
+        for (int k = 0; k < 3; ++k) { sf[(uint64_t)f->perm[k] * n + i] = y[k]; sf[(uint64_t)(3 + f->perm[k]) * n + i] = y[3 + k]; }
+        for (int k = 6; k < 9; ++k) sf[(uint64_t)k * n + i] = y[k];
+        if (nfev) nfev[i] = evals;
+    }
+}

@@ -161,6 +161,13 @@ def test_attenuation_and_faraday_channels(H, golden):
     assert np.max(np.abs(sf[7] - g["rk4_sf"][7])) < 1e-10 * np.abs(g["rk4_sf"][7]).max()       # phase
     assert np.max(np.abs(sf[8] - g["rk4_sf"][8])) < 1e-10 * np.abs(g["rk4_sf"][8]).max()       # polarisation
     assert np.ptp(g["rk4_sf"][6]) > 1e-3 and np.abs(g["rk4_sf"][8]).max() > 1e-6                # channels are live
+    # adaptive, per ray, all nine rows in the error norm: same accept/reject sequence as solve_ivp
+    sf, nfev = f.rk45_ext(g["s0"][:, :16], np.sqrt(8.0) * ext / C_LIGHT, verdet)
+    assert np.array_equal(nfev, g["perray_nfev"])
+    ref = g["perray_sf"]
+    assert np.max(np.abs(sf[:3] - ref[:3])) < 1e-9 * ext and np.max(np.abs(sf[3:6] - ref[3:6])) < 1e-9 * C_LIGHT
+    for row in (6, 7, 8):
+        assert np.max(np.abs(sf[row] - ref[row])) < 1e-9 * np.abs(ref[row]).max()
 
 
 def test_fp32_mode_within_1e4(H, golden):

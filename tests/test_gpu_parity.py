@@ -297,6 +297,7 @@ def test_fused_path_equals_two_stage(sp, golden):
 
 def test_attenuation_and_faraday_channels(sp, golden):
     """All nine state rows: amp' = kappa amp (inverse bremsstrahlung), pol' = V ne B.v (Faraday), phase."""
+    from synthpy_b200 import engine
     g = golden("g6_channels")
     lwl, ext = float(g["lwl"]), float(g["extent"])
     d = sp.ScalarDomain(g["x"], g["y"], g["z"], ext, B_on=True, inv_brems=True, phaseshift=True)
@@ -320,10 +321,19 @@ def test_attenuation_and_faraday_channels(sp, golden):
     dom.external_ne(g["ne"]); dom.external_B(g["B"]); dom.external_Te(g["Te"]); dom.external_Z(g["Z"])
     rf2, Jf2, _ = P.solve(g["s0"], dom, ext, lwl=lwl, return_E=True, method="rk4", n_steps=n, early_exit=False, phase_f64=True)
     assert rel_err(rf2, g["rk4_rf"], floor=1e-7) < 1e-9 and np.max(np.abs(Jf2 - g["rk4_Jf"])) < 1e-8
-    with pytest.raises(Exception, match="float64 RK4 only"):
-        P.solve(g["s0"], dom, ext, lwl=lwl, method="rk45")
-    with pytest.raises(Exception, match="float64 RK4 only"):
-        d.solve(g["s0"])                                    # legacy default = joint RK45: refused, not silently wrong
+    # the shipped algorithm (joint RK45 over all nine rows) and the per-ray variant
+    rf = d.solve(g["s0"])
+    h_log, en_log = engine.joint_log()
+    assert len(h_log) == g["joint_log"].shape[1] and np.allclose(h_log, g["joint_log"][0], rtol=1e-9, atol=0)
+    assert np.max(np.abs(d.sf[:3] - g["joint_sf"][:3])) < 1e-9 * ext and np.max(np.abs(rf - g["joint_rf"])) < 1e-9
+    for row in (6, 7, 8):
+        assert np.max(np.abs(d.sf[row] - g["joint_sf"][row])) < 1e-9 * np.abs(g["joint_sf"][row]).max()
+    d.solve(g["s0"][:, :16], method="rk45")
+    assert np.array_equal(6 * d.steps.astype(np.int64) + 2, g["perray_nfev"])
+    for row in (6, 7, 8):
+        assert np.max(np.abs(d.sf[row] - g["perray_sf"][row])) < 1e-9 * np.abs(g["perray_sf"][row]).max()
+    with pytest.raises(Exception, match="float64 only"):
+        d.solve(g["s0"], method="rk4", n_steps=10, h=1e-12, fp32=True)
 
 
 def test_device_beam_partition_invariance_and_statistics(sp):

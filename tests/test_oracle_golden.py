@@ -147,3 +147,6 @@ def test_attenuation_and_faraday_channels(golden):
     assert np.array_equal(sf, g["rk4_sf"])
     rf, Jf = O.ray_to_jones(sf, float(g["extent"]))
     assert np.array_equal(rf, g["rk4_rf"]) and np.array_equal(Jf, g["rk4_Jf"])
+    assert np.array_equal(d.solve_joint(g["s0"]), g["joint_sf"])
+    sf1, nfev = d.solve_per_ray(g["s0"][:, :4])
+    assert np.array_equal(sf1, g["perray_sf"][:, :4]) and np.array_equal(nfev, g["perray_nfev"][:4])
