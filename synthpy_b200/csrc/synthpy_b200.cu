@@ -320,6 +320,9 @@ extern "C" int sp_field_export_gradients(const sp_field* f, float* gx_dev, float
 }
 
 // -------------------------------------------------------------------------------------- detector channels
+#ifndef SP_RK4F_MIN_BLOCKS
+#define SP_RK4F_MIN_BLOCKS 1
+#endif
 #ifndef SP_RK45_MIN_BLOCKS
 #define SP_RK45_MIN_BLOCKS 3
 #endif
@@ -552,7 +555,7 @@ __device__ __noinline__ void rk45x_integrate(const PropArgs<double>& A, Ray<doub
 }
 
 template <typename T, int METHOD, bool PHASE, bool AUX64>
-__global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 8) ? SP_RK4_MIN_BLOCKS : ((METHOD == SP_METHOD_RK45 && sizeof(T) == 8) ? SP_RK45_MIN_BLOCKS : 1)) k_propagate(const PropArgs<T> A, const Epilogue E) {
+__global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 8) ? SP_RK4_MIN_BLOCKS : ((METHOD == SP_METHOD_RK45 && sizeof(T) == 8) ? SP_RK45_MIN_BLOCKS : ((METHOD == SP_METHOD_RK4 && sizeof(T) == 4) ? SP_RK4F_MIN_BLOCKS : 1))) k_propagate(const PropArgs<T> A, const Epilogue E) {
     const int lane = threadIdx.x & 31;
     const bool early = (A.flags & SP_FLAG_EARLY_EXIT) != 0;
     for (;;) {
