@@ -347,6 +347,46 @@ def test_device_beam_partition_invariance_and_statistics(sp):
     assert np.allclose(np.linalg.norm(full[3:6], axis=0), C_LIGHT, rtol=1e-12)
 
 
+def test_device_beam_equals_host_build_and_all_types(sp):
+    """sp_beam_generate (device Philox) against the host build of the same source, for every beam type / axis."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from harness import Harness
+    from synthpy_b200 import engine, _lib as L
+    H = Harness()
+    for bt in range(5):
+        for pd, ax in (("x", 0), ("y", 1), ("z", 2)):
+            spec = L.Beam(beam_type=bt, probing_axis=ax, size_a=3e-3, size_b=1.5e-3, divergence=1e-4, start=-7e-3, seed=99)
+            dev = engine.beam_generate(spec, 4096, ray_offset=123456789012).cpu().numpy()
+            host = H.beam(bt, ax, 3e-3, 1.5e-3, 1e-4, -7e-3, 99, 123456789012, 4096)
+            assert np.max(np.abs(dev[:3] - host[:3])) < 1e-17 + 1e-14 * 3e-3, (bt, pd)
+            assert np.max(np.abs(dev[3:6] - host[3:6])) < 1e-13 * C_LIGHT, (bt, pd)
+            assert np.all(dev[6] == 1) and np.all(dev[7] == 0) and np.all(dev[8] == 0)
+            if bt != 4:
+                assert np.all(dev[ax] == -7e-3)
+    # rectangular: uniform in [-a, a] x [-b, b]
+    spec = L.Beam(beam_type=3, probing_axis=2, size_a=3e-3, size_b=1.5e-3, divergence=1e-4, start=-7e-3, seed=5)
+    s0 = engine.beam_generate(spec, 200000).cpu().numpy()
+    assert abs(np.abs(s0[0]).max() - 3e-3) < 1e-6 and abs(np.abs(s0[1]).max() - 1.5e-3) < 1e-6
+    assert abs(s0[0].std() - 3e-3 / np.sqrt(3)) < 2e-5 and abs(s0[1].std() - 1.5e-3 / np.sqrt(3)) < 1e-5
+
+
+def test_current_api_probing_y_axis_convention(sp, golden):
+    """The current API swaps the exit-plane axes for 'y' probing (propagator.py:235-243: rows = z, x) relative to
+    the legacy solver (full_solver.py:866-872: rows = x, z); both are offered."""
+    from synthpy_b200 import domain as Dm, propagator as P
+    g = golden("g3_turb")
+    ext = float(g["extent"])
+    dom = Dm.ScalarDomain([10e-3, 20e-3, 10e-3], list(g["ne"].shape), probing_direction="y")
+    dom.external_ne(g["ne"])
+    h = np.sqrt(8.0) * ext / C_LIGHT / 120
+    rf_cur, _, _ = P.solve(g["y_s0"], dom, ext, lwl=float(g["lwl"]), method="rk4", n_steps=120, early_exit=False)
+    rf_leg, _, _ = P.solve(g["y_s0"], dom, ext, lwl=float(g["lwl"]), method="rk4", n_steps=120, early_exit=False,
+                           axis_convention="legacy")
+    assert rel_err(rf_leg, g["y_rf"], floor=1e-7) < 1e-9
+    assert np.array_equal(rf_cur[[2, 3, 0, 1]], rf_leg)
+
+
 def test_edge_cases(sp, golden):
     from synthpy_b200 import engine
     g = golden("g3_turb")
