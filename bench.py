@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4"],
                     help="C2 shadowgraphy+schlieren (default, the headline); C3 interferometry with phase accumulation; "
                          "C4 refractometry + knife-edge schlieren with adaptive RK45")
+    ap.add_argument("--bundle", action="store_true", help="C4: one step size per 32-ray bundle instead of per ray")
     ap.add_argument("--rtol", type=float, default=1e-3)
     ap.add_argument("--atol", type=float, default=1e-6)
     return ap.parse_args()
@@ -193,7 +194,7 @@ def workload_config(a):
     diag = {"C2": "shadowgraphy(two-lens) + schlieren(DF)", "C3": "interferometry(two-lens, phase accumulation, reference beam)",
             "C4": "refractometry(incoherent) + knife-edge schlieren"}[a.workload]
     integ = (f"rk4, ds = {a.ds_frac:g} cell, early exit" if a.workload != "C4" else
-             f"rk45 per ray (SciPy controller), rtol {a.rtol:g} atol {a.atol:g}, early exit")
+             f"rk45 {'per 32-ray bundle' if a.bundle else 'per ray'} (SciPy controller), rtol {a.rtol:g} atol {a.atol:g}, early exit")
     return {"workload": f"{a.workload}: {int(a.rays):d} rays/GPU through a {a.grid}^3 turbulent (k^-11/3) n_e field, "
                         f"{diag} at bin_scale {a.bin_scale}",
             "grid": a.grid, "rays_per_gpu": int(a.rays), "integrator": integ,
@@ -231,7 +232,7 @@ def run_ours(a):
     else:                          # BASELINE configs[3]: refractometry + knife-edge schlieren, adaptive RK45 (SciPy controller)
         specs = [D.spec("refracto_incoherent", bin_scale=a.bin_scale),
                  D.spec("schlieren_knife", bin_scale=a.bin_scale, offset=0.1, axis=2, direction=1)]
-        kw.update(method="rk45", rtol=a.rtol, atol=a.atol, max_steps=1000000)
+        kw.update(method="rk45_bundle" if a.bundle else "rk45", rtol=a.rtol, atol=a.atol, max_steps=1000000)
         kw.pop("ds")
     beam = B.Beam(n_rays, BEAM_R, BEAM_DIV, EXTENT, device=True, seed=2, beam_type="circular")
 

@@ -179,6 +179,8 @@ int sp_image_finalize(const sp_image* img, double* H_dev, void* stream);
 #define SP_FLAG_NO_SORT 16   /* do not reorder rays into coherent bundles                                    */
 #define SP_FLAG_ATTEN 32     /* integrate amp' = kappa(r) amp            (full_solver.py:540)                */
 #define SP_FLAG_FARADAY 64   /* integrate pol' = verdet ne(r) (B(r).v)   (full_solver.py:542)                */
+#define SP_FLAG_BUNDLE_STEP 128 /* SP_METHOD_RK45: one step size per 32-ray bundle (the shipped joint solver applied to
+                                   32-ray chunks; lanes stay in lock-step).  Results depend on bundle membership.  */
 
 typedef struct sp_params {
     int32_t method;

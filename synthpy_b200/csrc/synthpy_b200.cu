@@ -458,6 +458,21 @@ __global__ void k_sort_scatter(const uint32_t* __restrict__ keys, uint32_t* __re
     order[atomicAdd(cursor + keys[i], 1u)] = i;
 }
 
+// The scatter above fills each key's segment in atomic (i.e. arbitrary) order; sorting every segment by ray index
+// makes the bundle order -- and with it bundle-step results and the order of float64 interferogram sums within a
+// warp -- reproducible from run to run.  Segments are short (rays per cell column), one thread each.
+__global__ void k_sort_fix(const uint32_t* __restrict__ seg_end, uint32_t* __restrict__ order, uint32_t n_keys) {
+    const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= n_keys) return;
+    const uint32_t b = key ? seg_end[key - 1] : 0u, e = seg_end[key];
+    for (uint32_t i = b + 1; i < e; ++i) {
+        const uint32_t v = order[i];
+        uint32_t j = i;
+        while (j > b && order[j - 1] > v) { order[j] = order[j - 1]; --j; }
+        order[j] = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------- propagate
 template <typename T> struct PropArgs {
     FieldView<T> F;
@@ -480,6 +495,94 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned long long v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
+}
+
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Dormand-Prince with ONE step size per 32-ray bundle: the reference's shipped algorithm (joint RK45 over the
+// flattened state, full_solver.py:391) applied to the rays of a warp -- exactly what ScalarDomain.solve does
+// when called with a 32-ray chunk, as the reference's own drivers chunk their rays.  All lanes share t and h,
+// so the bundle marches in lock-step like the fixed-step kernel (coherent gathers, uniform accept/reject).
+// The RMS error norm runs over the n_state components of the valid lanes (butterfly sum: deterministic).
+template <typename T, bool PHASE, bool AUX64>
+__device__ __forceinline__ void rk45_bundle_integrate(const PropArgs<T>& A, Ray<T>& r, CellCache<T, PHASE>& cc, bool valid, bool early,
+                                                      double amp0, double pol0, unsigned& n_att, LaneStats& ls) {
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    const double size = (double)A.n_state * (double)__popc(vmask);        // x.size of the flattened bundle state
+    Deriv<T> f; int touched = 0;
+    f.dp[0] = f.dp[1] = f.dp[2] = f.dv[0] = f.dv[1] = f.dv[2] = f.dph = (T)0;
+    const T rtol = A.rtol, atol = A.atol;
+    double s_a = 0.0, s_b = 0.0;
+    T sc_p[3], sc_v[3], sc_ph = atol;
+    if (valid) {
+        touched += deriv<T, PHASE, AUX64>(A.F, cc, A.omega, r.p, r.v, f);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            sc_p[k] = atol + fabs(r.p[k]) * rtol; sc_v[k] = atol + fabs(r.v[k]) * rtol;
+            double q = r.p[k] / sc_p[k]; s_a += q * q; q = r.v[k] / sc_v[k]; s_a += q * q;
+            q = f.dp[k] / sc_p[k]; s_b += q * q; q = f.dv[k] / sc_v[k]; s_b += q * q;
+        }
+        sc_ph = atol + fabs(r.ph) * rtol;
+        double q = r.ph / sc_ph; s_a += q * q; q = f.dph / sc_ph; s_b += q * q;
+        if (A.n_state > 6) {
+            q = amp0 / (atol + fabs(amp0) * rtol); s_a += q * q;
+            q = pol0 / (atol + fabs(pol0) * rtol); s_a += q * q;
+        }
+    }
+    // select_initial_step (scipy/integrate/_ivp/common.py) on the bundle
+    const double d0 = sqrt(warp_sum_f64(s_a)) / sqrt(size), d1 = sqrt(warp_sum_f64(s_b)) / sqrt(size);
+    const double t_end = (double)A.t_end;
+    double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    h0 = fmin(h0, t_end);
+    double s_c = 0.0;
+    if (valid) {
+        T p1[3], v1[3];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { p1[k] = r.p[k] + (T)h0 * f.dp[k]; v1[k] = r.v[k] + (T)h0 * f.dv[k]; }
+        Deriv<T> f1;
+        touched += deriv<T, PHASE, AUX64>(A.F, cc, A.omega, p1, v1, f1);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double q = (f1.dp[k] - f.dp[k]) / sc_p[k]; s_c += q * q;
+            q = (f1.dv[k] - f.dv[k]) / sc_v[k]; s_c += q * q;
+        }
+        const double q = (f1.dph - f.dph) / sc_ph; s_c += q * q;
+    }
+    const double d2 = sqrt(warp_sum_f64(s_c)) / sqrt(size) / h0;
+    const double h1 = (d1 <= 1e-15 && d2 <= 1e-15) ? fmax(1e-6, h0 * 1e-3) : pow(0.01 / fmax(d1, d2), 0.2);
+    double h_abs = fmin(fmin(100 * h0, h1), t_end);
+    double t = 0.0;
+    const unsigned cap = A.n_steps > 0 ? (unsigned)A.n_steps : (1u << 30);
+    bool failed = false;
+    while (t < t_end && !failed) {
+        if (early && __all_sync(0xffffffffu, !valid || escaped(A.F, r))) break;
+        const double min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);
+        if (h_abs < min_step) h_abs = min_step;
+        bool rejected = false;
+        for (;;) {
+            if (n_att >= cap || h_abs < min_step) { failed = true; ls.capped += valid ? 1 : 0; break; }
+            double t_new = t + h_abs;
+            if (t_new - t_end > 0.0) t_new = t_end;
+            const double h = t_new - t;
+            h_abs = fabs(h);
+            Ray<T> rn = r; Deriv<T> fn = f; T esq = (T)0;
+            if (valid) touched += dp5_attempt<T, PHASE, AUX64>(A.F, cc, A.omega, (T)h, rtol, atol, r, f, rn, fn, esq);
+            ++n_att;
+            const double en = sqrt(warp_sum_f64((double)esq)) / sqrt(size);
+            if (en < 1.0) {
+                h_abs *= dp5_factor<double>(en, true, rejected);
+                t = t_new; r = rn; f = fn; ls.acc += valid ? 1 : 0;
+                break;
+            }
+            h_abs *= dp5_factor<double>(en, false, rejected);
+            rejected = true;
+        }
+    }
+    ls.evals += touched;
 }
 
 // RK4 over the full 9-component state (attenuation and Faraday rotation on): float64 only.
@@ -584,7 +687,12 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
         unsigned n_att = 0;
         CellCache<T, PHASE> cc;
         double amp_x = 1.0, pol_x = 0.0;
-        if (valid) {
+        if (METHOD == SP_METHOD_RK45 && (A.flags & SP_FLAG_BUNDLE_STEP)) {
+            const double amp0 = (valid && !A.use_beam) ? A.s0[6 * A.n_total + gi] : 1.0;
+            const double pol0 = (valid && !A.use_beam) ? A.s0[8 * A.n_total + gi] : 0.0;
+            rk45_bundle_integrate<T, PHASE, AUX64>(A, r, cc, valid, early, amp0, pol0, n_att, ls);
+            if (valid) ls.steps += n_att; else n_att = 0;
+        } else if (valid) {
             if (METHOD == SP_METHOD_RK4X) {
                 rk4x_integrate<PHASE, AUX64>(A, r, cc, early, gi, n_att, ls, amp_x, pol_x);
             } else if (METHOD == SP_METHOD_RK45X) {
@@ -1183,6 +1291,7 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
         return joint_solve(field, P, ws, s0_dev, n, E, stats_dev, st);
     }
     if (P->method != SP_METHOD_RK4 && P->method != SP_METHOD_RK45) return fail(SP_EINVAL, "unknown method");
+    if (ext && (P->flags & SP_FLAG_BUNDLE_STEP)) return fail(SP_EINVAL, "bundle-step RK45 does not integrate the attenuation / Faraday channels");
     const bool ext_aux64 = ext && (P->flags & SP_FLAG_PHASE) && (P->flags & SP_FLAG_PHASE_F64);
 
     const bool fp32 = (P->flags & SP_FLAG_FP32) != 0;
@@ -1220,6 +1329,8 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
             k_scan<<<1, 1024, 0, st>>>(ws->hist, n_keys);
             LAUNCH_CHECK();
             k_sort_scatter<<<(cn + 255) / 256, 256, 0, st>>>(ws->keys, ws->hist, ws->order, cn);
+            LAUNCH_CHECK();
+            k_sort_fix<<<(n_keys + 255) / 256, 256, 0, st>>>(ws->hist, ws->order, n_keys);   // hist now holds segment ends
             LAUNCH_CHECK();
             order = ws->order;
         }

@@ -15,7 +15,7 @@ C_LIGHT = 299792458.0          # scipy.constants.c, as used by the reference (fu
 
 OP_KINDS = {"travel": L.OP_TRAVEL, "travel_noE": L.OP_TRAVEL_NOE, "lens": L.OP_LENS, "circ_ap": L.OP_CIRC_AP,
             "circ_stop": L.OP_CIRC_STOP, "rect_ap": L.OP_RECT_AP, "knife": L.OP_KNIFE, "ref_beam": L.OP_REF_BEAM}
-METHODS = {"rk4": L.METHOD_RK4, "rk45": L.METHOD_RK45, "rk45_joint": L.METHOD_RK45_JOINT}
+METHODS = {"rk4": L.METHOD_RK4, "rk45": L.METHOD_RK45, "rk45_joint": L.METHOD_RK45_JOINT, "rk45_bundle": L.METHOD_RK45}
 BEAM_TYPES = {"circular": L.BEAM_CIRCULAR_POW2, "circular_legacy": L.BEAM_CIRCULAR_FOLD, "square": L.BEAM_SQUARE,
               "rectangular": L.BEAM_RECTANGULAR, "linear": L.BEAM_LINEAR}
 
@@ -169,7 +169,8 @@ def make_params(method="rk4", *, probing_direction="z", extent, omega, n_steps=0
         out_axes = {0: (1, 2), 1: (0, 2), 2: (0, 1)}[p]
     flags = ((L.FLAG_PHASE if phase else 0) | (L.FLAG_PHASE_F64 if (phase and phase_f64) else 0) |
              (L.FLAG_EARLY_EXIT if early_exit else 0) | (L.FLAG_FP32 if fp32 else 0) | (0 if sort else L.FLAG_NO_SORT) |
-             (L.FLAG_ATTEN if atten else 0) | (L.FLAG_FARADAY if faraday else 0))
+             (L.FLAG_ATTEN if atten else 0) | (L.FLAG_FARADAY if faraday else 0) |
+             (L.FLAG_BUNDLE_STEP if method == "rk45_bundle" else 0))
     if t_end is None:
         t_end = np.sqrt(8.0) * extent / C_LIGHT       # full_solver.py:381, propagator.py:454
     return L.Params(method=METHODS[method], flags=flags, n_steps=int(n_steps), n_state=int(n_state), h=float(h),

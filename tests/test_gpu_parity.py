@@ -174,6 +174,30 @@ def test_rk45_per_ray(sp, golden):
     assert np.all(np.abs(rf[:, :8] - rf_conv).max(axis=1) <= 2 * np.abs(rf_ref[:, :8] - rf_conv).max(axis=1) + 1e-12)
 
 
+def test_rk45_bundle_is_the_shipped_solver_on_32_ray_chunks(sp, golden):
+    """method='rk45_bundle': one step size per 32-ray bundle == full_solver.ScalarDomain.solve called on 32-ray chunks
+    (the reference's own drivers chunk their rays).  With sort=False bundles are consecutive rays."""
+    g = golden("g2_expcos")
+    ext = float(g["extent"])
+    d = _legacy_dom(sp, g, phaseshift=True)
+    s0 = g["s0"][:, :70]                                       # bundles [0:32], [32:64], [64:70]
+    o = O.Domain(g["x"], g["y"], g["z"], ext, phaseshift=True)
+    o.external_ne(g["ne"])
+    o.calc_dndr(float(g["lwl"]))
+    ref = np.concatenate([o.solve_joint(s0[:, a:b]) for a, b in ((0, 32), (32, 64), (64, 70))], axis=1)
+    rf = d.solve(s0, method="rk45_bundle", sort=False)
+    assert np.max(np.abs(d.sf[:3] - ref[:3])) < 1e-9 * ext and np.max(np.abs(d.sf[3:6] - ref[3:6])) < 1e-9 * C_LIGHT
+    assert np.max(np.abs(d.sf[7] - ref[7])) < 1e-9 * np.abs(ref[7]).max()
+    assert np.max(np.abs(rf - O.ray_to_jones(ref, ext)[0])) < 1e-9
+    assert len(set(d.steps[:32])) == 1 and len(set(d.steps[64:70])) == 1        # one controller per bundle
+    # sorted bundles: deterministic from run to run (stable bundle order), solver-level agreement with per-ray mode
+    a = d.solve(g["s0"], method="rk45_bundle").copy()
+    b = d.solve(g["s0"], method="rk45_bundle")
+    assert np.array_equal(a, b)
+    c = d.solve(g["s0"], method="rk45")
+    assert np.max(np.abs(a[[0, 2]] - c[[0, 2]])) < 1e-3 * ext and np.max(np.abs(a[[1, 3]] - c[[1, 3]])) < 5e-3
+
+
 def test_fp32_mode(sp, golden):
     g = golden("g3_turb")
     ext, n = float(g["extent"]), int(g["rk4_nsteps"])
