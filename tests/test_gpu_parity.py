@@ -195,7 +195,7 @@ def test_rk45_bundle_is_the_shipped_solver_on_32_ray_chunks(sp, golden):
     b = d.solve(g["s0"], method="rk45_bundle")
     assert np.array_equal(a, b)
     c = d.solve(g["s0"], method="rk45")
-    assert np.max(np.abs(a[[0, 2]] - c[[0, 2]])) < 1e-3 * ext and np.max(np.abs(a[[1, 3]] - c[[1, 3]])) < 5e-3
+    assert np.max(np.abs(a[[0, 2]] - c[[0, 2]])) < 5e-3 * ext and np.max(np.abs(a[[1, 3]] - c[[1, 3]])) < 5e-3   # rtol 1e-3 solves
 
 
 def test_fp32_mode(sp, golden):
