@@ -24,6 +24,15 @@
 #define SP_HD inline
 #endif
 
+// -DSP_BOUNDS_CHECK: device-side asserts on every index that feeds a global load (compute-sanitizer is not
+// available on the GPU pool; the test-suite is run once against a library built this way).
+#if defined(SP_BOUNDS_CHECK) && defined(__CUDA_ARCH__)
+#include <assert.h>
+#define SP_ASSERT(c) assert(c)
+#else
+#define SP_ASSERT(c) ((void)0)
+#endif
+
 namespace sp {
 
 struct alignas(16) f4 { float x, y, z, w; };
@@ -174,6 +183,7 @@ template <typename T> SP_HD bool locate(const AxisTab<T>& A, T x, int& i) {
     if (x < A.lo || x > A.hi) return false;
     int k = floor_to_int((x - A.g0) * A.inv_d);
     k = k < 0 ? 0 : (k > A.n - 2 ? A.n - 2 : k);
+    SP_ASSERT(A.n >= 2);
     if (x == x) {
         while (k > 0 && x < ldg(A.tab + k).x) --k;
         while (k < A.n - 2 && x >= ldg(A.tab + k + 1).x) ++k;
@@ -261,6 +271,8 @@ SP_HD bool rhs(const FieldView<T>& F, CellCache<T, PHASE>& cc, T pu, T pv, T pw,
         if (!relocate_axis(F.ax[0], pu, oku, v, cc.idx[0], cc.lo[0], cc.rinv[0])) return false;
         if (!relocate_axis(F.ax[1], pv, okv, v, cc.idx[1], cc.lo[1], cc.rinv[1])) return false;
         if (!relocate_axis(F.ax[2], pw, okw, v, cc.idx[2], cc.lo[2], cc.rinv[2])) return false;
+        SP_ASSERT(cc.idx[0] >= 0 && cc.idx[0] <= F.ax[0].n - 2 && cc.idx[1] >= 0 && cc.idx[1] <= F.ax[1].n - 2 &&
+                  cc.idx[2] >= 0 && cc.idx[2] <= F.ax[2].n - 2);
         const long long base = (long long)cc.idx[0] * F.su + (long long)cc.idx[1] * F.sv + cc.idx[2];
         const f4* p = F.data + base;
         const f4 c000 = ldg(p), c001 = ldg(p + 1);
@@ -374,6 +386,8 @@ SP_HD void ext_eval(const FieldView<double>& F, const ExtView& X, const CellCach
     const double wu = (p[0] - cc.lo[0]) * cc.rinv[0], wv = (p[1] - cc.lo[1]) * cc.rinv[1], ww = (p[2] - cc.lo[2]) * cc.rinv[2];
     const double mu = 1.0 - wu, mv = 1.0 - wv, mw = 1.0 - ww;
     const double k[8] = {mu * mv * mw, mu * mv * ww, mu * wv * mw, mu * wv * ww, wu * mv * mw, wu * mv * ww, wu * wv * mw, wu * wv * ww};
+    SP_ASSERT(cc.valid && cc.idx[0] >= 0 && cc.idx[0] <= F.ax[0].n - 2 && cc.idx[1] >= 0 && cc.idx[1] <= F.ax[1].n - 2 &&
+              cc.idx[2] >= 0 && cc.idx[2] <= F.ax[2].n - 2);
     const long long base = (long long)cc.idx[0] * F.su + (long long)cc.idx[1] * F.sv + cc.idx[2];
     const long long off[8] = {0, 1, F.sv, F.sv + 1, F.su, F.su + 1, F.su + F.sv, F.su + F.sv + 1};
 #pragma unroll

@@ -371,6 +371,7 @@ __device__ __forceinline__ int bin_ray(const ChannelDev& ch, const DetRay& d, bo
         const int ix = bin_index(d.x, ch.x_lo, ch.x_hi, ch.nx, hist);
         const int iy = bin_index(d.y, ch.y_lo, ch.y_hi, ch.ny, hist);
         if (ix >= 0 && iy >= 0) pix = iy * ch.nx + ix;
+        SP_ASSERT(pix < ch.nx * ch.ny && ix < ch.nx && iy < ch.ny);
     }
     if (ch.kind == SP_IMG_HISTOGRAM) {
         const unsigned peers = __match_any_sync(__activemask(), pix);
@@ -455,7 +456,9 @@ __global__ void k_sort_scatter(const uint32_t* __restrict__ keys, uint32_t* __re
                                uint32_t* __restrict__ order, uint32_t n) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    order[atomicAdd(cursor + keys[i], 1u)] = i;
+    const uint32_t pos = atomicAdd(cursor + keys[i], 1u);
+    SP_ASSERT(pos < n);
+    order[pos] = i;
 }
 
 // The scatter above fills each key's segment in atomic (i.e. arbitrary) order; sorting every segment by ray index
