@@ -199,7 +199,7 @@ def workload_config(a):
                         f"{diag} at bin_scale {a.bin_scale}",
             "grid": a.grid, "rays_per_gpu": int(a.rays), "integrator": integ,
             "precision": "fp32" if a.fp32 else "fp64", "field_bytes": 16 * a.grid ** 3,
-            "l2_policy": "inputs larger than L2 (packed field 2.1 GB at 512^3 vs 126 MB L2)",
+            "l2_policy": f"inputs larger than L2 (packed field {16 * a.grid ** 3 / 1e9:.2f} GB vs 126 MB L2); no flush needed",
             "rays": "generated on device (Philox4x32-10), sorted into cell-column bundles" if not a.no_sort else
                     "generated on device, unsorted"}
 

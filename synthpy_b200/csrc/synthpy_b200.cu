@@ -468,6 +468,7 @@ __global__ void k_sort_fix(const uint32_t* __restrict__ seg_end, uint32_t* __res
     const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
     if (key >= n_keys) return;
     const uint32_t b = key ? seg_end[key - 1] : 0u, e = seg_end[key];
+    if (e - b > 2048u) return;        // degenerate beams (everything in one column): keep the arbitrary order, stay O(n)
     for (uint32_t i = b + 1; i < e; ++i) {
         const uint32_t v = order[i];
         uint32_t j = i;
