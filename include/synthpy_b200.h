@@ -205,7 +205,7 @@ typedef struct sp_stats {
     uint64_t rays_capped;    /* rays that hit the n_steps cap before t_end (RK45)                            */
     uint64_t rays_binned;    /* rays that landed inside an image, summed over channels                       */
     uint64_t rays_rejected;  /* rays removed by an aperture/stop, summed over channels                       */
-    uint64_t rhs_evals;      /* right-hand-side evaluations that touched the field                           */
+    uint64_t rhs_evals;      /* right-hand-side evaluations (RK4: 4 per step; RK45: those that touched the field) */
 } sp_stats;
 
 typedef struct sp_workspace sp_workspace; /* opaque scratch (sort keys, joint-mode stage buffers) reused across calls */

@@ -203,9 +203,13 @@ template <typename T, bool PHASE> struct CellCache {
     T lo[3], rinv[3];                   // g[i] and 1/(g[i+1]-g[i]) of the cached cell, per axis
     T a[PHASE ? 4 : 3][8];
     int idx[3];
-    bool valid;
-    SP_HD CellCache() : valid(false) {
+    // "no cell cached" is encoded as rinv[2] = NaN: the w-weight is then NaN and fails the unit-interval test,
+    // so the hot path needs no separate flag
+    SP_HD bool valid() const { return rinv[2] == rinv[2]; }
+    SP_HD void invalidate() { rinv[2] = (T)NAN; }
+    SP_HD CellCache() {
         for (int k = 0; k < 3; ++k) { lo[k] = rinv[k] = (T)0; idx[k] = 0; }
+        invalidate();
         for (int c = 0; c < (PHASE ? 4 : 3); ++c)
             for (int k = 0; k < 8; ++k) a[c][k] = (T)0;
     }
@@ -264,13 +268,12 @@ template <typename T, bool PHASE, bool AUX64>
 SP_HD bool rhs(const FieldView<T>& F, CellCache<T, PHASE>& cc, T pu, T pv, T pw, T& au, T& av, T& aw, T& nm1) {
     T wu = (pu - cc.lo[0]) * cc.rinv[0], wv = (pv - cc.lo[1]) * cc.rinv[1], ww = (pw - cc.lo[2]) * cc.rinv[2];
     const bool oku = unit_interval(wu), okv = unit_interval(wv), okw = unit_interval(ww);
-    if (!(cc.valid && oku && okv && okw)) {
+    if (!(oku && okv && okw)) {
         au = av = aw = nm1 = (T)0;
-        const bool v = cc.valid;
-        cc.valid = false;
-        if (!relocate_axis(F.ax[0], pu, oku, v, cc.idx[0], cc.lo[0], cc.rinv[0])) return false;
-        if (!relocate_axis(F.ax[1], pv, okv, v, cc.idx[1], cc.lo[1], cc.rinv[1])) return false;
-        if (!relocate_axis(F.ax[2], pw, okw, v, cc.idx[2], cc.lo[2], cc.rinv[2])) return false;
+        const bool v = cc.valid();
+        if (!relocate_axis(F.ax[0], pu, oku, v, cc.idx[0], cc.lo[0], cc.rinv[0])) { cc.invalidate(); return false; }
+        if (!relocate_axis(F.ax[1], pv, okv, v, cc.idx[1], cc.lo[1], cc.rinv[1])) { cc.invalidate(); return false; }
+        if (!relocate_axis(F.ax[2], pw, okw, v, cc.idx[2], cc.lo[2], cc.rinv[2])) { cc.invalidate(); return false; }
         SP_ASSERT(cc.idx[0] >= 0 && cc.idx[0] <= F.ax[0].n - 2 && cc.idx[1] >= 0 && cc.idx[1] <= F.ax[1].n - 2 &&
                   cc.idx[2] >= 0 && cc.idx[2] <= F.ax[2].n - 2);
         const long long base = (long long)cc.idx[0] * F.su + (long long)cc.idx[1] * F.sv + cc.idx[2];
@@ -292,7 +295,6 @@ SP_HD bool rhs(const FieldView<T>& F, CellCache<T, PHASE>& cc, T pu, T pv, T pw,
                             cc.a[PHASE ? 3 : 0]);
             }
         }
-        cc.valid = true;
         wu = (pu - cc.lo[0]) * cc.rinv[0]; wv = (pv - cc.lo[1]) * cc.rinv[1]; ww = (pw - cc.lo[2]) * cc.rinv[2];
     }
     au = tri_eval<T>(cc.a[0], wu, wv, ww);
@@ -325,17 +327,15 @@ template <typename T> SP_HD bool escaped(const FieldView<T>& F, const Ray<T>& r)
 //     p' = (p + h v) + h^2/6 (a1 + a2 + a3)                 v' = v + h/6 (((a1 + 2 a2) + 2 a3) + a4)
 // This is classical RK4 exactly (same stage points, same weights); only the floating-point association of
 // the position update differs from y + h/6 (k1 + 2 k2 + 2 k3 + k4), at the 1e-16 level per step.
-// Returns how many of the four RHS evaluations touched the field, or -1 (state untouched) when `early` is set
-// and the ray has escaped: that test is only evaluated when the first stage is out of bounds, which is
-// necessary for "escaped" and costs nothing on the in-grid path.
+// Returns the number of RHS evaluations (4), or -1 (state untouched) when `early` is set and the ray has
+// escaped: that test is only evaluated when the first stage is out of bounds, which is necessary for "escaped"
+// and costs nothing on the in-grid path.
 template <typename T, bool PHASE, bool AUX64>
 SP_HD int rk4_step(const FieldView<T>& F, CellCache<T, PHASE>& cc, T h, T omega, Ray<T>& r, bool early = false) {
     const T hh = (T)0.5 * h, h6 = h / (T)6, hh2 = hh * hh, h2_2 = h * hh, h2_6 = h * h6;
     T a[3], n, sa[3], sv[3], q[3], ph_[3], sn = (T)0;
-    int touched = 0;
     const bool in1 = rhs<T, PHASE, AUX64>(F, cc, r.p[0], r.p[1], r.p[2], a[0], a[1], a[2], n);
     if (early && !in1 && escaped(F, r)) return -1;
-    touched += in1;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         sa[k] = a[k]; sv[k] = a[k];
@@ -343,7 +343,7 @@ SP_HD int rk4_step(const FieldView<T>& F, CellCache<T, PHASE>& cc, T h, T omega,
         ph_[k] = sp_fma(h, r.v[k], r.p[k]);           // p + h v
     }
     if (PHASE) sn = n;
-    touched += rhs<T, PHASE, AUX64>(F, cc, q[0], q[1], q[2], a[0], a[1], a[2], n);
+    rhs<T, PHASE, AUX64>(F, cc, q[0], q[1], q[2], a[0], a[1], a[2], n);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         q[k] = sp_fma(hh2, sa[k], q[k]);              // p3 = p2 + h^2/4 a1
@@ -351,19 +351,19 @@ SP_HD int rk4_step(const FieldView<T>& F, CellCache<T, PHASE>& cc, T h, T omega,
     }
     if (PHASE) sn = sp_fma((T)2, n, sn);
     const T a2u = a[0], a2v = a[1], a2w = a[2];
-    touched += rhs<T, PHASE, AUX64>(F, cc, q[0], q[1], q[2], a[0], a[1], a[2], n);
+    rhs<T, PHASE, AUX64>(F, cc, q[0], q[1], q[2], a[0], a[1], a[2], n);
     q[0] = sp_fma(h2_2, a2u, ph_[0]); q[1] = sp_fma(h2_2, a2v, ph_[1]); q[2] = sp_fma(h2_2, a2w, ph_[2]);   // p4
 #pragma unroll
     for (int k = 0; k < 3; ++k) { sa[k] = sa[k] + a[k]; sv[k] = sp_fma((T)2, a[k], sv[k]); }
     if (PHASE) sn = sp_fma((T)2, n, sn);
-    touched += rhs<T, PHASE, AUX64>(F, cc, q[0], q[1], q[2], a[0], a[1], a[2], n);
+    rhs<T, PHASE, AUX64>(F, cc, q[0], q[1], q[2], a[0], a[1], a[2], n);
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
         r.p[k] = sp_fma(h2_6, sa[k], ph_[k]);
         r.v[k] = sp_fma(h6, sv[k] + a[k], r.v[k]);
     }
     if (PHASE) r.ph = sp_fma(h6, omega * (sn + n), r.ph);
-    return touched;
+    return 4;
 }
 
 // ---- attenuation and Faraday-rotation channels (slow path, float64, RK4 only) ---------------------------------
@@ -386,7 +386,7 @@ SP_HD void ext_eval(const FieldView<double>& F, const ExtView& X, const CellCach
     const double wu = (p[0] - cc.lo[0]) * cc.rinv[0], wv = (p[1] - cc.lo[1]) * cc.rinv[1], ww = (p[2] - cc.lo[2]) * cc.rinv[2];
     const double mu = 1.0 - wu, mv = 1.0 - wv, mw = 1.0 - ww;
     const double k[8] = {mu * mv * mw, mu * mv * ww, mu * wv * mw, mu * wv * ww, wu * mv * mw, wu * mv * ww, wu * wv * mw, wu * wv * ww};
-    SP_ASSERT(cc.valid && cc.idx[0] >= 0 && cc.idx[0] <= F.ax[0].n - 2 && cc.idx[1] >= 0 && cc.idx[1] <= F.ax[1].n - 2 &&
+    SP_ASSERT(cc.valid() && cc.idx[0] >= 0 && cc.idx[0] <= F.ax[0].n - 2 && cc.idx[1] >= 0 && cc.idx[1] <= F.ax[1].n - 2 &&
               cc.idx[2] >= 0 && cc.idx[2] <= F.ax[2].n - 2);
     const long long base = (long long)cc.idx[0] * F.su + (long long)cc.idx[1] * F.sv + cc.idx[2];
     const long long off[8] = {0, 1, F.sv, F.sv + 1, F.su, F.su + 1, F.su + F.sv, F.su + F.sv + 1};
