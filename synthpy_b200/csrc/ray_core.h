@@ -156,6 +156,24 @@ template <> SP_HD double cvt<double>(float f) {
 #endif
 }
 
+// all three weights in [0, 1): one 3-input unsigned max + one compare
+SP_HD bool unit_interval3(double a, double b, double c) {
+#if defined(__CUDA_ARCH__)
+    const unsigned x = (unsigned)__double2hiint(a), y = (unsigned)__double2hiint(b), z = (unsigned)__double2hiint(c);
+    return max(max(x, y), z) < 0x3FF00000u;
+#else
+    return unit_interval(a) && unit_interval(b) && unit_interval(c);
+#endif
+}
+SP_HD bool unit_interval3(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    const unsigned x = (unsigned)__float_as_int(a), y = (unsigned)__float_as_int(b), z = (unsigned)__float_as_int(c);
+    return max(max(x, y), z) < 0x3F800000u;
+#else
+    return unit_interval(a) && unit_interval(b) && unit_interval(c);
+#endif
+}
+
 // ---- field view --------------------------------------------------------------------------------------
 // Kernel frame: axes (u, v, w) = (m+1, m+2, m) mod 3 of the caller's (x, y, z), m = march (probing) axis;
 // w is the fastest-varying axis of the packed grid, so the two corners a ray needs along its direction of
@@ -267,9 +285,9 @@ template <typename T> SP_HD T tri_eval(const T* a, T wu, T wv, T ww) {
 template <typename T, bool PHASE, bool AUX64>
 SP_HD bool rhs(const FieldView<T>& F, CellCache<T, PHASE>& cc, T pu, T pv, T pw, T& au, T& av, T& aw, T& nm1) {
     T wu = (pu - cc.lo[0]) * cc.rinv[0], wv = (pv - cc.lo[1]) * cc.rinv[1], ww = (pw - cc.lo[2]) * cc.rinv[2];
-    const bool oku = unit_interval(wu), okv = unit_interval(wv), okw = unit_interval(ww);
-    if (!(oku && okv && okw)) {
+    if (!unit_interval3(wu, wv, ww)) {
         au = av = aw = nm1 = (T)0;
+        const bool oku = unit_interval(wu), okv = unit_interval(wv), okw = unit_interval(ww);
         const bool v = cc.valid();
         if (!relocate_axis(F.ax[0], pu, oku, v, cc.idx[0], cc.lo[0], cc.rinv[0])) { cc.invalidate(); return false; }
         if (!relocate_axis(F.ax[1], pv, okv, v, cc.idx[1], cc.lo[1], cc.rinv[1])) { cc.invalidate(); return false; }
