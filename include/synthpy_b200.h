@@ -240,6 +240,16 @@ int sp_workspace_propagate_ms(sp_workspace* ws, double* total_ms, int* n_launche
  * (the counterpart of instrumenting scipy's RK45._estimate_error_norm).  Copies min(cap, n) entries. */
 int sp_workspace_joint_log(const sp_workspace* ws, double* h_out, double* en_out, int cap, int* n_out);
 
+/*
+ * Exit-plane projection of ODE states that already exist in HBM: ray_to_Jonesvector
+ * (src/solvers-legacy/full_solver.py:838-894; src/simulator/propagator.py:178-298 with keep_current_plane) and
+ * back_propogate (propagator.py:300-349).  sf_dev is 9 x n; any output may be NULL.
+ *   rf_dev  4 x n  [x, theta, y, phi]           jf_dev  2 x n complex128 Jones vectors
+ *   sback_dev 9 x n: the state moved along its straight line onto the plane coord[probing_axis] = extent
+ */
+int sp_exit_plane(const double* sf_dev, uint64_t n, int probing_axis, int out_axis_a, int out_axis_b, double extent,
+                  int keep_current_plane, double* rf_dev, double* jf_dev, double* sback_dev, void* stream);
+
 /* Right-hand side only: d(state)/dt for arbitrary states (parity level L0; full_solver.py:516-544). */
 int sp_rhs(const sp_field* field, const sp_params* params, const double* s_dev, uint64_t n, double* dsdt_dev,
            void* stream);

@@ -1083,6 +1083,35 @@ __global__ void k_optics_image(const double* __restrict__ rf, const double* __re
     }
 }
 
+__global__ void k_exit_plane(const double* __restrict__ sf, uint64_t n, int kp, int ka, int kb, double extent, int keep,
+                             double* __restrict__ rf, double* __restrict__ jf, double* __restrict__ sback) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Ray<double> r;                                   // caller frame here: kernel index == caller axis
+    for (int k = 0; k < 3; ++k) { r.p[k] = sf[(uint64_t)k * n + i]; r.v[k] = sf[(uint64_t)(3 + k) * n + i]; }
+    double xa, tha, xb, thb;
+    exit_project<double>(r, kp, ka, kb, extent, xa, tha, xb, thb);
+    if (rf) {
+        rf[i] = keep ? pick3(r.p, ka) : xa; rf[n + i] = tha;
+        rf[2 * n + i] = keep ? pick3(r.p, kb) : xb; rf[3 * n + i] = thb;
+    }
+    if (jf) {
+        const double amp = sf[6 * n + i], ph = sf[7 * n + i], pol = sf[8 * n + i];
+        double sp_, cp_, ss, cs;
+        sp_sincos(ph, &sp_, &cp_); sp_sincos(pol, &ss, &cs);
+        const double rr = amp * cp_, ri = amp * sp_;
+        jf[2 * i] = rr * (-ss); jf[2 * i + 1] = ri * (-ss); jf[2 * (n + i)] = rr * cs; jf[2 * (n + i) + 1] = ri * cs;
+    }
+    if (sback) {
+        const double tbp = (pick3(r.p, kp) - extent) / pick3(r.v, kp);
+        for (int k = 0; k < 3; ++k) {
+            sback[(uint64_t)k * n + i] = (k == kp) ? extent : r.p[k] - r.v[k] * tbp;
+            sback[(uint64_t)(3 + k) * n + i] = r.v[k];
+        }
+        for (int k = 6; k < 9; ++k) sback[(uint64_t)k * n + i] = sf[(uint64_t)k * n + i];
+    }
+}
+
 __global__ void k_finalize(const double* __restrict__ planes, double* __restrict__ H, size_t npix) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
@@ -1571,6 +1600,18 @@ extern "C" int sp_optics_image(const double* rf_dev, const double* jf_dev, uint6
         if (blocks > 148 * 16) blocks = 148 * 16;
         k_optics_image<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(rf_dev, jf_dev, n, ch, rf_out_dev, jf_out_dev);
     }
+    LAUNCH_CHECK();
+    return SP_OK;
+}
+
+extern "C" int sp_exit_plane(const double* sf_dev, uint64_t n, int probing_axis, int out_axis_a, int out_axis_b, double extent,
+                             int keep_current_plane, double* rf_dev, double* jf_dev, double* sback_dev, void* stream) {
+    if (!sf_dev) return fail(SP_EINVAL, "null argument");
+    if (probing_axis < 0 || probing_axis > 2 || out_axis_a < 0 || out_axis_a > 2 || out_axis_b < 0 || out_axis_b > 2)
+        return fail(SP_EINVAL, "axis index out of range");
+    if (n == 0) return SP_OK;
+    k_exit_plane<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(sf_dev, n, probing_axis, out_axis_a, out_axis_b,
+                                                                               extent, keep_current_plane, rf_dev, jf_dev, sback_dev);
     LAUNCH_CHECK();
     return SP_OK;
 }

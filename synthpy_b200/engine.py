@@ -309,6 +309,18 @@ def rhs(field, params, s):
     return out
 
 
+def exit_plane(sf, probing_axis, out_axes, extent, *, keep_current_plane=False, want_rf=True, want_jf=False, want_state=False):
+    """sp_exit_plane on a (9,N) CUDA float64 state: returns (rf, jf, back-propagated state), None where not asked."""
+    require_cuda()
+    n = sf.shape[1]
+    rf = torch.empty((4, n), dtype=torch.float64, device="cuda") if want_rf else None
+    jf = torch.empty((2, n), dtype=torch.complex128, device="cuda") if want_jf else None
+    sb = torch.empty((9, n), dtype=torch.float64, device="cuda") if want_state else None
+    L.check(L.lib.sp_exit_plane(_ptr(sf), n, int(probing_axis), int(out_axes[0]), int(out_axes[1]), float(extent),
+                                int(bool(keep_current_plane)), _ptr(rf), _ptr(jf), _ptr(sb), _stream()))
+    return rf, jf, sb
+
+
 def beam_generate(beam, n, ray_offset=0):
     require_cuda()
     s0 = torch.empty((9, int(n)), dtype=torch.float64, device="cuda")

@@ -120,6 +120,28 @@ def solve_and_image(ScalarDomain, rays, probing_depth, diagnostics, *, lwl=1064e
     return engine.stats_dict(out["stats_dev"]), time() - start
 
 
+def ray_to_Jonesvector(rays, ne_extent, *, probing_direction="z", keep_current_plane=False, return_E=False,
+                       axis_convention="current"):
+    """propagator.py:178-298 (legacy: full_solver.py:838-894): (9,N) ODE states -> (ray_p (4,N), ray_J (2,N) or None)."""
+    as_numpy = not isinstance(rays, torch.Tensor)
+    sf = engine.to_device(rays, torch.float64)
+    rf, jf, _ = engine.exit_plane(sf, engine.AXIS[probing_direction], _out_axes(probing_direction, axis_convention), ne_extent,
+                                  keep_current_plane=keep_current_plane, want_jf=return_E)
+    if as_numpy:
+        rf, jf = rf.cpu().numpy(), (None if jf is None else jf.cpu().numpy())
+    return rf, jf
+
+
+def back_propogate(rays, ne_extent, probing_direction):
+    """propagator.py:300-349 (spelling as upstream): move (9,N) states along their straight lines onto the exit plane.
+    (Upstream additionally permutes the rows for 'y'; here rows keep their x, y, z meaning.)"""
+    as_numpy = not isinstance(rays, torch.Tensor)
+    sf = engine.to_device(rays, torch.float64)
+    p = engine.AXIS[probing_direction]
+    _, _, sb = engine.exit_plane(sf, p, _out_axes(probing_direction, "legacy"), ne_extent, want_rf=False, want_state=True)
+    return sb.cpu().numpy() if as_numpy else sb
+
+
 def rhs(s, ScalarDomain, *, lwl=1064e-9, phase_f64=False):
     """d(state)/dt of the ray ODE (propagator.py:94-175 / full_solver.py:516-544) for a (9,N) state."""
     as_numpy = not isinstance(s, torch.Tensor)

@@ -411,6 +411,23 @@ def test_current_api_probing_y_axis_convention(sp, golden):
     assert np.array_equal(rf_cur[[2, 3, 0, 1]], rf_leg)
 
 
+def test_ray_to_jonesvector_and_back_propogate(sp, golden):
+    from synthpy_b200 import propagator as P
+    g = golden("g2_expcos")
+    ext = float(g["extent"])
+    rf, Jf = P.ray_to_Jonesvector(g["sf"], ext, probing_direction="z", return_E=True)
+    assert rel_err(rf, g["rf"], floor=1e-7) < 1e-13 and np.max(np.abs(Jf - g["Jf"])) < 1e-12
+    rf_k, none = P.ray_to_Jonesvector(g["sf"], ext, keep_current_plane=True)
+    assert none is None and np.array_equal(rf_k[0], g["sf"][0]) and np.array_equal(rf_k[2], g["sf"][1])
+    assert np.array_equal(rf_k[[1, 3]], rf[[1, 3]])
+    sb = P.back_propogate(g["sf"], ext, "z")
+    assert np.all(sb[2] == ext) and rel_err(sb[0], g["rf"][0], floor=1e-7) < 1e-13 and np.array_equal(sb[3:], g["sf"][3:])
+    g3 = golden("g3_turb")
+    for pd in ("x", "y"):
+        rf, _ = P.ray_to_Jonesvector(g3[pd + "_sf"], float(g3["extent"]), probing_direction=pd, axis_convention="legacy")
+        assert rel_err(rf, g3[pd + "_rf"], floor=1e-7) < 1e-13
+
+
 def test_edge_cases(sp, golden):
     from synthpy_b200 import engine
     g = golden("g3_turb")
