@@ -492,64 +492,91 @@ SP_HD int deriv(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega, const T
 // One attempted DP5 step of size h from (r, k1 = f(r)).  Outputs the 5th-order state, f(new state) (FSAL)
 // and sum over the live components of (err_i / scale_i)^2 with scale = atol + rtol max(|y|, |y_new|)
 // (rk.py:_step_impl).  amp (|y| = amp0) and pol contribute zero error.
+//
+// Because p' = v is linear, the position rows of the stage matrix K are the stage velocities
+// v_s = v + h sum_j a_sj Kv_j; substituting them (Nystrom form of the same tableau) leaves only the velocity rows
+// Kv and the phase row to keep:   p_s = p + c_s h v + h^2 sum_j Abar_sj Kv_j,  Abar_sj = sum_i a_si a_ij,
+//                                 p'  = p + h v + h^2 sum_j Bbar_j Kv_j,       err_p = h^2 sum_j Ebar_j Kv_j
+// (sum_s E_s = 0, so the h v term drops out of the error).  Same method, same stage points; 21 fewer live
+// doubles per ray than carrying the position rows.
+struct DPN {
+    static constexpr double A31 = DP::a32 * DP::a21;
+    static constexpr double A41 = DP::a42 * DP::a21 + DP::a43 * DP::a31, A42 = DP::a43 * DP::a32;
+    static constexpr double A51 = DP::a52 * DP::a21 + DP::a53 * DP::a31 + DP::a54 * DP::a41,
+                            A52 = DP::a53 * DP::a32 + DP::a54 * DP::a42, A53 = DP::a54 * DP::a43;
+    static constexpr double A61 = DP::a62 * DP::a21 + DP::a63 * DP::a31 + DP::a64 * DP::a41 + DP::a65 * DP::a51,
+                            A62 = DP::a63 * DP::a32 + DP::a64 * DP::a42 + DP::a65 * DP::a52,
+                            A63 = DP::a64 * DP::a43 + DP::a65 * DP::a53, A64 = DP::a65 * DP::a54;
+    static constexpr double B1 = DP::b3 * DP::a31 + DP::b4 * DP::a41 + DP::b5 * DP::a51 + DP::b6 * DP::a61,
+                            B2 = DP::b3 * DP::a32 + DP::b4 * DP::a42 + DP::b5 * DP::a52 + DP::b6 * DP::a62,
+                            B3 = DP::b4 * DP::a43 + DP::b5 * DP::a53 + DP::b6 * DP::a63,
+                            B4 = DP::b5 * DP::a54 + DP::b6 * DP::a64, B5 = DP::b6 * DP::a65;
+    static constexpr double E1 = DP::e3 * DP::a31 + DP::e4 * DP::a41 + DP::e5 * DP::a51 + DP::e6 * DP::a61 + DP::e7 * DP::b1,
+                            E2 = DP::e3 * DP::a32 + DP::e4 * DP::a42 + DP::e5 * DP::a52 + DP::e6 * DP::a62,
+                            E3 = DP::e4 * DP::a43 + DP::e5 * DP::a53 + DP::e6 * DP::a63 + DP::e7 * DP::b3,
+                            E4 = DP::e5 * DP::a54 + DP::e6 * DP::a64 + DP::e7 * DP::b4,
+                            E5 = DP::e6 * DP::a65 + DP::e7 * DP::b5, E6 = DP::e7 * DP::b6;
+};
+
 template <typename T, bool PHASE, bool AUX64>
 SP_HD int dp5_attempt(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega, T h, T rtol, T atol, const Ray<T>& r, const Deriv<T>& k1,
                       Ray<T>& rn, Deriv<T>& k7, T& err_sq) {
-    Deriv<T> k2, k3, k4, k5, k6;
-    T p[3], v[3];
+    T K2[3], K3[3], K4[3], K5[3], K6[3], n2, n3, n4, n5, n6, n7;
+    const T* K1 = k1.dv;
+    const T h2 = h * h;
     int touched = 0;
-    // stage states: y + (K[:s].T @ a[:s]) * h     (rk.py: rk_step)
-#define SP_STAGE(expr_p, expr_v)                          \
-    _Pragma("unroll") for (int c = 0; c < 3; ++c) {       \
-        p[c] = r.p[c] + (expr_p) * h;                     \
-        v[c] = r.v[c] + (expr_v) * h;                     \
-    }
-    SP_STAGE((T)DP::a21 * k1.dp[c], (T)DP::a21 * k1.dv[c]);
-    touched += deriv<T, PHASE, AUX64>(F, cc, omega, p, v, k2);
-    SP_STAGE((T)DP::a31 * k1.dp[c] + (T)DP::a32 * k2.dp[c], (T)DP::a31 * k1.dv[c] + (T)DP::a32 * k2.dv[c]);
-    touched += deriv<T, PHASE, AUX64>(F, cc, omega, p, v, k3);
-    SP_STAGE((T)DP::a41 * k1.dp[c] + (T)DP::a42 * k2.dp[c] + (T)DP::a43 * k3.dp[c],
-             (T)DP::a41 * k1.dv[c] + (T)DP::a42 * k2.dv[c] + (T)DP::a43 * k3.dv[c]);
-    touched += deriv<T, PHASE, AUX64>(F, cc, omega, p, v, k4);
-    SP_STAGE((T)DP::a51 * k1.dp[c] + (T)DP::a52 * k2.dp[c] + (T)DP::a53 * k3.dp[c] + (T)DP::a54 * k4.dp[c],
-             (T)DP::a51 * k1.dv[c] + (T)DP::a52 * k2.dv[c] + (T)DP::a53 * k3.dv[c] + (T)DP::a54 * k4.dv[c]);
-    touched += deriv<T, PHASE, AUX64>(F, cc, omega, p, v, k5);
-    SP_STAGE((T)DP::a61 * k1.dp[c] + (T)DP::a62 * k2.dp[c] + (T)DP::a63 * k3.dp[c] + (T)DP::a64 * k4.dp[c] +
-                 (T)DP::a65 * k5.dp[c],
-             (T)DP::a61 * k1.dv[c] + (T)DP::a62 * k2.dv[c] + (T)DP::a63 * k3.dv[c] + (T)DP::a64 * k4.dv[c] +
-                 (T)DP::a65 * k5.dv[c]);
-    touched += deriv<T, PHASE, AUX64>(F, cc, omega, p, v, k6);
-#undef SP_STAGE
+#define SP_POS(cs, expr) (r.p[c] + (T)(cs) * h * r.v[c] + h2 * (expr))
+    T p[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p[c] = r.p[c] + (T)DP::c2 * h * r.v[c];
+    touched += rhs<T, PHASE, AUX64>(F, cc, p[0], p[1], p[2], K2[0], K2[1], K2[2], n2);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p[c] = SP_POS(DP::c3, (T)DPN::A31 * K1[c]);
+    touched += rhs<T, PHASE, AUX64>(F, cc, p[0], p[1], p[2], K3[0], K3[1], K3[2], n3);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p[c] = SP_POS(DP::c4, (T)DPN::A41 * K1[c] + (T)DPN::A42 * K2[c]);
+    touched += rhs<T, PHASE, AUX64>(F, cc, p[0], p[1], p[2], K4[0], K4[1], K4[2], n4);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) p[c] = SP_POS(DP::c5, (T)DPN::A51 * K1[c] + (T)DPN::A52 * K2[c] + (T)DPN::A53 * K3[c]);
+    touched += rhs<T, PHASE, AUX64>(F, cc, p[0], p[1], p[2], K5[0], K5[1], K5[2], n5);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+        p[c] = SP_POS(1.0, (T)DPN::A61 * K1[c] + (T)DPN::A62 * K2[c] + (T)DPN::A63 * K3[c] + (T)DPN::A64 * K4[c]);
+    touched += rhs<T, PHASE, AUX64>(F, cc, p[0], p[1], p[2], K6[0], K6[1], K6[2], n6);
+#undef SP_POS
     // y_new = y + h * (K[:-1].T @ B)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        rn.p[c] = r.p[c] + h * ((T)DP::b1 * k1.dp[c] + (T)DP::b3 * k3.dp[c] + (T)DP::b4 * k4.dp[c] +
-                                (T)DP::b5 * k5.dp[c] + (T)DP::b6 * k6.dp[c]);
-        rn.v[c] = r.v[c] + h * ((T)DP::b1 * k1.dv[c] + (T)DP::b3 * k3.dv[c] + (T)DP::b4 * k4.dv[c] +
-                                (T)DP::b5 * k5.dv[c] + (T)DP::b6 * k6.dv[c]);
+        rn.p[c] = r.p[c] + h * r.v[c] + h2 * ((T)DPN::B1 * K1[c] + (T)DPN::B2 * K2[c] + (T)DPN::B3 * K3[c] + (T)DPN::B4 * K4[c] +
+                                              (T)DPN::B5 * K5[c]);
+        rn.v[c] = r.v[c] + h * ((T)DP::b1 * K1[c] + (T)DP::b3 * K3[c] + (T)DP::b4 * K4[c] + (T)DP::b5 * K5[c] + (T)DP::b6 * K6[c]);
     }
     rn.ph = r.ph;
     if (PHASE)
-        rn.ph = r.ph + h * ((T)DP::b1 * k1.dph + (T)DP::b3 * k3.dph + (T)DP::b4 * k4.dph + (T)DP::b5 * k5.dph +
-                            (T)DP::b6 * k6.dph);
-    touched += deriv<T, PHASE, AUX64>(F, cc, omega, rn.p, rn.v, k7);
+        rn.ph = r.ph + h * ((T)DP::b1 * k1.dph + omega * ((T)DP::b3 * n3 + (T)DP::b4 * n4 + (T)DP::b5 * n5 + (T)DP::b6 * n6));
+    touched += rhs<T, PHASE, AUX64>(F, cc, rn.p[0], rn.p[1], rn.p[2], k7.dv[0], k7.dv[1], k7.dv[2], n7);
+#pragma unroll
+    for (int c = 0; c < 3; ++c) k7.dp[c] = rn.v[c];
+    k7.dph = PHASE ? omega * n7 : (T)0;
     // error estimate  (K.T @ E) * h / scale
     T acc = (T)0;
-#define SP_ERR(y0, y1, K1, K3, K4, K5, K6, K7)                                                           \
-    {                                                                                                    \
-        const T e = ((T)DP::e1 * (K1) + (T)DP::e3 * (K3) + (T)DP::e4 * (K4) + (T)DP::e5 * (K5) +         \
-                     (T)DP::e6 * (K6) + (T)DP::e7 * (K7)) * h;                                            \
-        const T a0 = fabs(y0), a1_ = fabs(y1);                                                           \
-        const T q = e / (atol + (a0 > a1_ ? a0 : a1_) * rtol);                                           \
-        acc += q * q;                                                                                    \
-    }
+#define SP_SCALE(y0, y1) (atol + (fabs(y0) > fabs(y1) ? fabs(y0) : fabs(y1)) * rtol)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        SP_ERR(r.p[c], rn.p[c], k1.dp[c], k3.dp[c], k4.dp[c], k5.dp[c], k6.dp[c], k7.dp[c]);
-        SP_ERR(r.v[c], rn.v[c], k1.dv[c], k3.dv[c], k4.dv[c], k5.dv[c], k6.dv[c], k7.dv[c]);
+        const T ep = h2 * ((T)DPN::E1 * K1[c] + (T)DPN::E2 * K2[c] + (T)DPN::E3 * K3[c] + (T)DPN::E4 * K4[c] + (T)DPN::E5 * K5[c] +
+                           (T)DPN::E6 * K6[c]);
+        const T ev = h * ((T)DP::e1 * K1[c] + (T)DP::e3 * K3[c] + (T)DP::e4 * K4[c] + (T)DP::e5 * K5[c] + (T)DP::e6 * K6[c] +
+                          (T)DP::e7 * k7.dv[c]);
+        const T qp = ep / SP_SCALE(r.p[c], rn.p[c]), qv = ev / SP_SCALE(r.v[c], rn.v[c]);
+        acc += qp * qp + qv * qv;
     }
-    if (PHASE) SP_ERR(r.ph, rn.ph, k1.dph, k3.dph, k4.dph, k5.dph, k6.dph, k7.dph);
-#undef SP_ERR
+    if (PHASE) {
+        const T e = h * ((T)DP::e1 * k1.dph + omega * ((T)DP::e3 * n3 + (T)DP::e4 * n4 + (T)DP::e5 * n5 + (T)DP::e6 * n6 + (T)DP::e7 * n7));
+        const T q = e / SP_SCALE(r.ph, rn.ph);
+        acc += q * q;
+    }
+#undef SP_SCALE
+    (void)n2;
     err_sq = acc;
     return touched;
 }
