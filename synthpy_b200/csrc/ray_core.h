@@ -97,6 +97,22 @@ SP_HD double ldg(const double* p) {
     return *p;
 #endif
 }
+// Load that the compiler may not sink into a later branch (asm volatile): used to put two independent
+// requests in flight before the first comparison that would otherwise serialise them.
+SP_HD double ldg_now(const double* p) {
+#if defined(__CUDA_ARCH__)
+    double v; asm volatile("ld.global.nc.f64 %0, [%1];" : "=d"(v) : "l"(p)); return v;
+#else
+    return *p;
+#endif
+}
+SP_HD float ldg_now(const float* p) {
+#if defined(__CUDA_ARCH__)
+    float v; asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(v) : "l"(p)); return v;
+#else
+    return *p;
+#endif
+}
 SP_HD f4 ldg(const f4* p) {
 #if defined(__CUDA_ARCH__)
     const float4 v = __ldg(reinterpret_cast<const float4*>(p));
@@ -241,9 +257,10 @@ template <typename T> SP_HD bool relocate_axis(const AxisTab<T>& A, T x, bool w_
         if (w_ok) return true;
         if (x >= lo) {
             if (i + 2 < A.n) {
-                const typename Pair<T>::type e1 = ldg(A.tab + i + 1), e2 = ldg(A.tab + i + 2);
+                const typename Pair<T>::type e1 = ldg(A.tab + i + 1);
+                const T e2x = ldg_now(&(A.tab + i + 2)->x);          // requested together with e1: one round trip
                 if (x < e1.x) return true;                       // weight rounded up to 1: still this cell
-                if (x < e2.x) { ++i; lo = e1.x; rinv = e1.y; return true; }
+                if (x < e2x) { ++i; lo = e1.x; rinv = e1.y; return true; }
             }
         } else if (x < lo && i > 0) {
             const typename Pair<T>::type e0 = ldg(A.tab + i - 1);
@@ -521,40 +538,68 @@ struct DPN {
 template <typename T, bool PHASE, bool AUX64>
 SP_HD int dp5_attempt(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega, T h, T rtol, T atol, const Ray<T>& r, const Deriv<T>& k1,
                       Ray<T>& rn, Deriv<T>& k7, T& err_sq) {
-    T K2[3], K3[3], K4[3], K5[3], K6[3], n2, n3, n4, n5, n6, n7;
+    T K2[3] = {0, 0, 0}, K3[3] = {0, 0, 0}, K4[3] = {0, 0, 0}, K5[3] = {0, 0, 0}, K6[3] = {0, 0, 0};
+    T n3 = (T)0, n4 = (T)0, n5 = (T)0, n6 = (T)0, n7 = (T)0;
     const T* K1 = k1.dv;
     const T h2 = h * h;
     int touched = 0;
+    // The six evaluations go through ONE copy of rhs() (a rolled loop with the stage-specific algebra in switch
+    // arms): with rhs() inlined six times the step loop was ~80 KB of SASS against a 32 KB instruction cache, and
+    // ncu showed `no_instruction` as the top stall (5 per issue).  Every index below is a compile-time constant,
+    // so the stage vectors stay in registers; the arithmetic is unchanged.
 #define SP_POS(cs, expr) (r.p[c] + (T)(cs) * h * r.v[c] + h2 * (expr))
-    T p[3];
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int s = 2; s <= 7; ++s) {
+        T p[3] = {0, 0, 0};
+        switch (s) {
+        case 2:
 #pragma unroll
-    for (int c = 0; c < 3; ++c) p[c] = r.p[c] + (T)DP::c2 * h * r.v[c];
-    touched += rhs<T, PHASE, AUX64>(F, cc, p[0], p[1], p[2], K2[0], K2[1], K2[2], n2);
+            for (int c = 0; c < 3; ++c) p[c] = r.p[c] + (T)DP::c2 * h * r.v[c];
+            break;
+        case 3:
 #pragma unroll
-    for (int c = 0; c < 3; ++c) p[c] = SP_POS(DP::c3, (T)DPN::A31 * K1[c]);
-    touched += rhs<T, PHASE, AUX64>(F, cc, p[0], p[1], p[2], K3[0], K3[1], K3[2], n3);
+            for (int c = 0; c < 3; ++c) p[c] = SP_POS(DP::c3, (T)DPN::A31 * K1[c]);
+            break;
+        case 4:
 #pragma unroll
-    for (int c = 0; c < 3; ++c) p[c] = SP_POS(DP::c4, (T)DPN::A41 * K1[c] + (T)DPN::A42 * K2[c]);
-    touched += rhs<T, PHASE, AUX64>(F, cc, p[0], p[1], p[2], K4[0], K4[1], K4[2], n4);
+            for (int c = 0; c < 3; ++c) p[c] = SP_POS(DP::c4, (T)DPN::A41 * K1[c] + (T)DPN::A42 * K2[c]);
+            break;
+        case 5:
 #pragma unroll
-    for (int c = 0; c < 3; ++c) p[c] = SP_POS(DP::c5, (T)DPN::A51 * K1[c] + (T)DPN::A52 * K2[c] + (T)DPN::A53 * K3[c]);
-    touched += rhs<T, PHASE, AUX64>(F, cc, p[0], p[1], p[2], K5[0], K5[1], K5[2], n5);
+            for (int c = 0; c < 3; ++c) p[c] = SP_POS(DP::c5, (T)DPN::A51 * K1[c] + (T)DPN::A52 * K2[c] + (T)DPN::A53 * K3[c]);
+            break;
+        case 6:
 #pragma unroll
-    for (int c = 0; c < 3; ++c)
-        p[c] = SP_POS(1.0, (T)DPN::A61 * K1[c] + (T)DPN::A62 * K2[c] + (T)DPN::A63 * K3[c] + (T)DPN::A64 * K4[c]);
-    touched += rhs<T, PHASE, AUX64>(F, cc, p[0], p[1], p[2], K6[0], K6[1], K6[2], n6);
-#undef SP_POS
-    // y_new = y + h * (K[:-1].T @ B)
+            for (int c = 0; c < 3; ++c)
+                p[c] = SP_POS(1.0, (T)DPN::A61 * K1[c] + (T)DPN::A62 * K2[c] + (T)DPN::A63 * K3[c] + (T)DPN::A64 * K4[c]);
+            break;
+        default:   // 7: y_new = y + h * (K[:-1].T @ B), then f(y_new) (FSAL)
 #pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        rn.p[c] = r.p[c] + h * r.v[c] + h2 * ((T)DPN::B1 * K1[c] + (T)DPN::B2 * K2[c] + (T)DPN::B3 * K3[c] + (T)DPN::B4 * K4[c] +
-                                              (T)DPN::B5 * K5[c]);
-        rn.v[c] = r.v[c] + h * ((T)DP::b1 * K1[c] + (T)DP::b3 * K3[c] + (T)DP::b4 * K4[c] + (T)DP::b5 * K5[c] + (T)DP::b6 * K6[c]);
+            for (int c = 0; c < 3; ++c) {
+                rn.p[c] = r.p[c] + h * r.v[c] + h2 * ((T)DPN::B1 * K1[c] + (T)DPN::B2 * K2[c] + (T)DPN::B3 * K3[c] + (T)DPN::B4 * K4[c] +
+                                                      (T)DPN::B5 * K5[c]);
+                rn.v[c] = r.v[c] + h * ((T)DP::b1 * K1[c] + (T)DP::b3 * K3[c] + (T)DP::b4 * K4[c] + (T)DP::b5 * K5[c] + (T)DP::b6 * K6[c]);
+                p[c] = rn.p[c];
+            }
+            rn.ph = r.ph;
+            if (PHASE)
+                rn.ph = r.ph + h * ((T)DP::b1 * k1.dph + omega * ((T)DP::b3 * n3 + (T)DP::b4 * n4 + (T)DP::b5 * n5 + (T)DP::b6 * n6));
+            break;
+        }
+        T a0, a1, a2, nn;
+        touched += rhs<T, PHASE, AUX64>(F, cc, p[0], p[1], p[2], a0, a1, a2, nn);
+        switch (s) {
+        case 2: K2[0] = a0; K2[1] = a1; K2[2] = a2; break;
+        case 3: K3[0] = a0; K3[1] = a1; K3[2] = a2; n3 = nn; break;
+        case 4: K4[0] = a0; K4[1] = a1; K4[2] = a2; n4 = nn; break;
+        case 5: K5[0] = a0; K5[1] = a1; K5[2] = a2; n5 = nn; break;
+        case 6: K6[0] = a0; K6[1] = a1; K6[2] = a2; n6 = nn; break;
+        default: k7.dv[0] = a0; k7.dv[1] = a1; k7.dv[2] = a2; n7 = nn; break;
+        }
     }
-    rn.ph = r.ph;
-    if (PHASE)
-        rn.ph = r.ph + h * ((T)DP::b1 * k1.dph + omega * ((T)DP::b3 * n3 + (T)DP::b4 * n4 + (T)DP::b5 * n5 + (T)DP::b6 * n6));
-    touched += rhs<T, PHASE, AUX64>(F, cc, rn.p[0], rn.p[1], rn.p[2], k7.dv[0], k7.dv[1], k7.dv[2], n7);
+#undef SP_POS
 #pragma unroll
     for (int c = 0; c < 3; ++c) k7.dp[c] = rn.v[c];
     k7.dph = PHASE ? omega * n7 : (T)0;
@@ -576,7 +621,6 @@ SP_HD int dp5_attempt(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega, T
         acc += q * q;
     }
 #undef SP_SCALE
-    (void)n2;
     err_sq = acc;
     return touched;
 }
