@@ -626,18 +626,29 @@ __device__ __noinline__ void rk45x_integrate(const PropArgs<double>& A, Ray<doub
     double h_abs = dp5_initial_step9<PHASE, AUX64>(A.F, A.X, cc, A.omega, with_phase, A.t_end, A.rtol, A.atol, y, f, touched);
     double t = 0.0;
     const unsigned cap = A.n_steps > 0 ? (unsigned)A.n_steps : (1u << 30);
-    bool failed = false;
-    while (t < A.t_end && !failed) {
-        if (early) {
-            Ray<double> q;
-            for (int k = 0; k < 3; ++k) { q.p[k] = y[k]; q.v[k] = y[3 + k]; }
-            if (escaped(A.F, q)) break;
+    // one attempt per iteration and lane (new step or retry), warp-voted loop condition: see k_propagate
+    bool failed = false, rejected = false, fresh = true;
+    double min_step = 0.0;
+    const unsigned lanes = __activemask();
+    for (;;) {
+        bool go = (t < A.t_end) && !failed;
+        if (go && fresh) {
+            bool out = false;
+            if (early) {
+                Ray<double> q;
+                for (int k = 0; k < 3; ++k) { q.p[k] = y[k]; q.v[k] = y[3 + k]; }
+                out = escaped(A.F, q);
+            }
+            if (out) go = false;
+            else {
+                min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);
+                if (h_abs < min_step) h_abs = min_step;
+                rejected = false; fresh = false;
+            }
         }
-        const double min_step = 10.0 * (nextafter(t, (double)INFINITY) - t);
-        if (h_abs < min_step) h_abs = min_step;
-        bool rejected = false;
-        for (;;) {
-            if (n_att >= cap || h_abs < min_step) { failed = true; ls.capped += 1; break; }
+        if (go && (n_att >= cap || h_abs < min_step)) { failed = true; ls.capped += 1; go = false; }
+        if (!__any_sync(lanes, go)) break;
+        if (go) {
             double t_new = t + h_abs;
             if (t_new - A.t_end > 0.0) t_new = A.t_end;
             const double h = t_new - t;
@@ -650,10 +661,11 @@ __device__ __noinline__ void rk45x_integrate(const PropArgs<double>& A, Ray<doub
                 h_abs *= dp5_factor<double>(en, true, rejected);
                 t = t_new; ls.acc += 1;
                 for (int i = 0; i < 9; ++i) { y[i] = yn[i]; f[i] = fn[i]; }
-                break;
+                fresh = true;
+            } else {
+                h_abs *= dp5_factor<double>(en, false, rejected);
+                rejected = true;
             }
-            h_abs *= dp5_factor<double>(en, false, rejected);
-            rejected = true;
         }
     }
     ls.evals += touched;
@@ -720,15 +732,26 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
                 T t = (T)0;
                 const unsigned cap = A.n_steps > 0 ? (unsigned)A.n_steps : (1u << 30);
                 const T inv_n = (T)1 / (T)A.n_state;
-                bool failed = false;
-                while (t < A.t_end && !failed) {
-                    if (early && escaped(A.F, r)) break;
-                    const T min_step = (T)10 * (nextafter(t, (T)INFINITY) - t);
-                    if (h_abs < min_step) h_abs = min_step;
-                    bool rejected = false;
-                    for (;;) {
-                        if (n_att >= cap) { failed = true; ls.capped += 1; break; }
-                        if (h_abs < min_step) { failed = true; ls.capped += 1; break; }
+                // One attempt per loop iteration and per lane, whether it opens a new step or retries a rejected one:
+                // with solve_ivp's nested "retry until accepted" loop, the lanes that accepted idled while the few that
+                // rejected repeated the whole attempt (ncu: 10 of 32 lanes active on average).  The loop condition is a
+                // warp vote, so the lanes reconverge every iteration; per-lane arithmetic and order are unchanged.
+                bool failed = false, rejected = false, fresh = true;
+                T min_step = (T)0;
+                const unsigned lanes = __activemask();
+                for (;;) {
+                    bool go = (t < A.t_end) && !failed;
+                    if (go && fresh) {
+                        if (early && escaped(A.F, r)) go = false;
+                        else {
+                            min_step = (T)10 * (nextafter(t, (T)INFINITY) - t);
+                            if (h_abs < min_step) h_abs = min_step;
+                            rejected = false; fresh = false;
+                        }
+                    }
+                    if (go && (n_att >= cap || h_abs < min_step)) { failed = true; ls.capped += 1; go = false; }
+                    if (!__any_sync(lanes, go)) break;
+                    if (go) {
                         T t_new = t + h_abs;
                         if (t_new - A.t_end > (T)0) t_new = A.t_end;
                         const T h = t_new - t;
@@ -740,10 +763,11 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
                         if (en < (T)1) {
                             h_abs *= dp5_factor<T>(en, true, rejected);
                             t = t_new; r = rn; f = fn; ls.acc += 1;
-                            break;
+                            fresh = true;
+                        } else {
+                            h_abs *= dp5_factor<T>(en, false, rejected);
+                            rejected = true;
                         }
-                        h_abs *= dp5_factor<T>(en, false, rejected);
-                        rejected = true;
                     }
                 }
                 ls.evals += touched;
