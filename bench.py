@@ -312,18 +312,16 @@ def run_ours(a):
         return
     peak, peak_src = peaks()
     per_launch_steps = steps_per_pass * a.steps / max(1, klaunch)
-    achieved = per_launch_steps * BYTES_PER_RAY_STEP / (kms / max(1, klaunch) * 1e-3) / 1e9 if kms > 0 else None
+    bytes_per_step = 768 if a.workload == "C4" else BYTES_PER_RAY_STEP      # DP5: 6 evaluations x 128 B; RK4: 4 x 128 B
+    achieved = per_launch_steps * bytes_per_step / (kms / max(1, klaunch) * 1e-3) / 1e9 if kms > 0 else None
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak if achieved else None,
             "traffic": None, "kernel": "k_propagate<%s, %s>" % ("float" if a.fp32 else "double", "RK45" if a.workload == "C4" else "RK4"), "kernel_ms_per_launch": kms / max(1, klaunch),
             "kernel_share_of_step": kms / ms if ms > 0 else None, "peak_source": peak_src,
-            "note": "achieved = algorithmic gather bytes (512 B per ray-step) / event-timed kernel duration; "
+            "note": "achieved = algorithmic gather bytes (%d B per ray-step) / event-timed kernel duration; " % bytes_per_step +
                     "gathers are served mostly by L1/L2 (rays are bundled per cell column), so frac may exceed 1; "
                     "see profiles/ for dram__bytes and L2 hit rate"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
-    roof["bytes_per_ray_step"] = 768 if a.workload == "C4" else 512
-    if a.workload == "C4" and achieved:
-        roof["achieved"] = achieved * 768 / 512
-        roof["frac"] = roof["achieved"] / peak
+    roof["bytes_per_ray_step"] = bytes_per_step
     if os.path.exists(traffic_file) and a.workload == "C2" and a.grid == 512 and n_rays == int(1e7) and not a.fp32:
         try:
             roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
