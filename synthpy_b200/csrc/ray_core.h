@@ -252,25 +252,47 @@ template <typename T, bool PHASE> struct CellCache {
 // Move the cached interval of one axis to the cell containing x.  `w_ok` = the weight test already placed x
 // in the cached cell.  Common case: the neighbouring cell (two table reads, exact comparisons); anything else
 // falls back to the exact search.  False = x is outside the grid.
-template <typename T> SP_HD bool relocate_axis(const AxisTab<T>& A, T x, bool w_ok, bool valid, int& i, T& lo, T& rinv) {
+// locate() plus the cell's (g[i], 1/(g[i+1]-g[i])): the table entry of the uniform first guess and the next node are
+// requested together and, when the guess is right (the rule on float32-rounded linspace axes), nothing else is read.
+template <typename T> SP_HD bool locate_cell(const AxisTab<T>& A, T x, int& i, T& lo, T& rinv) {
+    if (x < A.lo || x > A.hi) return false;
+    int k = floor_to_int((x - A.g0) * A.inv_d);
+    k = k < 0 ? 0 : (k > A.n - 2 ? A.n - 2 : k);
+    SP_ASSERT(A.n >= 2);
+    typename Pair<T>::type e = ldg(A.tab + k);
+    const T up = ldg_now(&(A.tab + k + 1)->x);
+    if (x == x && ((k > 0 && x < e.x) || (k < A.n - 2 && x >= up))) {       // exact walk, as locate()
+        while (k > 0 && x < ldg(A.tab + k).x) --k;
+        while (k < A.n - 2 && x >= ldg(A.tab + k + 1).x) ++k;
+        e = ldg(A.tab + k);
+    }
+    i = k; lo = e.x; rinv = e.y;
+    return true;
+}
+
+// Move the cached interval of one axis to the cell containing x.  `w_ok` = the weight test already placed x
+// in the cached cell.  NEAR (fixed-step marching: a miss is almost always the neighbouring cell): two table reads
+// and exact comparisons, anything else falls back to the exact search.  !NEAR (adaptive steps jump several cells
+// and the lanes of a warp disagree on how far): straight to the search, one code path for every lane.
+// False = x is outside the grid.
+template <bool NEAR, typename T> SP_HD bool relocate_axis(const AxisTab<T>& A, T x, bool w_ok, bool valid, int& i, T& lo, T& rinv) {
     if (valid) {
         if (w_ok) return true;
-        if (x >= lo) {
-            if (i + 2 < A.n) {
-                const typename Pair<T>::type e1 = ldg(A.tab + i + 1);
-                const T e2x = ldg_now(&(A.tab + i + 2)->x);          // requested together with e1: one round trip
-                if (x < e1.x) return true;                       // weight rounded up to 1: still this cell
-                if (x < e2x) { ++i; lo = e1.x; rinv = e1.y; return true; }
+        if (NEAR) {
+            if (x >= lo) {
+                if (i + 2 < A.n) {
+                    const typename Pair<T>::type e1 = ldg(A.tab + i + 1);
+                    const T e2x = ldg_now(&(A.tab + i + 2)->x);          // requested together with e1: one round trip
+                    if (x < e1.x) return true;                       // weight rounded up to 1: still this cell
+                    if (x < e2x) { ++i; lo = e1.x; rinv = e1.y; return true; }
+                }
+            } else if (x < lo && i > 0) {
+                const typename Pair<T>::type e0 = ldg(A.tab + i - 1);
+                if (x >= e0.x) { --i; lo = e0.x; rinv = e0.y; return true; }
             }
-        } else if (x < lo && i > 0) {
-            const typename Pair<T>::type e0 = ldg(A.tab + i - 1);
-            if (x >= e0.x) { --i; lo = e0.x; rinv = e0.y; return true; }
         }
     }
-    if (!locate(A, x, i)) return false;
-    const typename Pair<T>::type e = ldg(A.tab + i);
-    lo = e.x; rinv = e.y;
-    return true;
+    return locate_cell(A, x, i, lo, rinv);
 }
 
 template <typename T> SP_HD void tri_coef(T c000, T c001, T c010, T c011, T c100, T c101, T c110, T c111, T* a) {
@@ -299,16 +321,16 @@ template <typename T> SP_HD T tri_eval(const T* a, T wu, T wv, T ww) {
 // weights (needed anyway) with integer compares.  (A point within one ulp above a cell face can thus still be
 // evaluated with the previous cell's polynomial; the trilinear interpolant is continuous across faces, so
 // the value is the same to rounding.  Every decision taken on a miss is exact against the axis tables.)
-template <typename T, bool PHASE, bool AUX64>
+template <typename T, bool PHASE, bool AUX64, bool NEAR = true>
 SP_HD bool rhs(const FieldView<T>& F, CellCache<T, PHASE>& cc, T pu, T pv, T pw, T& au, T& av, T& aw, T& nm1) {
     T wu = (pu - cc.lo[0]) * cc.rinv[0], wv = (pv - cc.lo[1]) * cc.rinv[1], ww = (pw - cc.lo[2]) * cc.rinv[2];
     if (!unit_interval3(wu, wv, ww)) {
         au = av = aw = nm1 = (T)0;
         const bool oku = unit_interval(wu), okv = unit_interval(wv), okw = unit_interval(ww);
         const bool v = cc.valid();
-        if (!relocate_axis(F.ax[0], pu, oku, v, cc.idx[0], cc.lo[0], cc.rinv[0])) { cc.invalidate(); return false; }
-        if (!relocate_axis(F.ax[1], pv, okv, v, cc.idx[1], cc.lo[1], cc.rinv[1])) { cc.invalidate(); return false; }
-        if (!relocate_axis(F.ax[2], pw, okw, v, cc.idx[2], cc.lo[2], cc.rinv[2])) { cc.invalidate(); return false; }
+        if (!relocate_axis<NEAR>(F.ax[0], pu, oku, v, cc.idx[0], cc.lo[0], cc.rinv[0])) { cc.invalidate(); return false; }
+        if (!relocate_axis<NEAR>(F.ax[1], pv, okv, v, cc.idx[1], cc.lo[1], cc.rinv[1])) { cc.invalidate(); return false; }
+        if (!relocate_axis<NEAR>(F.ax[2], pw, okw, v, cc.idx[2], cc.lo[2], cc.rinv[2])) { cc.invalidate(); return false; }
         SP_ASSERT(cc.idx[0] >= 0 && cc.idx[0] <= F.ax[0].n - 2 && cc.idx[1] >= 0 && cc.idx[1] <= F.ax[1].n - 2 &&
                   cc.idx[2] >= 0 && cc.idx[2] <= F.ax[2].n - 2);
         const long long base = (long long)cc.idx[0] * F.su + (long long)cc.idx[1] * F.sv + cc.idx[2];
@@ -589,7 +611,7 @@ SP_HD int dp5_attempt(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega, T
             break;
         }
         T a0, a1, a2, nn;
-        touched += rhs<T, PHASE, AUX64>(F, cc, p[0], p[1], p[2], a0, a1, a2, nn);
+        touched += rhs<T, PHASE, AUX64, false>(F, cc, p[0], p[1], p[2], a0, a1, a2, nn);
         switch (s) {
         case 2: K2[0] = a0; K2[1] = a1; K2[2] = a2; break;
         case 3: K3[0] = a0; K3[1] = a1; K3[2] = a2; n3 = nn; break;

@@ -611,11 +611,11 @@ __device__ __forceinline__ void rk4x_integrate(const PropArgs<double>& A, Ray<do
 
 // Per-ray adaptive solve over the full 9-component state (same controller as the RK45 branch of k_propagate).
 template <bool PHASE, bool AUX64, typename T>
-__device__ __forceinline__ void rk45x_integrate(const PropArgs<T>& A, Ray<T>& r, CellCache<T, PHASE>& cc, bool early, uint64_t gi,
+__device__ __forceinline__ void rk45x_integrate(const PropArgs<T>& A, Ray<T>& r, CellCache<T, PHASE>& cc, bool early, unsigned lanes, uint64_t gi,
                                                 unsigned& n_att, LaneStats& ls, double& amp, double& pol) {}
 template <bool PHASE, bool AUX64>
 __device__ __noinline__ void rk45x_integrate(const PropArgs<double>& A, Ray<double>& r, CellCache<double, PHASE>& cc, bool early,
-                                             uint64_t gi, unsigned& n_att, LaneStats& ls, double& amp, double& pol) {
+                                             unsigned lanes, uint64_t gi, unsigned& n_att, LaneStats& ls, double& amp, double& pol) {
     const bool with_phase = (A.flags & SP_FLAG_PHASE) != 0;
     double y[9], f[9], yn[9], fn[9];
     for (int k = 0; k < 3; ++k) { y[k] = r.p[k]; y[3 + k] = r.v[k]; }
@@ -629,7 +629,6 @@ __device__ __noinline__ void rk45x_integrate(const PropArgs<double>& A, Ray<doub
     // one attempt per iteration and lane (new step or retry), warp-voted loop condition: see k_propagate
     bool failed = false, rejected = false, fresh = true;
     double min_step = 0.0;
-    const unsigned lanes = __activemask();
     for (;;) {
         bool go = (t < A.t_end) && !failed;
         if (go && fresh) {
@@ -685,6 +684,7 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
         if (slot0 >= A.chunk_n) break;
         const unsigned long long slot = slot0 + lane;
         const bool valid = slot < A.chunk_n;
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);      // the lanes that integrate a ray (warp converged here)
         const uint64_t li = valid ? (A.order ? (uint64_t)A.order[slot] : slot) : 0;
         const uint64_t gi = A.chunk_off + li;         // index into the caller's arrays
         double s[6];
@@ -712,7 +712,7 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
             if (METHOD == SP_METHOD_RK4X) {
                 rk4x_integrate<PHASE, AUX64>(A, r, cc, early, gi, n_att, ls, amp_x, pol_x);
             } else if (METHOD == SP_METHOD_RK45X) {
-                rk45x_integrate<PHASE, AUX64>(A, r, cc, early, gi, n_att, ls, amp_x, pol_x);
+                rk45x_integrate<PHASE, AUX64>(A, r, cc, early, vmask, gi, n_att, ls, amp_x, pol_x);
             } else if (METHOD == SP_METHOD_RK4) {
                 const T h = A.h;
                 for (int it = 0; it < A.n_steps; ++it) {
@@ -738,7 +738,7 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
                 // warp vote, so the lanes reconverge every iteration; per-lane arithmetic and order are unchanged.
                 bool failed = false, rejected = false, fresh = true;
                 T min_step = (T)0;
-                const unsigned lanes = __activemask();
+                const unsigned lanes = vmask;
                 for (;;) {
                     bool go = (t < A.t_end) && !failed;
                     if (go && fresh) {
