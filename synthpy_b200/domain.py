@@ -65,6 +65,14 @@ class ScalarDomain:
         XX, YY, _ = self._mesh()
         self._set(ne_0 * 10 ** (XX / s) * (1 + np.cos(2 * np.pi * YY / Ly)))
 
+    def test_lens(self, ne_0=1e24, LR=1e-3):           # minimal_solver.py:192-201: Gaussian column along z
+        XX, YY, _ = self._mesh()
+        self._set(ne_0 * np.exp(-(np.sqrt(XX ** 2 + YY ** 2)) ** 2 / LR ** 2))
+
+    def test_liner(self, ne_0=1e24, LR=1e-3):          # minimal_solver.py:203-212: Gaussian column along y
+        XX, _, ZZ = self._mesh()
+        self._set(ne_0 * np.exp(-(np.sqrt(XX ** 2 + ZZ ** 2)) ** 2 / LR ** 2))
+
     # -- external grids (domain.py:453-491)
     def external_ne(self, ne):
         """ne: (x_n, y_n, z_n) numpy array or CUDA torch tensor (float64 or float32), m^-3."""

@@ -62,6 +62,11 @@ def omega_of(lwl):
     return 2 * np.pi * (C_LIGHT / lwl)          # full_solver.py:218, propagator.py:357
 
 
+def critical_density(omega):
+    """n_c in m^-3 as the reference writes it (full_solver.py:220)."""
+    return 3.14207787e-4 * omega ** 2
+
+
 class DeviceField:
     """Owner of an ``sp_field`` handle (packed float4 grid + axis tables in HBM)."""
 

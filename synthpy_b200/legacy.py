@@ -40,6 +40,14 @@ class ScalarDomain:
         XX, YY, _ = self._mesh()
         self.ne = n_e0 * 10 ** (XX / s) * (1 + np.cos(2 * np.pi * YY / Ly))
 
+    def test_lens(self, n_e0=1e24, LR=1e-3):        # minimal_solver.py:192-201
+        XX, YY, _ = self._mesh()
+        self.ne = n_e0 * np.exp(-(np.sqrt(XX ** 2 + YY ** 2)) ** 2 / LR ** 2)
+
+    def test_liner(self, n_e0=1e24, LR=1e-3):       # minimal_solver.py:203-212
+        XX, _, ZZ = self._mesh()
+        self.ne = n_e0 * np.exp(-(np.sqrt(XX ** 2 + ZZ ** 2)) ** 2 / LR ** 2)
+
     def external_ne(self, ne):
         self.ne = ne
 
@@ -62,12 +70,17 @@ class ScalarDomain:
         kappa = engine.kappa_grid(self.ne, self.Te, self.Z, self.omega) if self.inv_brems else None
         self.field.attach_channels(kappa=kappa, ne=self.ne if self.B_on else None, B=self.B if self.B_on else None)
 
-    def calc_dndr(self, lwl=1053e-9, phase_f64=True):
-        """full_solver.py:211-234 on the device (float32 stencil identical to np.gradient)."""
+    def calc_dndr(self, lwl=1053e-9, phase_f64=True, ne_max=None):
+        """full_solver.py:211-234 on the device (float32 stencil identical to np.gradient).  ``ne_max`` (in units of
+        the critical density) is minimal_solver.calc_dndr's clamp, minimal_solver.py:231: ne_nc[ne_nc > ne_max] = ne_max."""
         self.lwl = lwl
         self.omega = engine.omega_of(lwl)
         self.VerdetConst = 2.62e-13 * lwl ** 2 if self.B_on else 0.0          # full_solver.py:222-223
-        self.field = engine.DeviceField.from_ne(self.ne, self.x, self.y, self.z, self.omega,
+        ne = self.ne
+        if ne_max is not None:
+            cap = ne_max * engine.critical_density(self.omega)
+            ne = ne.clamp(max=cap) if isinstance(ne, torch.Tensor) else np.minimum(ne, cap)
+        self.field = engine.DeviceField.from_ne(ne, self.x, self.y, self.z, self.omega,
                                                 march_axis=engine.AXIS[self.probing_direction],
                                                 phase=self.phaseshift, phase_f64=self.phaseshift and phase_f64)
 

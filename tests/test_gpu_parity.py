@@ -50,6 +50,28 @@ def test_field_stencil_bit_equal(sp, golden):
             assert np.array_equal(got[a], o.grads[a]), (dt, a)
 
 
+def test_ne_max_clamp(sp):
+    """minimal_solver.calc_dndr's clamp (minimal_solver.py:231): densities above ne_max critical densities are cut
+    before the gradient; bit-equal to the oracle's float32 pipeline on the clamped grid."""
+    x = np.float64(np.float32(np.linspace(-1e-3, 1e-3, 14)))
+    ne = 4e27 * np.random.default_rng(3).random((14, 14, 14))           # n_c(1064 nm) ~ 9.85e26: about 3/4 of the nodes clamp
+    omega = 2 * np.pi * C_LIGHT / 1064e-9
+    cap = 1.0 * 3.14207787e-4 * omega ** 2
+    assert 0.5 < np.mean(ne > cap) < 0.9
+    o = O.Domain(x, x, x, 1e-3)
+    o.external_ne(np.minimum(ne, cap))
+    o.calc_dndr(1064e-9)
+    d = sp.ScalarDomain(x, x, x, 1e-3)
+    d.external_ne(ne)
+    d.calc_dndr(1064e-9, ne_max=1.0)
+    got = [t.cpu().numpy() for t in d.field.export_gradients()[:3]]
+    for a in range(3):
+        assert np.array_equal(got[a], o.grads[a]), a
+    d.external_ne(torch.as_tensor(ne, device="cuda"))                   # device-resident grid takes the torch clamp
+    d.calc_dndr(1064e-9, ne_max=1.0)
+    assert np.array_equal(d.field.export_gradients()[0].cpu().numpy(), o.grads[0])
+
+
 def test_rhs_L0(sp, golden):
     g = golden("g1_rhs")
     for ph in (False, True):

@@ -64,3 +64,20 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["unit"] == "rays*steps/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+
+
+def test_gaussian_column_profiles():
+    """test_lens / test_liner (minimal_solver.py:192-212) in both API generations, against the closed form."""
+    from synthpy_b200 import domain as Dm, legacy
+    d = Dm.ScalarDomain([2e-3, 2e-3, 4e-3], [9, 11, 13])
+    d.test_lens(ne_0=3e24, LR=5e-4)
+    X, Y, Z = np.meshgrid(np.linspace(-1e-3, 1e-3, 9), np.linspace(-1e-3, 1e-3, 11), np.linspace(-2e-3, 2e-3, 13), indexing="ij")
+    assert d.ne.shape == (9, 11, 13) and np.allclose(d.ne, 3e24 * np.exp(-(X ** 2 + Y ** 2) / 5e-4 ** 2), rtol=1e-12)
+    d.test_liner(ne_0=3e24, LR=5e-4)
+    assert np.allclose(d.ne, 3e24 * np.exp(-(X ** 2 + Z ** 2) / 5e-4 ** 2), rtol=1e-12)
+    x, y, z = np.linspace(-1e-3, 1e-3, 9), np.linspace(-1e-3, 1e-3, 11), np.linspace(-2e-3, 2e-3, 13)
+    ld = legacy.ScalarDomain(x, y, z, 2e-3)
+    ld.test_lens(n_e0=3e24, LR=5e-4)
+    assert np.allclose(ld.ne, 3e24 * np.exp(-(X ** 2 + Y ** 2) / 5e-4 ** 2), rtol=1e-12)
+    ld.test_liner(n_e0=3e24, LR=5e-4)
+    assert np.allclose(ld.ne, 3e24 * np.exp(-(X ** 2 + Z ** 2) / 5e-4 ** 2), rtol=1e-12)
