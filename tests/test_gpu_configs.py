@@ -190,6 +190,36 @@ def test_C2_null_field_is_identity_at_full_size(mods):
     assert torch.max(torch.abs(rf[0] - x_exit)) < 1e-14
 
 
+def test_C5_grid_1024_properties(mods):
+    """BASELINE configs[4] at its full GRID size on one GPU (1024^3: 17 GB packed field, the largest grid the configs
+    name), with a 2e6-ray shard: conservation, two-shard partition invariance bit for bit, steps ~ 2 per cell."""
+    Dm, FG, B, D, P = mods["Dm"], mods["FG"], mods["B"], mods["D"], mods["P"]
+    free, _ = torch.cuda.mem_get_info()
+    if free < 90e9:
+        pytest.skip("needs ~90 GB of free device memory while the field is generated (FFT) and packed")
+    ne = FG.turbulent_ne(512, noise="torch", seed=3)
+    dom = Dm.ScalarDomain(LENGTHS, 1024)
+    dom.external_ne(ne)
+    fld = dom.device_field(LWL)
+    del ne
+    dom.ne = None
+    torch.cuda.empty_cache()
+    assert fld.nbytes >= 16 * 1024 ** 3
+    N = 2000000
+    beam = B.Beam(N, 5e-3, 5e-5, EXT, device=True, seed=2)
+
+    def run(n, off):
+        spec = D.spec("shadow_two", bin_scale=1)
+        st, _ = P.solve_and_image(dom, beam, EXT, [spec], lwl=LWL, n_rays=n, ray_offset=off)
+        return spec.image.counts.clone(), st
+    whole, st = run(N, 0)
+    assert st["rays_binned"] == int(whole.sum()) and 0 < int(whole.sum()) <= N
+    assert 1900 * N < st["ray_steps"] < 2100 * N                     # 2 steps per cell over 1023 cells, early exit
+    a, sa = run(1200000, 0)
+    b, sb = run(800000, 1200000)
+    assert torch.equal(a + b, whole) and sa["ray_steps"] + sb["ray_steps"] == st["ray_steps"]
+
+
 def test_quickstart_example_runs(mods):
     """examples/quickstart.py = the reference notebook's walkthrough; must run unchanged on the GPU."""
     import importlib.util
