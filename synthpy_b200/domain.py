@@ -101,11 +101,11 @@ class ScalarDomain:
     # -- device side
     def device_field(self, lwl, *, phase=None, phase_f64=False):
         """Packed float4 {grad, n-1} grid for wavelength ``lwl`` (cached)."""
-        if self.ne is None:
-            raise RuntimeError("no electron density loaded (call a test_* profile or external_ne)")
         phase = self.phaseshift if phase is None else phase
         key = (float(lwl), bool(phase), bool(phase_f64), self.probing_direction)
         if key not in self._fields:
+            if self.ne is None:
+                raise RuntimeError("no electron density loaded (call a test_* profile or external_ne)")
             self._fields[key] = engine.DeviceField.from_ne(
                 self.ne, self.x, self.y, self.z, engine.omega_of(lwl),
                 march_axis=engine.AXIS[self.probing_direction], phase=phase, phase_f64=phase_f64)
@@ -114,6 +114,11 @@ class ScalarDomain:
                 kappa = engine.kappa_grid(ne, self.Te, self.Z, engine.omega_of(lwl)) if self.inv_brems else None
                 self._fields[key].attach_channels(kappa=kappa, ne=ne if self.B_on else None, B=self.B if self.B_on else None)
         return self._fields[key]
+
+    def release_ne(self):
+        """Drop the density grid but keep the packed device fields built from it (a 1024^3 float64 grid is 8.6 GB
+        that the ray kernels never read again)."""
+        self.ne = None
 
     def cell_size(self, axis=None):
         a = engine.AXIS[self.probing_direction] if axis is None else axis

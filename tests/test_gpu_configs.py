@@ -202,7 +202,7 @@ def test_C5_grid_1024_properties(mods):
     dom.external_ne(ne)
     fld = dom.device_field(LWL)
     del ne
-    dom.ne = None
+    dom.release_ne()
     torch.cuda.empty_cache()
     assert fld.nbytes >= 16 * 1024 ** 3
     N = 2000000
