@@ -41,10 +41,13 @@ def main():
     del ne
     beam = B.Beam(n, bench.BEAM_R, bench.BEAM_DIV, bench.EXTENT, device=True, seed=2, beam_type="circular")
     rows, images = [], []
-    for rtol, atol in SWEEP:
+    for rtol, atol in [(None, None)] + SWEEP:              # first row: the fixed-step production mode, for comparison
         specs = [D.spec("refracto_incoherent", bin_scale=a.bin_scale),
                  D.spec("schlieren_knife", bin_scale=a.bin_scale, offset=0.1, axis=2, direction=1)]
-        kw = dict(lwl=bench.LWL, method="rk45_bundle" if a.bundle else "rk45", rtol=rtol, atol=atol, max_steps=a.max_steps)
+        if rtol is None:
+            kw = dict(lwl=bench.LWL, method="rk4", ds=0.5 * dom.cell_size())
+        else:
+            kw = dict(lwl=bench.LWL, method="rk45_bundle" if a.bundle else "rk45", rtol=rtol, atol=atol, max_steps=a.max_steps)
         for rep in range(2):                              # first pass warms caches / clocks, second is timed
             for s in specs:
                 s.image.zero_()
@@ -53,7 +56,7 @@ def main():
         ms, _ = engine.propagate_kernel_ms()
         sd = st                                             # sync=True returns the counters as a dict
         images.append([s.image.result().double().clone() for s in specs])
-        rows.append({"rtol": rtol, "atol": atol, "mode": "bundle" if a.bundle else "per ray", "rays": n,
+        rows.append({"rtol": rtol, "atol": atol, "mode": "rk4, ds = 0.5 cell" if rtol is None else ("bundle" if a.bundle else "per ray"), "rays": n,
                      "steps_per_ray": sd["ray_steps"] / n, "accepted_per_ray": sd["ray_steps_acc"] / n,
                      "rays_capped": sd["rays_capped"], "kernel_ms": ms, "rays_steps_per_s": sd["ray_steps"] / (ms * 1e-3),
                      "rays_per_s": n / (ms * 1e-3), "rays_binned": sd["rays_binned"]})
