@@ -2,7 +2,7 @@
 // exit-plane projection, ray-transfer-matrix optics and detector bin search.
 //
 // Everything here is `SP_HD` (host + device) and free of CUDA runtime calls so that the very same source
-// is (a) inlined into the sm_100a kernels in kernels.cu and (b) compiled by g++ into the CPU-side
+// is (a) inlined into the sm_100a kernels in synthpy_b200.cu and (b) compiled by g++ into the CPU-side
 // self-test harness (tests/host_harness.cpp) -- the build container has no GPU, so (b) is how the
 // arithmetic is exercised before a gpurun call.  (b) is a test build, not a product path.
 //
