@@ -478,3 +478,24 @@ def _odom(g):
     o.external_ne(g["ne"])
     o.calc_dndr(float(g["lwl"]))
     return o
+
+
+def test_integration_stub_runs(sp):
+    """The ctypes binding printed in INTEGRATION.md section 2, executed verbatim (only the library path is filled in),
+    gives the same exit rays as the shipped host side."""
+    import os
+    import types
+    from synthpy_b200 import _lib, beam as B, domain as Dm, propagator as P
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    md = open(os.path.join(root, "INTEGRATION.md")).read()
+    code = md[md.index("# src/simulator/_b200.py"):]
+    code = code[:code.index("```")].replace('C.CDLL("libsynthpy_b200.so")', "C.CDLL(%r)" % _lib.LIB_PATH)
+    ns = {}
+    exec(compile(code, "INTEGRATION.md", "exec"), ns)
+    dom = Dm.ScalarDomain([2e-3, 2e-3, 4e-3], 48, ne_type="test_exponential_cos")
+    s0 = B.Beam(3000, 0.6e-3, 1e-4, 2e-3, seeded=True).s0
+    ref, _, _ = P.solve(s0, dom, 2e-3, lwl=1064e-9)
+    duck = types.SimpleNamespace(ne=dom.ne, x=dom.x, y=dom.y, z=dom.z, probing_direction="z", lengths=dom.lengths, dims=dom.dims)
+    got = ns["solve"](s0, duck, 2e-3, 1064e-9)
+    ref = ref.cpu().numpy() if hasattr(ref, "cpu") else np.asarray(ref)
+    assert got.shape == ref.shape == (4, 3000) and np.array_equal(got, ref)
