@@ -489,6 +489,7 @@ template <typename T> struct PropArgs {
     int kp, ka, kb;                           // kernel-frame indices: probing axis, rf rows (0,1), rf rows (2,3)
     int method, flags, n_steps, n_state;
     T h, t_end, rtol, atol, omega, extent;
+    RK4Step<T> rk;                            // constants of the fixed step (host-computed, constant-bank operands)
     sp_stats* stats;
     ExtView X;                                // attenuation / Faraday channels (METHOD == SP_METHOD_RK4X only)
 };
@@ -714,9 +715,8 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
             } else if (METHOD == SP_METHOD_RK45X) {
                 rk45x_integrate<PHASE, AUX64>(A, r, cc, early, vmask, gi, n_att, ls, amp_x, pol_x);
             } else if (METHOD == SP_METHOD_RK4) {
-                const T h = A.h;
                 for (int it = 0; it < A.n_steps; ++it) {
-                    const int t = rk4_step<T, PHASE, AUX64>(A.F, cc, h, A.omega, r, early);
+                    const int t = rk4_step<T, PHASE, AUX64>(A.F, cc, A.rk, A.omega, r, early);
                     if (t < 0) break;
                     ls.evals += t;
                     ++n_att;
@@ -1406,7 +1406,7 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
         A.kb = kernel_index_of(field, P->out_axis_b);                                                    \
         A.method = P->method; A.flags = P->flags; A.n_steps = P->n_steps; A.n_state = P->n_state > 0 ? P->n_state : 9; \
         A.h = (T)P->h; A.t_end = (T)P->t_end; A.rtol = (T)P->rtol; A.atol = (T)P->atol; A.omega = (T)P->omega; \
-        A.extent = (T)P->extent; A.stats = stats_dev;
+        A.extent = (T)P->extent; A.stats = stats_dev; A.rk = RK4Step<T>((T)P->h);
         rc = ws_event(ws, st);
         if (rc) return rc;
         if (fp32) {
