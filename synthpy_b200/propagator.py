@@ -94,7 +94,8 @@ def solve_and_image(ScalarDomain, rays, probing_depth, diagnostics, *, lwl=1064e
                     phase_f64=False, sort=True, axis_convention="current", max_steps=None, sync=True):
     """Fused hot path: rays -> ODE -> exit plane -> optics -> detector images, in one kernel per chunk.
 
-    rays         a (9,N) array/tensor, or a ``Beam(device=True)`` whose rays are generated on the GPU
+    rays         a (9,N) array/tensor, a ``prefetch_rays`` handle (host bundle whose copy overlaps the previous call), or
+                 a ``Beam(device=True)`` whose rays are generated on the GPU
     diagnostics  list of ``DiagnosticSpec`` (see ``diagnostics.spec``); their images accumulate
     Returns (stats dict or None, elapsed seconds or None)."""
     engine.require_cuda()
@@ -108,16 +109,73 @@ def solve_and_image(ScalarDomain, rays, probing_depth, diagnostics, *, lwl=1064e
     if hasattr(rays, "spec"):                       # device Beam
         n = rays.Np if n_rays is None else n_rays
         kw.update(beam=rays.spec, n=n, ray_offset=ray_offset)
+    elif isinstance(rays, PrefetchedRays):          # copy already in flight on the side stream
+        torch.cuda.current_stream().wait_event(rays.copied)
+        kw.update(s0=rays.tensor)
     else:
         kw.update(s0=engine.to_device(rays, torch.float64))
     if sync:
         torch.cuda.synchronize()
     start = time()
     out = engine.propagate(field, P, **kw)
+    if isinstance(rays, PrefetchedRays):
+        rays.release()
     if not sync:
         return out["stats_dev"], None
     torch.cuda.synchronize()
     return engine.stats_dict(out["stats_dev"]), time() - start
+
+
+class PrefetchedRays:
+    """Handle returned by ``prefetch_rays``: a (9,N) device buffer whose host->device copy may still be running."""
+
+    def __init__(self, tensor, copied, state, slot):
+        self.tensor, self.copied, self._state, self._slot = tensor, copied, state, slot
+
+    def release(self):
+        """Mark the buffer reusable once the work queued so far on the current stream has read it."""
+        self._state["free"][self._slot].record(torch.cuda.current_stream())
+        self._state["busy"][self._slot] = False
+
+
+_PREFETCH = {}
+
+
+def prefetch_rays(s0_host):
+    """Start copying a (9,N) float64 ray bundle from PINNED host memory on a side stream and return a handle that
+    ``solve_and_image`` accepts in place of the rays.  Two device buffers alternate, so the copy of the next bundle
+    overlaps the propagation of the current one (the reference's drivers feed their workers chunk by chunk in the same
+    way, pvti_trace_multiprocess.py:102-125):
+
+        nxt = prefetch_rays(batches[0])
+        for k in range(len(batches)):
+            cur, nxt = nxt, (prefetch_rays(batches[k + 1]) if k + 1 < len(batches) else None)
+            solve_and_image(domain, cur, depth, specs, sync=False)
+    """
+    engine.require_cuda()
+    if not (isinstance(s0_host, torch.Tensor) and not s0_host.is_cuda and s0_host.is_pinned() and s0_host.dtype == torch.float64
+            and s0_host.ndim == 2 and s0_host.shape[0] == 9 and s0_host.is_contiguous()):
+        raise TypeError("prefetch_rays needs a contiguous (9, N) float64 tensor in pinned host memory")
+    n = int(s0_host.shape[1])
+    dev = torch.cuda.current_device()
+    st = _PREFETCH.get(dev)
+    if st is None or st["cap"] < 9 * n:
+        st = dict(stream=st["stream"] if st else torch.cuda.Stream(), cap=9 * n, next=0,
+                  bufs=[torch.empty(9 * n, dtype=torch.float64, device="cuda") for _ in range(2)],
+                  free=[torch.cuda.Event() for _ in range(2)], busy=[False, False])
+        _PREFETCH[dev] = st
+    b = st["next"]
+    if st["busy"][b]:
+        raise RuntimeError("two prefetched bundles are already outstanding: pass one to solve_and_image first")
+    st["next"] ^= 1
+    st["busy"][b] = True
+    dst = st["bufs"][b][:9 * n].view(9, n)
+    copied = torch.cuda.Event()
+    with torch.cuda.stream(st["stream"]):
+        st["stream"].wait_event(st["free"][b])          # the propagation that last read this buffer has finished
+        dst.copy_(s0_host, non_blocking=True)
+        copied.record(st["stream"])
+    return PrefetchedRays(dst, copied, st, b)
 
 
 def ray_to_Jonesvector(rays, ne_extent, *, probing_direction="z", keep_current_plane=False, return_E=False,

@@ -499,3 +499,32 @@ def test_integration_stub_runs(sp):
     got = ns["solve"](s0, duck, 2e-3, 1064e-9)
     ref = ref.cpu().numpy() if hasattr(ref, "cpu") else np.asarray(ref)
     assert got.shape == ref.shape == (4, 3000) and np.array_equal(got, ref)
+
+
+def test_prefetched_host_rays(sp, golden):
+    """propagator.prefetch_rays: bundles in pinned host memory copied on a side stream into two alternating device
+    buffers; images must equal those of the same rays passed as device tensors, count for count, over several rounds."""
+    from synthpy_b200 import beam as B, diagnostics as D, domain as Dm, propagator as P
+    dom = Dm.ScalarDomain([2e-3, 2e-3, 4e-3], 64, ne_type="test_exponential_cos")
+    batches = [torch.from_numpy(B.Beam(n, 0.8e-3, 1e-4, 2e-3, seeded=False).s0).pin_memory() for n in (50001, 70000, 33, 64000)]
+
+    def images(rays):
+        specs = [D.spec("shadow_single", bin_scale=8), D.spec("schlieren_DF", bin_scale=8, R_stop=0.2)]
+        st, _ = P.solve_and_image(dom, rays, 2e-3, specs, sync=False)
+        return [s.image.counts.clone() for s in specs], st
+    want = [images(b.cuda()) for b in batches]
+    got = []
+    nxt = P.prefetch_rays(batches[0])
+    for k in range(len(batches)):
+        cur, nxt = nxt, (P.prefetch_rays(batches[k + 1]) if k + 1 < len(batches) else None)
+        got.append(images(cur))
+    torch.cuda.synchronize()
+    for (gi, gs), (wi, ws) in zip(got, want):
+        assert all(torch.equal(a, b) for a, b in zip(gi, wi)) and torch.equal(gs, ws)
+    assert int(want[0][0][0].sum()) > 0
+    a, b = P.prefetch_rays(batches[0]), P.prefetch_rays(batches[1])
+    with pytest.raises(RuntimeError, match="outstanding"):
+        P.prefetch_rays(batches[2])
+    a.release(); b.release()
+    with pytest.raises(TypeError):
+        P.prefetch_rays(batches[0].cuda())
