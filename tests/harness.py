@@ -123,6 +123,12 @@ class HField:
                           C.c_int(int(self.f64 if aux64 is None else aux64)))
         return out
 
+    def rhs_walk(self, s, near):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        out = np.empty_like(s)
+        self.H.lib.hh_rhs_walk(self.h, _p(s), C.c_uint64(s.shape[1]), _p(out), C.c_int(int(near)))
+        return out
+
     def rk4(self, s0, n_steps, h, early=False, fp32=False, aux64=None):
         s0 = np.ascontiguousarray(s0, dtype=np.float64)
         sf = np.empty_like(s0)

@@ -129,6 +129,25 @@ extern "C" void hh_rhs(void* h, const double* s, uint64_t n, double* out, double
     else rhs_t<true, true>(f, s, n, out, omega);
 }
 
+// One persistent cell cache walked through the points in order (near = the fixed-step neighbour relocation, else the
+// direct search of the adaptive steppers): must give what a fresh cache gives at every point.
+template <bool NEARP>
+static void rhs_walk_t(const HostField* f, const double* s, uint64_t n, double* out) {
+    FieldView<double> F = f->view64();
+    CellCache<double, false> cc;
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray<double> r; load(f, s, n, i, r);
+        double a[3], nm1;
+        const bool in = rhs<double, false, false, NEARP>(F, cc, r.p[0], r.p[1], r.p[2], a[0], a[1], a[2], nm1);
+        for (int k = 0; k < 3; ++k) { out[(uint64_t)f->perm[k] * n + i] = r.v[k]; out[(uint64_t)(3 + f->perm[k]) * n + i] = in ? a[k] : 0.0; }
+        out[6 * n + i] = 0; out[7 * n + i] = 0; out[8 * n + i] = 0;
+    }
+}
+extern "C" void hh_rhs_walk(void* h, const double* s, uint64_t n, double* out, int near_) {
+    if (near_) rhs_walk_t<true>((const HostField*)h, s, n, out);
+    else rhs_walk_t<false>((const HostField*)h, s, n, out);
+}
+
 template <typename T, bool PH, bool A64>
 static void rk4_t(const HostField* f, const FieldView<T>& F, const double* s0, uint64_t n, int n_steps, double h,
                   double omega, int early, double* sf, uint32_t* steps) {

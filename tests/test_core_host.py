@@ -75,6 +75,51 @@ def test_non_uniform_axes(H):
     assert np.max(np.abs(out[3:6] - ref[3:6])) < 1e-11 * np.abs(ref[3:6]).max()
 
 
+def test_cell_cache_walk_equals_fresh_lookups(H):
+    """A cell cache dragged through an arbitrary walk -- single-cell moves in both directions on every axis, jumps,
+    excursions outside the grid and back, points exactly on nodes -- returns what a fresh lookup returns (bit for bit
+    away from nodes), for the neighbour relocation of the fixed-step kernel and for the direct search of the adaptive ones."""
+    rng = np.random.default_rng(21)
+    x = np.cumsum(rng.uniform(0.5, 2.0, 17)); x = (x - x.mean()) * 1e-3 / 3
+    y = np.linspace(-3e-3, 3e-3, 13); z = np.linspace(-1, 1, 29) ** 3 * 6e-3
+    ne = 1e25 * (1 + 0.5 * rng.random((17, 13, 29)))
+    f = H.field(ne, x, y, z, omega_of(1064e-9))
+    ax = [np.float64(np.float32(a)) for a in (x, y, z)]
+    n = 40000
+    pts = np.zeros((3, n))
+    p = np.array([a[len(a) // 2] for a in ax]) + 1e-7
+    for i in range(n):
+        u = rng.random()
+        if u < 0.70:                                   # small move: stays or crosses one face, either direction
+            k = rng.integers(3)
+            p[k] += rng.normal() * 0.6 * np.median(np.diff(ax[k]))
+        elif u < 0.85:                                 # jump anywhere, sometimes outside
+            p = np.array([rng.uniform(a[0] - 0.2 * (a[-1] - a[0]), a[-1] + 0.2 * (a[-1] - a[0])) for a in ax])
+        elif u < 0.95:                                 # exactly on a node of one axis
+            k = rng.integers(3)
+            p[k] = ax[k][rng.integers(len(ax[k]))]
+        else:                                          # one ulp either side of a node
+            k = rng.integers(3)
+            p[k] = np.nextafter(ax[k][rng.integers(len(ax[k]))], rng.choice([-np.inf, np.inf]))
+        pts[:, i] = p
+    s = np.zeros((9, n)); s[0:3] = pts; s[3:6] = 1.0
+    fresh = f.rhs(s)
+    assert 0.05 < np.mean(np.all(fresh[3:6] == 0, axis=0)) < 0.6          # the walk spends real time outside the grid too
+    scale = np.abs(fresh[3:6]).max()
+    for near in (True, False):
+        got = f.rhs_walk(s, near)
+        assert np.array_equal(got[3:6] == 0, fresh[3:6] == 0), near           # same in / out of grid decisions
+        differs = np.any(got[3:6] != fresh[3:6], axis=0)
+        # a point ON a node may be served by the cell below it with weight 1 - ulp instead of the cell above with
+        # weight 0 (the interpolant is continuous there): equal to rounding, and only there
+        assert differs.mean() < 0.01 and np.max(np.abs(got[3:6] - fresh[3:6])) < 1e-14 * scale, near
+        on_node = np.zeros(n, dtype=bool)
+        for k in range(3):
+            d = np.abs(pts[k][:, None] - ax[k][None, :]).min(axis=1)
+            on_node |= d <= 4 * np.spacing(np.abs(pts[k]))
+        assert not np.any(differs & ~on_node), near
+
+
 def test_rk4_matches_reference_rhs_loop(H, golden):
     for name, ph in (("g2_expcos", True), ("g3_turb", False)):
         g = golden(name)
