@@ -310,3 +310,36 @@ def test_philox_known_answer_and_beam_statistics(H):
     a = H.beam(1, 2, R, R, div, -ext, 7, 1000, 50)
     b = H.beam(1, 2, R, R, div, -ext, 7, 0, 1050)[:, 1000:]
     assert np.array_equal(a, b)
+
+
+def test_rk4_reflecting_rays(H):
+    """Over-critical density ramp: oblique rays turn around inside the plasma and leave through the face they entered
+    (v_z changes sign, cells are crossed downwards, early exit must not fire while a ray outside is heading back in).
+    Product RK4 against the loop around the reference RHS, with and without early exit."""
+    n = 40
+    x = np.linspace(-1e-3, 1e-3, n); z = np.linspace(-2e-3, 2e-3, 2 * n)
+    omega = omega_of(1064e-9)
+    nc = 3.14207787e-4 * omega ** 2
+    _, _, ZZ = np.meshgrid(x, x, z, indexing="ij")
+    ne = 1.6 * nc * np.clip((ZZ + 2e-3) / 4e-3, 0, 1)                       # 0 -> 1.6 n_c along z
+    d = O.Domain(x, x, z, 2e-3)
+    d.external_ne(ne)
+    d.calc_dndr(1064e-9)
+    f = H.field(ne, x, x, z, omega)
+    rng = np.random.default_rng(4)
+    N = 300
+    s0 = np.zeros((9, N))
+    s0[0], s0[1] = rng.uniform(-3e-4, 3e-4, N), rng.uniform(-3e-4, 3e-4, N)
+    s0[2] = -2e-3 - 1e-5 * rng.random(N)                                     # start just outside, heading in
+    th = rng.uniform(0.02, 0.1, N); ph = rng.uniform(0, 2 * np.pi, N)
+    s0[3], s0[4], s0[5] = C_LIGHT * np.sin(th) * np.cos(ph), C_LIGHT * np.sin(th) * np.sin(ph), C_LIGHT * np.cos(th)
+    s0[6] = 1.0
+    h = 0.5 * (z[1] - z[0]) / C_LIGHT
+    steps = 700
+    for early in (False, True):
+        ref, ref_steps = d.solve_rk4(s0, steps, h=h, early_exit=early)
+        got, got_steps = f.rk4(s0, steps, h, early=early)
+        assert np.mean(ref[5] < 0) > 0.9                                      # the rays did turn around
+        assert rel_err(got[:6], ref[:6]) < 1e-9
+        if early:
+            assert np.array_equal(got_steps, ref_steps) and ref_steps.max() < steps

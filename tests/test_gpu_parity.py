@@ -528,3 +528,36 @@ def test_prefetched_host_rays(sp, golden):
     a.release(); b.release()
     with pytest.raises(TypeError):
         P.prefetch_rays(batches[0].cuda())
+
+
+def test_rk4_reflecting_rays(sp):
+    """Over-critical density ramp: rays turn around inside the plasma (cells crossed downwards, v_z changes sign) and the
+    early exit must not fire while a ray outside is heading back in.  CUDA RK4 against the loop around the reference RHS."""
+    n = 40
+    x = np.linspace(-1e-3, 1e-3, n); z = np.linspace(-2e-3, 2e-3, 2 * n)
+    omega = 2 * np.pi * C_LIGHT / 1064e-9
+    nc = 3.14207787e-4 * omega ** 2
+    _, _, ZZ = np.meshgrid(x, x, z, indexing="ij")
+    ne = 1.6 * nc * np.clip((ZZ + 2e-3) / 4e-3, 0, 1)
+    o = O.Domain(x, x, z, 2e-3)
+    o.external_ne(ne)
+    o.calc_dndr(1064e-9)
+    d = sp.ScalarDomain(x, x, z, 2e-3)
+    d.external_ne(ne)
+    d.calc_dndr(1064e-9)
+    rng = np.random.default_rng(4)
+    N = 300
+    s0 = np.zeros((9, N))
+    s0[0], s0[1] = rng.uniform(-3e-4, 3e-4, N), rng.uniform(-3e-4, 3e-4, N)
+    s0[2] = -2e-3 - 1e-5 * rng.random(N)
+    th = rng.uniform(0.02, 0.1, N); ph = rng.uniform(0, 2 * np.pi, N)
+    s0[3], s0[4], s0[5] = C_LIGHT * np.sin(th) * np.cos(ph), C_LIGHT * np.sin(th) * np.sin(ph), C_LIGHT * np.cos(th)
+    s0[6] = 1.0
+    h = 0.5 * (z[1] - z[0]) / C_LIGHT
+    for early in (False, True):
+        ref, ref_steps = o.solve_rk4(s0, 700, h=h, early_exit=early)
+        d.solve(s0, method="rk4", n_steps=700, h=h, early_exit=early)
+        assert np.mean(ref[5] < 0) > 0.9
+        assert rel_err(d.sf[:6], ref[:6]) < 1e-9
+        if early:
+            assert np.array_equal(d.steps, ref_steps) and ref_steps.max() < 700
