@@ -578,6 +578,7 @@ __device__ __forceinline__ void rk45_bundle_integrate(const PropArgs<T>& A, Ray<
             if (valid) touched += dp5_attempt<T, PHASE, AUX64>(A.F, cc, A.omega, (T)h, rtol, atol, r, f, rn, fn, esq);
             ++n_att;
             const double en = sqrt(warp_sum_f64((double)esq)) / sqrt(size);
+            if (!(en == en)) { failed = true; ls.capped += valid ? 1 : 0; break; }   // NaN state: solve_ivp would never return
             if (en < 1.0) {
                 h_abs *= dp5_factor<double>(en, true, rejected);
                 t = t_new; r = rn; f = fn; ls.acc += valid ? 1 : 0;
@@ -657,7 +658,8 @@ __device__ __noinline__ void rk45x_integrate(const PropArgs<double>& A, Ray<doub
             touched += dp5_attempt9<PHASE, AUX64>(A.F, A.X, cc, A.omega, with_phase, h, A.rtol, A.atol, y, f, yn, fn, esq);
             ++n_att;
             const double en = sqrt(esq / 9.0);
-            if (en < 1.0) {
+            if (!(en == en)) { failed = true; ls.capped += 1; }                      // NaN state: solve_ivp would never return
+            else if (en < 1.0) {
                 h_abs *= dp5_factor<double>(en, true, rejected);
                 t = t_new; ls.acc += 1;
                 for (int i = 0; i < 9; ++i) { y[i] = yn[i]; f[i] = fn[i]; }
@@ -760,7 +762,8 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
                         touched += dp5_attempt<T, PHASE, AUX64>(A.F, cc, A.omega, h, A.rtol, A.atol, r, f, rn, fn, esq);
                         ++n_att;
                         const T en = sqrt(esq * inv_n);
-                        if (en < (T)1) {
+                        if (!(en == en)) { failed = true; ls.capped += 1; }          // NaN state: solve_ivp would never return
+                        else if (en < (T)1) {
                             h_abs *= dp5_factor<T>(en, true, rejected);
                             t = t_new; r = rn; f = fn; ls.acc += 1;
                             fresh = true;
@@ -1538,6 +1541,7 @@ static int joint_solve(const sp_field* field, const sp_params* P, sp_workspace* 
             ++attempts; evals += 6 * n;
             const double en = sqrt(ws->host_pair[0]) / sqrt(size);
             ws->jlog_h.push_back(h); ws->jlog_en.push_back(en);
+            if (!(en == en)) { failed = true; break; }                               // NaN state: solve_ivp would never return
             if (en < 1) {
                 double f = (en == 0) ? DP::MAX_FACTOR : fmin(DP::MAX_FACTOR, DP::SAFETY * pow(en, -0.2));
                 if (rejected) f = fmin(1.0, f);

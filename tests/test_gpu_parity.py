@@ -561,3 +561,20 @@ def test_rk4_reflecting_rays(sp):
         assert rel_err(d.sf[:6], ref[:6]) < 1e-9
         if early:
             assert np.array_equal(d.steps, ref_steps) and ref_steps.max() < 700
+
+
+def test_adaptive_solvers_stop_on_nan_rays(sp, golden):
+    """A NaN ray makes SciPy's error norm NaN: solve_ivp then rejects for ever.  The kernels mark such a ray (per ray),
+    its bundle (rk45_bundle) or the batch (rk45_joint, one norm for all rays as shipped) as failed and return."""
+    g = golden("g2_expcos")
+    d = _legacy_dom(sp, g)
+    s0 = g["s0"][:, :70].copy()
+    clean = d.solve(s0, method="rk45").copy()
+    s0[0, 37] = np.nan
+    rf = d.solve(s0, method="rk45")
+    assert d.stats["rays_capped"] == 1 and np.isnan(rf[0, 37])
+    assert np.array_equal(np.delete(rf, 37, axis=1), np.delete(clean, 37, axis=1))       # the other rays are untouched
+    rf = d.solve(s0, method="rk45_bundle", sort=False)
+    assert 1 <= d.stats["rays_capped"] <= 32 and not np.isnan(rf[:, 64:]).any()          # rays 64.. are another bundle
+    d.solve(s0, method="rk45_joint")
+    assert d.stats["ray_steps"] <= 70 * 3
