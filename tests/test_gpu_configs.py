@@ -257,3 +257,48 @@ def test_bench_contract_on_a_small_workload():
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 72 * 200000 and e["d2h_bytes_per_step"] > 0
     assert d["gpu_launches"] >= 2 * 4 and d["value"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+
+
+def test_pvti_field_equals_direct_field_and_driver_example_runs(mods, tmp_path, monkeypatch):
+    """a density grid written to .pvti and streamed back into HBM gives bit-identical gradients and
+    images to the same grid handed over directly; examples/pvti_trace.py (the reference's
+    pvti_trace_multiprocess.py driver) runs on it and conserves rays."""
+    import importlib.util
+    import os
+    import pickle
+    import sys
+    from synthpy_b200 import handle_filetypes as io
+    B, D, Dm, P = mods["B"], mods["D"], mods["Dm"], mods["P"]
+    n = 64
+    ax = np.linspace(-1, 1, n)
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing="ij")
+    ne = (3e24 * np.exp(-(X ** 2 + Z ** 2) / 0.3 ** 2) * (1 + 0.2 * np.cos(9 * Y))).astype(np.float32)
+    io.export_pvti(ne, fname=str(tmp_path / "dump"), extent_x=5e-3, extent_y=5e-3, extent_z=5e-3)
+    t, dim, sp = io.pvti_readin(str(tmp_path / "dump.pvti"), device="cuda")
+    assert t.is_cuda and t.is_contiguous() and dim == (n, n, n) and torch.equal(t.cpu(), torch.from_numpy(ne))
+    dom_f, ext = io.domain_from_pvti(str(tmp_path / "dump.pvti"), probing_direction="y")
+    dom_d = Dm.ScalarDomain([2 * e for e in ext], n, probing_direction="y")
+    dom_d.external_ne(ne)
+    ga, gb = dom_f.device_field(LWL).export_gradients(), dom_d.device_field(LWL).export_gradients()
+    assert all(torch.equal(a, b) for a, b in zip(ga[:3], gb[:3]))
+    imgs = []
+    for dom in (dom_f, dom_d):
+        s = D.spec("shadow_single", bin_scale=8)
+        P.solve_and_image(dom, B.Beam(200000, ext[0], 5e-5, ext[1], probing_direction="y", device=True, seed=4), ext[1], [s])
+        imgs.append(s.image.result())
+    assert torch.equal(imgs[0], imgs[1]) and imgs[0].sum() > 0
+    # the driver, end to end, in the reference's units (ne * 1e12)
+    io.export_pvti(ne * 1e-12, fname=str(tmp_path / "drv"), extent_x=5e-3, extent_y=5e-3, extent_z=5e-3)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("pvti_trace", os.path.join(root, "examples", "pvti_trace.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    monkeypatch.setattr(sys, "argv", ["pvti_trace.py", "3e5", str(tmp_path / "drv.pvti"), str(tmp_path / "out_"), "--chunk", "1e5",
+                                      "--bin-scale", "8"])
+    sh_H, r_H = m.main()
+    assert sh_H.shape == (2574 // 8, 3448 // 8) and 0 < sh_H.sum() <= 3e5 and 0 < r_H.sum() <= 3e5
+    assert np.array_equal(pickle.load(open(tmp_path / "out_shadow.pkl", "rb")), sh_H)
+    # three chunks of 1e5 == one launch of 3e5 (device rays depend on (seed, index) only)
+    monkeypatch.setattr(sys, "argv", ["pvti_trace.py", "3e5", str(tmp_path / "drv.pvti"), str(tmp_path / "one_"), "--bin-scale", "8"])
+    sh1, r1 = m.main()
+    assert np.array_equal(sh1, sh_H) and np.array_equal(r1, r_H)
