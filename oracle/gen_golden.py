@@ -83,6 +83,39 @@ def probe_states(rng, n, lengths, frac_out=0.15):
     return s
 
 
+def fresnel_fixture():
+    """G7: the reference's wave-optics step, src/simulator/fresnel_integral.py (NumPy/SciPy only, imported unmodified):
+    scattered rays -> LinearNDInterpolator grids -> reflect pad + Tukey window -> Fresnel transfer function."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("fresnel_integral", os.path.join(REF, "simulator", "fresnel_integral.py"))
+    fi = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fi)
+    from scipy.interpolate import LinearNDInterpolator as LND
+    rng = np.random.default_rng(21)
+    N, nx, ny = 6000, 96, 72
+    Lx, Ly = 18e-3, 13.5e-3
+    r0 = np.zeros((4, N))
+    r0[0] = rng.uniform(-0.48 * Lx, 0.48 * Lx, N)            # the hull stops short of the grid: fill_value region
+    r0[2] = rng.uniform(-0.47 * Ly, 0.47 * Ly, N)
+    r0[1], r0[3] = rng.normal(0, 1e-3, (2, N))
+    amp = 1.0 + 0.3 * np.cos(2 * np.pi * r0[0] / 4e-3) * np.exp(-(r0[2] / 5e-3) ** 2)
+    phase = 40.0 * np.exp(-(r0[0] ** 2 + r0[2] ** 2) / (3e-3) ** 2) + 0.05 * rng.normal(size=N)
+    x, y = np.linspace(-Lx / 2, Lx / 2, nx), np.linspace(-Ly / 2, Ly / 2, ny)
+    lwl, z = 1064e-9, 0.3
+    XX, YY = np.meshgrid(x, y)
+    g = dict(r0=r0, amp=amp, phase=phase, x=x, y=y, Lx=Lx, Ly=Ly, lwl=lwl, z=z)
+    g["phase_grid"] = LND((r0[0], r0[2]), phase, fill_value=0.0)((XX, YY))          # fresnel_integral.py:71-77
+    g["amp_grid"] = LND((r0[0], r0[2]), amp, fill_value=0.0)((XX, YY))
+    U0 = g["amp_grid"] * np.exp(-1j * g["phase_grid"])
+    for pf in (2, 1):
+        prep = fi.prepare_field_for_propagation(U0, pad_factor=pf)
+        g["prep_pf%d_sub" % pf] = prep[::7, ::5]                                     # subsample: keeps the fixture small
+        g["out_pf%d" % pf] = fi.propagate(lwl, x, y, Lx, Ly, r0, amp, phase, z, pad_factor=pf)
+    g["out_lanex"] = fi.fresnel_propagate(fi.prepare_field_for_propagation(U0), (Lx, Ly), lwl, z, U0.shape,
+                                          lanex_fwhm_m=150e-6)
+    np.savez_compressed(os.path.join(OUT, "g7_fresnel.npz"), **g)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     fs, rtm, g3 = import_reference()
@@ -278,9 +311,13 @@ def main():
     kat["linear_cos_integrated"] = dom.ne.sum(axis=2)
     np.savez_compressed(os.path.join(OUT, "g5_kat.npz"), axis=a, extent=ext, **kat)
 
+    fresnel_fixture()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)) // 1024, "KiB")
 
 
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["fresnel"]:
+        fresnel_fixture()
+    else:
+        main()

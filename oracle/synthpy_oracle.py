@@ -395,3 +395,74 @@ def interfere_ref_beam(rf_m, E, n_fringes=10, deg=20):
     E = np.array(E, dtype=complex, copy=True)
     E[1] = E[1] + np.exp(2 * n_fringes / 3 * 1.0j * (xw * rf_m[0] + yw * rf_m[2]))
     return E
+
+
+# --------------------------------------------------------------------------------------------------
+# Wave-optics step                                     (/root/reference/src/simulator/fresnel_integral.py)
+# --------------------------------------------------------------------------------------------------
+# Pinned: tests/golden/g7_fresnel.npz is produced by the reference module itself (NumPy/SciPy only).
+
+def scatter_to_grid(px, py, values, x, y, fill_value=0.0):
+    """fresnel_integral.py:71-77: piecewise-linear interpolation of scattered samples on their Delaunay
+    triangulation (``scipy.interpolate.LinearNDInterpolator``, the reference's own call), evaluated on
+    ``np.meshgrid(x, y)`` -> (len(y), len(x)); ``fill_value`` outside the convex hull."""
+    from scipy.interpolate import LinearNDInterpolator
+    XX, YY = np.meshgrid(x, y)
+    return LinearNDInterpolator((px, py), values, fill_value=fill_value)((XX, YY))
+
+
+def tukey_window(M, alpha=0.4):
+    """``scipy.signal.windows.tukey(M, alpha)`` (symmetric) written out: cosine tapers of width
+    floor(alpha (M-1) / 2) + 1 samples at both ends, 1 between."""
+    n = np.arange(M, dtype=float)
+    if alpha <= 0:
+        return np.ones(M)
+    if alpha >= 1:
+        return 0.5 - 0.5 * np.cos(2 * np.pi * n / (M - 1))
+    width = int(np.floor(alpha * (M - 1) / 2.0))
+    w = np.ones(M)
+    head, tail = n[:width + 1], n[M - width - 1:]
+    w[:width + 1] = 0.5 * (1 + np.cos(np.pi * (-1 + 2.0 * head / alpha / (M - 1))))
+    w[M - width - 1:] = 0.5 * (1 + np.cos(np.pi * (-2.0 / alpha + 1 + 2.0 * tail / alpha / (M - 1))))
+    return w
+
+
+def reflect_index(i, n):
+    """Source index of ``np.pad(..., mode='reflect')`` for (possibly far) out-of-range i: period 2(n-1), no
+    repeated edge sample."""
+    if n == 1:
+        return np.zeros_like(i)
+    p = 2 * (n - 1)
+    m = np.mod(i, p)
+    return np.where(m < n, m, p - m)
+
+
+def fresnel_prepare(U0, pad_factor=2, alpha=0.4):
+    """fresnel_integral.py:7-24: reflect-pad by pad_factor x size on every side, then a separable Tukey window."""
+    n0, n1 = U0.shape
+    i0 = reflect_index(np.arange(-n0 * pad_factor, n0 * (1 + pad_factor)), n0)
+    i1 = reflect_index(np.arange(-n1 * pad_factor, n1 * (1 + pad_factor)), n1)
+    return U0[np.ix_(i0, i1)] * np.outer(tukey_window(len(i0), alpha), tukey_window(len(i1), alpha))
+
+
+def fresnel_propagate(U0_prepared, L, wavelength, z, original_shape, pad_factor=2, lanex_fwhm_m=None):
+    """fresnel_integral.py:27-59: transfer function exp(-i pi lambda z (fx^2 + fy^2)) on the padded grid (sample
+    spacing L / original size), optional Gaussian PSF, factor exp(i k z) / (i lambda z), crop to the original window."""
+    n0, n1 = original_shape
+    f0 = np.fft.fftfreq(U0_prepared.shape[0], d=L[0] / n0)
+    f1 = np.fft.fftfreq(U0_prepared.shape[1], d=L[1] / n1)
+    F2 = f0[:, None] ** 2 + f1[None, :] ** 2
+    spec = np.fft.fft2(U0_prepared) * np.exp(-1j * np.pi * wavelength * z * F2)
+    if lanex_fwhm_m is not None and lanex_fwhm_m > 0:
+        sigma = lanex_fwhm_m / (2 * np.sqrt(2 * np.log(2)))
+        spec = spec * np.exp(-2 * (np.pi * sigma) ** 2 * F2)
+    out = np.fft.ifft2(spec) * np.exp(1j * (2 * np.pi / wavelength) * z) / (1j * wavelength * z)
+    return out[n0 * pad_factor:n0 * (pad_factor + 1), n1 * pad_factor:n1 * (pad_factor + 1)]
+
+
+def fresnel(lwl, x, y, x_length, y_length, rays, amplitudes, phases, z, pad_factor=2):
+    """fresnel_integral.py:61-93 ``propagate``: rays (4,N) rows 0 / 2 are the sample positions."""
+    ph = scatter_to_grid(rays[0], rays[2], phases, x, y)
+    am = scatter_to_grid(rays[0], rays[2], amplitudes, x, y)
+    U0 = am * np.exp(-1j * ph)
+    return fresnel_propagate(fresnel_prepare(U0, pad_factor), (x_length, y_length), lwl, z, U0.shape, pad_factor)

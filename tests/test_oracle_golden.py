@@ -150,3 +150,28 @@ def test_attenuation_and_faraday_channels(golden):
     assert np.array_equal(d.solve_joint(g["s0"]), g["joint_sf"])
     sf1, nfev = d.solve_per_ray(g["s0"][:, :4])
     assert np.array_equal(sf1, g["perray_sf"][:, :4]) and np.array_equal(nfev, g["perray_nfev"][:4])
+
+
+def test_fresnel_step(golden):
+    """fresnel_integral.py (reference module run unmodified -> g7): interpolated grids bit-exact (same SciPy call),
+    window/pad bit-exact, propagated field to FFT rounding."""
+    g = golden("g7_fresnel")
+    r0, x, y = g["r0"], g["x"], g["y"]
+    assert np.array_equal(O.scatter_to_grid(r0[0], r0[2], g["phase"], x, y), g["phase_grid"])
+    assert np.array_equal(O.scatter_to_grid(r0[0], r0[2], g["amp"], x, y), g["amp_grid"])
+    from scipy.signal.windows import tukey
+    for M in (5, 96, 360, 481):
+        assert np.allclose(O.tukey_window(M, 0.4), tukey(M, 0.4), rtol=0, atol=1e-15)
+    a = np.arange(7.0)
+    for n_pad in (3, 6, 14):
+        assert np.array_equal(a[O.reflect_index(np.arange(-n_pad, 7 + n_pad), 7)], np.pad(a, n_pad, mode="reflect"))
+    U0 = g["amp_grid"] * np.exp(-1j * g["phase_grid"])
+    for pf in (2, 1):
+        prep = O.fresnel_prepare(U0, pf)
+        assert np.allclose(prep[::7, ::5], g["prep_pf%d_sub" % pf], rtol=0, atol=1e-15)
+        out = O.fresnel(float(g["lwl"]), x, y, float(g["Lx"]), float(g["Ly"]), r0, g["amp"], g["phase"], float(g["z"]), pad_factor=pf)
+        ref = g["out_pf%d" % pf]
+        assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
+    out = O.fresnel_propagate(O.fresnel_prepare(U0), (float(g["Lx"]), float(g["Ly"])), float(g["lwl"]), float(g["z"]), U0.shape,
+                              lanex_fwhm_m=150e-6)
+    assert np.abs(out - g["out_lanex"]).max() <= 1e-12 * np.abs(g["out_lanex"]).max()
