@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define SP_ABI_VERSION 2
+#define SP_ABI_VERSION 3
 
 /* error codes */
 #define SP_OK 0
@@ -253,6 +253,45 @@ int sp_exit_plane(const double* sf_dev, uint64_t n, int probing_axis, int out_ax
 /* Right-hand side only: d(state)/dt for arbitrary states (parity level L0; full_solver.py:516-544). */
 int sp_rhs(const sp_field* field, const sp_params* params, const double* s_dev, uint64_t n, double* dsdt_dev,
            void* stream);
+
+/* ------------------------------------------------------------------------------------- wave-optics step */
+/* The step that follows the ray path in the reference's coherent refractometer:
+ * src/simulator/fresnel_integral.py, called from Refractometry.fresnel_solve (src/simulator/diagnostics.py:529-552).
+ * The 2-D FFT between sp_fresnel_transfer's two neighbours is the caller's (cuFFT via torch.fft), as np.fft.fft2 is
+ * the reference's. */
+
+/*
+ * Piecewise-linear interpolation of scattered samples on a triangulation, evaluated on the nodes of a rectilinear
+ * grid: scipy.interpolate.LinearNDInterpolator((px, py), v, fill_value)(np.meshgrid(gx, gy)) of
+ * fresnel_integral.py:71-77.  The triangulation is the caller's (the host side builds it with scipy.spatial.Delaunay,
+ * i.e. the same Qhull call LinearNDInterpolator makes).
+ *   px_dev, py_dev  n_pts sample positions           val_dev  [n_val][n_pts] sample values (interpolated in one pass)
+ *   tri_dev         [n_tri][3] vertex indices        gx_dev (nx), gy_dev (ny) ascending grid coordinates
+ *   owner_dev       ny*nx int32 scratch              out_dev  [n_val][ny][nx]; fill_value outside the hull
+ */
+int sp_scatter_to_grid(const double* px_dev, const double* py_dev, const double* val_dev, int n_val, uint64_t n_pts,
+                       const int32_t* tri_dev, uint64_t n_tri, const double* gx_dev, const double* gy_dev, int nx, int ny,
+                       double fill_value, int32_t* owner_dev, double* out_dev, void* stream);
+
+/*
+ * prepare_field_for_propagation (fresnel_integral.py:7-24) fused with the construction of U0 (:79-84):
+ * np.pad(U0, pad_factor * shape, mode='reflect') times the outer product of two Tukey(alpha) windows.
+ *   mode 0: a_dev = U0 as interleaved complex128 [n0][n1], b_dev unused
+ *   mode 1: a_dev = amplitude grid, b_dev = phase grid, U0 = a exp(-i b)
+ *   u_pad_dev: complex128 [(2 pad_factor + 1) n0][(2 pad_factor + 1) n1]
+ */
+int sp_fresnel_prepare(const double* a_dev, const double* b_dev, int mode, int n0, int n1, int pad_factor, double alpha,
+                       double* u_pad_dev, void* stream);
+
+/* In place: spectrum[k0][k1] *= exp(-i pi lambda z (f0^2 + f1^2)) [* exp(-2 (pi sigma)^2 (f0^2 + f1^2)) if
+ * psf_sigma > 0], f = np.fft.fftfreq(m, d)  (fresnel_integral.py:36-49). */
+int sp_fresnel_transfer(double* spec_dev, int m0, int m1, double d0, double d1, double wavelength, double z,
+                        double psf_sigma, void* stream);
+
+/* Crop the centre [n0][n1] window of the padded field and multiply by the complex constant
+ * exp(i k z) / (i lambda z) given as (scale_re, scale_im)  (fresnel_integral.py:51-59). */
+int sp_fresnel_finish(const double* u_pad_dev, int n0, int n1, int pad_factor, double scale_re, double scale_im,
+                      double* out_dev, void* stream);
 
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 uint64_t sp_launch_count(void);

@@ -1652,3 +1652,148 @@ extern "C" int sp_image_finalize(const sp_image* img, double* H_dev, void* strea
     LAUNCH_CHECK();
     return SP_OK;
 }
+
+// ------------------------------------------------------------------------------- wave-optics step
+// Scattered rays -> detector grid on a triangulation, then the Fresnel step around the library FFT.  All four
+// kernels are streaming passes (HBM-bound: 16-32 B per sample); per-sample math is fresnel_core.h.
+#include "fresnel_core.h"
+
+static unsigned stream_grid(unsigned long long n) {                    // grid-stride launches: a few waves of 148 SMs
+    unsigned long long b = (n + 255) / 256;
+    return (unsigned)(b < 148ull * 16 ? (b ? b : 1) : 148ull * 16);
+}
+
+// pass 1: every triangle claims the grid nodes it contains; ties (nodes on shared edges) go to the lowest index,
+// so the result does not depend on scheduling
+__global__ void k_tri_owner(const double* __restrict__ px, const double* __restrict__ py, const int32_t* __restrict__ tri,
+                            unsigned long long n_tri, const double* __restrict__ gx, const double* __restrict__ gy, int nx,
+                            int ny, int32_t* __restrict__ owner) {
+    for (unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t < n_tri;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const int32_t ia = tri[3 * t], ib = tri[3 * t + 1], ic = tri[3 * t + 2];
+        const double ax = px[ia], ay = py[ia], bx = px[ib], by = py[ib], cx = px[ic], cy = py[ic];
+        const double x0 = fmin(ax, fmin(bx, cx)), x1 = fmax(ax, fmax(bx, cx));
+        const double y0 = fmin(ay, fmin(by, cy)), y1 = fmax(ay, fmax(by, cy));
+        const double sx = (x1 - x0) * 1e-12, sy = (y1 - y0) * 1e-12;
+        const int i0 = lower_bound_d(gx, nx, x0 - sx), j0 = lower_bound_d(gy, ny, y0 - sy);
+        for (int j = j0; j < ny && gy[j] <= y1 + sy; ++j)
+            for (int i = i0; i < nx && gx[i] <= x1 + sx; ++i) {
+                double l0, l1, l2;
+                if (bary2(ax, ay, bx, by, cx, cy, gx[i], gy[j], l0, l1, l2) && tri_inside(l0, l1, l2))
+                    atomicMin(owner + (size_t)j * nx + i, (int32_t)t);
+            }
+    }
+}
+
+// pass 2: one thread per grid node interpolates every value array inside its owning triangle
+__global__ void k_tri_interp(const double* __restrict__ px, const double* __restrict__ py, const double* __restrict__ val,
+                             int n_val, unsigned long long n_pts, const int32_t* __restrict__ tri,
+                             const double* __restrict__ gx, const double* __restrict__ gy, int nx, int ny,
+                             const int32_t* __restrict__ owner, double fill, double* __restrict__ out) {
+    const size_t npix = (size_t)nx * ny;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < npix; p += (size_t)gridDim.x * blockDim.x) {
+        const int32_t t = owner[p];
+        if (t == INT32_MAX) {
+            for (int v = 0; v < n_val; ++v) out[v * npix + p] = fill;
+            continue;
+        }
+        const int32_t ia = tri[3 * (size_t)t], ib = tri[3 * (size_t)t + 1], ic = tri[3 * (size_t)t + 2];
+        double l0, l1, l2;
+        bary2(px[ia], py[ia], px[ib], py[ib], px[ic], py[ic], gx[p % nx], gy[p / nx], l0, l1, l2);
+        for (int v = 0; v < n_val; ++v) {
+            const double* w = val + (size_t)v * n_pts;
+            out[v * npix + p] = l0 * w[ia] + l1 * w[ib] + l2 * w[ic];
+        }
+    }
+}
+
+__global__ void k_fill_i32(int32_t* __restrict__ a, size_t n, int32_t v) {
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < n; p += (size_t)gridDim.x * blockDim.x) a[p] = v;
+}
+
+extern "C" int sp_scatter_to_grid(const double* px_dev, const double* py_dev, const double* val_dev, int n_val,
+                                  uint64_t n_pts, const int32_t* tri_dev, uint64_t n_tri, const double* gx_dev,
+                                  const double* gy_dev, int nx, int ny, double fill_value, int32_t* owner_dev,
+                                  double* out_dev, void* stream) {
+    if (!px_dev || !py_dev || !val_dev || !gx_dev || !gy_dev || !owner_dev || !out_dev) return fail(SP_EINVAL, "null argument");
+    if (n_val < 1 || nx < 1 || ny < 1) return fail(SP_EINVAL, "need n_val, nx, ny >= 1");
+    if (n_tri && !tri_dev) return fail(SP_EINVAL, "null triangulation");
+    if (n_pts > (uint64_t)INT32_MAX || n_tri >= (uint64_t)INT32_MAX) return fail(SP_EINVAL, "more than 2^31 - 1 points / triangles");
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t npix = (size_t)nx * ny;
+    k_fill_i32<<<stream_grid(npix), 256, 0, st>>>(owner_dev, npix, INT32_MAX);
+    LAUNCH_CHECK();
+    if (n_tri) {
+        k_tri_owner<<<stream_grid(n_tri), 256, 0, st>>>(px_dev, py_dev, tri_dev, n_tri, gx_dev, gy_dev, nx, ny, owner_dev);
+        LAUNCH_CHECK();
+    }
+    k_tri_interp<<<stream_grid(npix), 256, 0, st>>>(px_dev, py_dev, val_dev, n_val, n_pts, tri_dev, gx_dev, gy_dev, nx, ny,
+                                                    owner_dev, fill_value, out_dev);
+    LAUNCH_CHECK();
+    return SP_OK;
+}
+
+__global__ void k_fresnel_prepare(const double* __restrict__ a, const double* __restrict__ b, int mode, long long n0,
+                                  long long n1, long long pad, double alpha, d2* __restrict__ out) {
+    const long long m0 = (2 * pad + 1) * n0, m1 = (2 * pad + 1) * n1, total = m0 * m1;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+        d2 u;
+        prepare_sample(a, b, mode, n0, n1, pad, alpha, p / m1, p % m1, u.x, u.y);
+        out[p] = u;
+    }
+}
+
+__global__ void k_fresnel_transfer(d2* __restrict__ spec, long long m0, long long m1, double d0, double d1,
+                                   double wavelength, double z, double sigma) {
+    const long long total = m0 * m1;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+        d2 u = spec[p];
+        transfer_sample(u.x, u.y, p / m1, p % m1, m0, m1, d0, d1, wavelength, z, sigma);
+        spec[p] = u;
+    }
+}
+
+__global__ void k_fresnel_finish(const d2* __restrict__ u_pad, long long n0, long long n1, long long pad, double cr,
+                                 double ci, d2* __restrict__ out) {
+    const long long m1 = (2 * pad + 1) * n1, total = n0 * n1;
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+        const d2 u = u_pad[(p / n1 + pad * n0) * m1 + (p % n1 + pad * n1)];
+        d2 o;
+        o.x = u.x * cr - u.y * ci;
+        o.y = u.x * ci + u.y * cr;
+        out[p] = o;
+    }
+}
+
+extern "C" int sp_fresnel_prepare(const double* a_dev, const double* b_dev, int mode, int n0, int n1, int pad_factor,
+                                  double alpha, double* u_pad_dev, void* stream) {
+    if (!a_dev || !u_pad_dev || (mode == 1 && !b_dev)) return fail(SP_EINVAL, "null argument");
+    if (mode != 0 && mode != 1) return fail(SP_EINVAL, "mode must be 0 (complex field) or 1 (amplitude, phase)");
+    if (n0 < 1 || n1 < 1 || pad_factor < 0) return fail(SP_EINVAL, "need n0, n1 >= 1 and pad_factor >= 0");
+    const unsigned long long total = (unsigned long long)(2 * pad_factor + 1) * n0 * (2 * pad_factor + 1) * n1;
+    k_fresnel_prepare<<<stream_grid(total), 256, 0, (cudaStream_t)stream>>>(a_dev, b_dev, mode, n0, n1, pad_factor, alpha,
+                                                                           (d2*)u_pad_dev);
+    LAUNCH_CHECK();
+    return SP_OK;
+}
+
+extern "C" int sp_fresnel_transfer(double* spec_dev, int m0, int m1, double d0, double d1, double wavelength, double z,
+                                   double psf_sigma, void* stream) {
+    if (!spec_dev) return fail(SP_EINVAL, "null argument");
+    if (m0 < 1 || m1 < 1 || !(d0 > 0) || !(d1 > 0)) return fail(SP_EINVAL, "need m0, m1 >= 1 and positive sample spacings");
+    k_fresnel_transfer<<<stream_grid((unsigned long long)m0 * m1), 256, 0, (cudaStream_t)stream>>>((d2*)spec_dev, m0, m1, d0, d1,
+                                                                                                  wavelength, z, psf_sigma);
+    LAUNCH_CHECK();
+    return SP_OK;
+}
+
+extern "C" int sp_fresnel_finish(const double* u_pad_dev, int n0, int n1, int pad_factor, double scale_re, double scale_im,
+                                 double* out_dev, void* stream) {
+    if (!u_pad_dev || !out_dev) return fail(SP_EINVAL, "null argument");
+    if (n0 < 1 || n1 < 1 || pad_factor < 0) return fail(SP_EINVAL, "need n0, n1 >= 1 and pad_factor >= 0");
+    k_fresnel_finish<<<stream_grid((unsigned long long)n0 * n1), 256, 0, (cudaStream_t)stream>>>((const d2*)u_pad_dev, n0, n1,
+                                                                                                pad_factor, scale_re, scale_im,
+                                                                                                (d2*)out_dev);
+    LAUNCH_CHECK();
+    return SP_OK;
+}

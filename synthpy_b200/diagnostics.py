@@ -228,6 +228,22 @@ class Refractometry(Diagnostic):
     def refractogram(self, bin_scale=1, pix_x=3448, pix_y=2574, clear_mem=False):   # diagnostics.py:526-527
         self.histogram_legacy(bin_scale=bin_scale, pix_x=pix_x, pix_y=pix_y, clear_mem=clear_mem)
 
+    def fresnel_solve(self, bin_scale=1, pix_x=3448, pix_y=2574, clear_mem=False):
+        """diagnostics.py:529-552: the exit rays' amplitude and phase (constructor arguments ``amp``, ``phase``) are
+        interpolated onto the grid ``x`` x ``y`` (lengths ``x_l``, ``y_l``) and carried over ``3L/4 - focal_plane`` by the
+        Fresnel integral (``fresnel_integral.propagate``); ``self.Jf`` becomes that field, as upstream.  Upstream then
+        indexes the (ny, nx) field with ray numbers while binning (``self.Jf[0, i]``), which JAX's clamped indexing turns
+        into an image of two grid rows; here ``H`` is the field's magnitude on the grid instead."""
+        from . import fresnel_integral
+        if any(v is None for v in (self.x, self.y, self.x_l, self.y_l, self.amp, self.phase)):
+            raise ValueError("fresnel_solve needs x, y, x_l, y_l, amp and phase (constructor keyword arguments)")
+        U = fresnel_integral.propagate(self.wavelength, self.x, self.y, self.x_l, self.y_l, m_to_mm(self._rf_m), self.amp,
+                                       self.phase, 3 * self.L / 4 - self.focal_plane)
+        self._Jf = U
+        self.H = self._view(U.abs())
+        if clear_mem:
+            clear_rays(self)
+
 
 class Interferometry(Diagnostic):
     def interfere_ref_beam(self, n_fringes, deg):    # diagnostics.py:559-581 (evaluated on exit rays in METRES)

@@ -9,7 +9,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 SO = os.path.join(HERE, "_build", "libhost_harness.so")
 SRC = os.path.join(HERE, "host_harness.cpp")
 DEPS = [SRC, os.path.join(HERE, "..", "synthpy_b200", "csrc", "ray_core.h"),
-        os.path.join(HERE, "..", "synthpy_b200", "csrc", "field_prep.h")]
+        os.path.join(HERE, "..", "synthpy_b200", "csrc", "field_prep.h"),
+        os.path.join(HERE, "..", "synthpy_b200", "csrc", "fresnel_core.h")]
 
 OPK = {"travel": 0, "travel_noE": 1, "lens": 2, "circ_ap": 3, "circ_stop": 4, "rect_ap": 5, "knife": 6, "ref_beam": 7}
 
@@ -76,6 +77,50 @@ class Harness:
     def philox(self, key, ctr):
         out = np.empty(4, dtype=np.uint32)
         self.lib.hh_philox(*(C.c_uint32(k) for k in key), *(C.c_uint32(c) for c in ctr), _p(out))
+        return out
+
+
+class Fresnel:
+    """The wave-optics kernels' per-sample code (fresnel_core.h) run serially on the host; FFT by NumPy."""
+
+    def __init__(self, H):
+        self.lib = H.lib
+
+    def scatter_to_grid(self, px, py, values, tri, gx, gy, fill=0.0):
+        px, py, gx, gy = (np.ascontiguousarray(a, dtype=np.float64) for a in (px, py, gx, gy))
+        vals = np.ascontiguousarray(np.stack(values), dtype=np.float64)
+        tri = np.ascontiguousarray(tri, dtype=np.int32)
+        out = np.empty((vals.shape[0], len(gy), len(gx)))
+        self.lib.hh_scatter_to_grid(_p(px), _p(py), _p(vals), C.c_int(vals.shape[0]), C.c_uint64(len(px)), _p(tri),
+                                    C.c_uint64(len(tri)), _p(gx), _p(gy), C.c_int(len(gx)), C.c_int(len(gy)), C.c_double(fill), _p(out))
+        return out
+
+    def prepare(self, a, b=None, pad=2, alpha=0.4):
+        mode = 0 if b is None else 1
+        a = np.ascontiguousarray(a, dtype=np.complex128 if mode == 0 else np.float64)
+        b = None if b is None else np.ascontiguousarray(b, dtype=np.float64)
+        n0, n1 = a.shape
+        out = np.empty(((2 * pad + 1) * n0, (2 * pad + 1) * n1), dtype=np.complex128)
+        self.lib.hh_fresnel_prepare(_p(a), _p(b), C.c_int(mode), C.c_int(n0), C.c_int(n1), C.c_int(pad), C.c_double(alpha), _p(out))
+        return out
+
+    def propagate(self, prepared, L, wavelength, z, original_shape, pad=2, sigma=0.0):
+        n0, n1 = original_shape
+        spec = np.ascontiguousarray(np.fft.fft2(prepared))
+        self.lib.hh_fresnel_transfer(_p(spec), C.c_int(spec.shape[0]), C.c_int(spec.shape[1]), C.c_double(L[0] / n0),
+                                     C.c_double(L[1] / n1), C.c_double(wavelength), C.c_double(z), C.c_double(sigma))
+        back = np.fft.ifft2(spec)
+        scale = np.exp(1j * (2 * np.pi / wavelength) * z) / (1j * wavelength * z)
+        return back[pad * n0:(pad + 1) * n0, pad * n1:(pad + 1) * n1] * scale
+
+    def window(self, M, alpha):
+        w = np.empty(M)
+        self.lib.hh_window(C.c_int(M), C.c_double(alpha), _p(w))
+        return w
+
+    def reflect(self, n, lo, hi):
+        out = np.empty(hi - lo, dtype=np.int32)
+        self.lib.hh_reflect(C.c_int(n), C.c_int(lo), C.c_int(hi), _p(out))
         return out
 
 

@@ -387,3 +387,63 @@ extern "C" void hh_rk45_ext(void* hnd, const double* s0, uint64_t n, double t_en
         if (nfev) nfev[i] = evals;
     }
 }
+
+// ---- wave-optics step (fresnel_core.h): the loops below are the kernels of synthpy_b200.cu run serially ------------
+#include <limits.h>
+
+#include "../synthpy_b200/csrc/fresnel_core.h"
+
+extern "C" void hh_scatter_to_grid(const double* px, const double* py, const double* val, int n_val, uint64_t n_pts,
+                                   const int32_t* tri, uint64_t n_tri, const double* gx, const double* gy, int nx, int ny,
+                                   double fill, double* out) {
+    const size_t npix = (size_t)nx * ny;
+    std::vector<int32_t> owner(npix, INT32_MAX);
+    for (uint64_t t = 0; t < n_tri; ++t) {                                 // k_tri_owner
+        const int32_t ia = tri[3 * t], ib = tri[3 * t + 1], ic = tri[3 * t + 2];
+        const double ax = px[ia], ay = py[ia], bx = px[ib], by = py[ib], cx = px[ic], cy = py[ic];
+        const double x0 = fmin(ax, fmin(bx, cx)), x1 = fmax(ax, fmax(bx, cx));
+        const double y0 = fmin(ay, fmin(by, cy)), y1 = fmax(ay, fmax(by, cy));
+        const double sx = (x1 - x0) * 1e-12, sy = (y1 - y0) * 1e-12;
+        const int i0 = lower_bound_d(gx, nx, x0 - sx), j0 = lower_bound_d(gy, ny, y0 - sy);
+        for (int j = j0; j < ny && gy[j] <= y1 + sy; ++j)
+            for (int i = i0; i < nx && gx[i] <= x1 + sx; ++i) {
+                double l0, l1, l2;
+                if (bary2(ax, ay, bx, by, cx, cy, gx[i], gy[j], l0, l1, l2) && tri_inside(l0, l1, l2)) {
+                    int32_t& o = owner[(size_t)j * nx + i];
+                    if ((int32_t)t < o) o = (int32_t)t;
+                }
+            }
+    }
+    for (size_t p = 0; p < npix; ++p) {                                    // k_tri_interp
+        const int32_t t = owner[p];
+        if (t == INT32_MAX) {
+            for (int v = 0; v < n_val; ++v) out[v * npix + p] = fill;
+            continue;
+        }
+        const int32_t ia = tri[3 * (size_t)t], ib = tri[3 * (size_t)t + 1], ic = tri[3 * (size_t)t + 2];
+        double l0, l1, l2;
+        bary2(px[ia], py[ia], px[ib], py[ib], px[ic], py[ic], gx[p % nx], gy[p / nx], l0, l1, l2);
+        for (int v = 0; v < n_val; ++v) {
+            const double* w = val + (size_t)v * n_pts;
+            out[v * npix + p] = l0 * w[ia] + l1 * w[ib] + l2 * w[ic];
+        }
+    }
+}
+
+extern "C" void hh_fresnel_prepare(const double* a, const double* b, int mode, int n0, int n1, int pad, double alpha, double* out) {
+    const long long m0 = (2LL * pad + 1) * n0, m1 = (2LL * pad + 1) * n1;
+    for (long long p = 0; p < m0 * m1; ++p) prepare_sample(a, b, mode, n0, n1, pad, alpha, p / m1, p % m1, out[2 * p], out[2 * p + 1]);
+}
+
+extern "C" void hh_fresnel_transfer(double* spec, int m0, int m1, double d0, double d1, double wavelength, double z, double sigma) {
+    for (long long p = 0; p < (long long)m0 * m1; ++p)
+        transfer_sample(spec[2 * p], spec[2 * p + 1], p / m1, p % m1, m0, m1, d0, d1, wavelength, z, sigma);
+}
+
+extern "C" void hh_window(int M, double alpha, double* w) {
+    for (int i = 0; i < M; ++i) w[i] = tukey_w(i, M, alpha);
+}
+
+extern "C" void hh_reflect(int n, int lo, int hi, int32_t* out) {
+    for (int i = lo; i < hi; ++i) out[i - lo] = (int32_t)reflect_idx(i, n);
+}

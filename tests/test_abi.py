@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_binding_covers_header():
     from synthpy_b200 import _lib
     assert sorted(_lib.EXPORTS) == declared_symbols()
-    assert _lib.lib.sp_version() == 2
+    assert _lib.lib.sp_version() == 3
 
 
 def test_struct_sizes_match_header_layout():
@@ -82,6 +82,14 @@ def test_error_codes_without_touching_the_gpu():
     assert lib.sp_beam_generate(None, 0, 0, None, None) == -1
     assert lib.sp_image_finalize(None, None, None) == -1
     assert lib.sp_field_destroy(None) == 0 and lib.sp_workspace_destroy(None) == 0
+    d = C.c_void_p(8)
+    assert lib.sp_scatter_to_grid(None, None, None, 1, 0, None, 0, None, None, 1, 1, 0.0, None, None, None) == -1
+    assert lib.sp_scatter_to_grid(d, d, d, 0, 3, d, 1, d, d, 4, 4, 0.0, d, d, None) == -1 and b"n_val" in lib.sp_last_error()
+    assert lib.sp_scatter_to_grid(d, d, d, 1, 3, None, 1, d, d, 4, 4, 0.0, d, d, None) == -1 and b"triangulation" in lib.sp_last_error()
+    assert lib.sp_fresnel_prepare(d, None, 1, 4, 4, 2, 0.4, d, None) == -1 and b"null" in lib.sp_last_error()
+    assert lib.sp_fresnel_prepare(d, None, 2, 4, 4, 2, 0.4, d, None) == -1 and b"mode" in lib.sp_last_error()
+    assert lib.sp_fresnel_transfer(d, 4, 4, 0.0, 1.0, 1e-6, 0.1, 0.0, None) == -1 and b"spacings" in lib.sp_last_error()
+    assert lib.sp_fresnel_finish(None, 4, 4, 2, 1.0, 0.0, d, None) == -1
     import pytest
     with pytest.raises(L.SynthpyB200Error, match="synthpy_b200 error -1"):
         L.check(lib.sp_rhs(None, None, None, 0, None, None))

@@ -343,3 +343,70 @@ def test_rk4_reflecting_rays(H):
         assert rel_err(got[:6], ref[:6]) < 1e-9
         if early:
             assert np.array_equal(got_steps, ref_steps) and ref_steps.max() < steps
+
+
+def test_fresnel_step_matches_reference(H, golden):
+    """csrc/fresnel_core.h (host build) against g7 = the reference's fresnel_integral.py run unmodified."""
+    from harness import Fresnel
+    from scipy.signal.windows import tukey
+    from scipy.spatial import Delaunay
+    F, g = Fresnel(H), golden("g7_fresnel")
+    for M in (1, 2, 5, 96, 360, 481):
+        for alpha in (0.0, 0.4, 0.77, 1.0):
+            assert np.allclose(F.window(M, alpha), tukey(M, alpha), rtol=0, atol=2e-16 if alpha < 1 else 2e-15), (M, alpha)
+    a = np.arange(9)
+    for n_pad in (3, 8, 20):
+        assert np.array_equal(a[F.reflect(9, -n_pad, 9 + n_pad)], np.pad(a, n_pad, mode="reflect"))
+    assert np.array_equal(F.reflect(1, -3, 4), np.zeros(7))
+    # scattered rays -> grids on the Delaunay triangulation (Qhull on the host, as inside LinearNDInterpolator)
+    r0, x, y = g["r0"], g["x"], g["y"]
+    tri = Delaunay(np.stack([r0[0], r0[2]], axis=1)).simplices
+    ph, am = F.scatter_to_grid(r0[0], r0[2], [g["phase"], g["amp"]], tri, x, y)
+    assert np.array_equal(ph == 0.0, g["phase_grid"] == 0.0)                 # same nodes fall outside the hull
+    assert np.abs(ph - g["phase_grid"]).max() <= 1e-11 * np.abs(g["phase_grid"]).max()
+    assert np.abs(am - g["amp_grid"]).max() <= 1e-11
+    # pad + window (fused with U0 = amp exp(-i phase)), transfer function, crop
+    U0 = g["amp_grid"] * np.exp(-1j * g["phase_grid"])
+    Lxy = (float(g["Lx"]), float(g["Ly"]))
+    for pf in (2, 1):
+        prep = F.prepare(g["amp_grid"], g["phase_grid"], pad=pf)
+        assert np.abs(prep[::7, ::5] - g["prep_pf%d_sub" % pf]).max() <= 1e-15
+        assert np.abs(F.prepare(U0, pad=pf) - prep).max() <= 1e-15          # complex-input mode
+        out = F.propagate(prep, Lxy, float(g["lwl"]), float(g["z"]), U0.shape, pad=pf)
+        ref = g["out_pf%d" % pf]
+        assert np.abs(out - ref).max() <= 1e-12 * np.abs(ref).max()
+    sigma = 150e-6 / (2 * np.sqrt(2 * np.log(2)))
+    out = F.propagate(F.prepare(U0), Lxy, float(g["lwl"]), float(g["z"]), U0.shape, sigma=sigma)
+    assert np.abs(out - g["out_lanex"]).max() <= 1e-12 * np.abs(g["out_lanex"]).max()
+    # end to end from the device-side interpolation
+    out = F.propagate(F.prepare(am, ph), Lxy, float(g["lwl"]), float(g["z"]), U0.shape)
+    assert np.abs(out - g["out_pf2"]).max() <= 1e-9 * np.abs(g["out_pf2"]).max()
+
+
+def test_scatter_to_grid_edge_cases(H):
+    """Nodes on vertices and edges, a non-uniform grid, nodes outside the hull, duplicate-free degenerate input."""
+    from harness import Fresnel
+    from scipy.interpolate import LinearNDInterpolator
+    from scipy.spatial import Delaunay
+    F = Fresnel(H)
+    rng = np.random.default_rng(5)
+    gx = np.sort(np.concatenate([np.linspace(-1, 1, 21), rng.uniform(-1, 1, 12)]))
+    gy = np.linspace(-0.8, 0.8, 17)
+    # sample positions include exact grid nodes (vertex hits) and points on grid lines (edge hits)
+    XX, YY = np.meshgrid(gx[::4], gy[::3])
+    pts = np.concatenate([np.stack([XX.ravel(), YY.ravel()], 1), rng.uniform(-0.9, 0.9, (400, 2))])
+    v = np.sin(3 * pts[:, 0]) * np.cos(2 * pts[:, 1]) + pts[:, 0]
+    tri = Delaunay(pts).simplices
+    out = F.scatter_to_grid(pts[:, 0], pts[:, 1], [v], tri, gx, gy, fill=-7.0)[0]
+    ref = LinearNDInterpolator(pts, v, fill_value=-7.0)(*np.meshgrid(gx, gy))
+    assert np.array_equal(out == -7.0, ref == -7.0)
+    assert np.abs(out - ref).max() <= 1e-12
+    # a linear function is reproduced exactly (to rounding) inside the hull whatever the triangulation
+    lin = 2.0 * pts[:, 0] - 3.0 * pts[:, 1] + 0.5
+    out = F.scatter_to_grid(pts[:, 0], pts[:, 1], [lin], tri, gx, gy, fill=np.nan)[0]
+    GX, GY = np.meshgrid(gx, gy)
+    m = ~np.isnan(out)
+    assert m.sum() > 0.7 * m.size and np.abs(out[m] - (2.0 * GX - 3.0 * GY + 0.5)[m]).max() <= 1e-13
+    # no triangles at all: everything is fill
+    out = F.scatter_to_grid(pts[:3, 0], pts[:3, 1], [v[:3]], np.zeros((0, 3), np.int32), gx, gy, fill=1.5)[0]
+    assert np.all(out == 1.5)

@@ -578,3 +578,46 @@ def test_adaptive_solvers_stop_on_nan_rays(sp, golden):
     assert 1 <= d.stats["rays_capped"] <= 32 and not np.isnan(rf[:, 64:]).any()          # rays 64.. are another bundle
     d.solve(s0, method="rk45_joint")
     assert d.stats["ray_steps"] <= 70 * 3
+
+
+def test_fresnel_step(sp, golden):
+    """synthpy_b200.fresnel_integral (kernels + cuFFT) against g7 = the reference's fresnel_integral.py run
+    unmodified: interpolated grids, padded/windowed field, propagated field (with and without the PSF), and
+    Refractometry.fresnel_solve on top of it."""
+    from synthpy_b200 import diagnostics as D, fresnel_integral as FI
+    g = golden("g7_fresnel")
+    r0, x, y = g["r0"], g["x"], g["y"]
+    lwl, z, Lx, Ly = float(g["lwl"]), float(g["z"]), float(g["Lx"]), float(g["Ly"])
+    grids = FI.scatter_to_grid(r0[0], r0[2], [g["phase"], g["amp"]], x, y).cpu().numpy()
+    assert np.array_equal(grids[0] == 0.0, g["phase_grid"] == 0.0)           # same nodes outside the hull
+    assert np.abs(grids[0] - g["phase_grid"]).max() <= 1e-11 * np.abs(g["phase_grid"]).max()
+    assert np.abs(grids[1] - g["amp_grid"]).max() <= 1e-11
+    again = FI.scatter_to_grid(r0[0], r0[2], [g["phase"], g["amp"]], x, y).cpu().numpy()
+    assert np.array_equal(again, grids)                                       # owner by lowest index: run-to-run identical
+    U0 = g["amp_grid"] * np.exp(-1j * g["phase_grid"])
+    for pf in (2, 1):
+        prep = FI.prepare_field_for_propagation(U0, pad_factor=pf)
+        assert prep.shape == ((2 * pf + 1) * 72, (2 * pf + 1) * 96)
+        assert np.abs(prep[::7, ::5] - g["prep_pf%d_sub" % pf]).max() <= 1e-15
+        assert np.abs(prep - O.fresnel_prepare(U0, pf)).max() <= 1e-15
+        out = FI.fresnel_propagate(prep, (Lx, Ly), lwl, z, U0.shape, pad_factor=pf)
+        ref = g["out_pf%d" % pf]
+        assert np.abs(out - ref).max() <= 1e-11 * np.abs(ref).max()
+        full = FI.propagate(lwl, x, y, Lx, Ly, r0, g["amp"], g["phase"], z, pad_factor=pf)
+        assert np.abs(full - ref).max() <= 1e-9 * np.abs(ref).max()
+    out = FI.fresnel_propagate(FI.prepare_field_for_propagation(U0), (Lx, Ly), lwl, z, U0.shape, lanex_fwhm_m=150e-6)
+    assert np.abs(out - g["out_lanex"]).max() <= 1e-11 * np.abs(g["out_lanex"]).max()
+    with pytest.raises(ValueError):
+        FI.fresnel_propagate(np.zeros((10, 10), complex), (Lx, Ly), lwl, z, (3, 3))
+    # tensors in -> tensors out, no host round trip
+    t = FI.propagate(lwl, torch.from_numpy(x).cuda(), torch.from_numpy(y).cuda(), Lx, Ly, torch.from_numpy(r0).cuda(),
+                     torch.from_numpy(g["amp"]).cuda(), torch.from_numpy(g["phase"]).cuda(), z)
+    assert t.is_cuda and np.abs(t.cpu().numpy() - g["out_pf2"]).max() <= 1e-9 * np.abs(g["out_pf2"]).max()
+    # the diagnostic built on it (diagnostics.py:529-552): z = 3L/4 - focal_plane, rays in mm
+    rf_m = r0.copy()
+    rf_m[0::2] *= 1e-3                                                        # pretend the fixture positions are mm
+    rfr = D.Refractometry(lwl, rf_m, x=x, y=y, x_l=Lx, y_l=Ly, amp=g["amp"], phase=g["phase"], L=0.4, focal_plane=0.0)
+    rfr.fresnel_solve()
+    assert rfr.H.shape == (72, 96) and np.abs(rfr.H - np.abs(g["out_pf2"])).max() <= 1e-9 * np.abs(g["out_pf2"]).max()
+    with pytest.raises(ValueError):
+        D.Refractometry(lwl, rf_m).fresnel_solve()
