@@ -52,8 +52,17 @@ SP_HD double fft_freq(long long k, long long m, double d) {
     return (double)ks * (1.0 / ((double)m * d));
 }
 
+// U0 = amp exp(-i phase) (fresnel_integral.py:79)
+SP_HD void u0_from_amp_phase(double amp, double phase, double& re, double& im) {
+    double sn, cs;
+    sincos(phase, &sn, &cs);
+    re = amp * cs;
+    im = -(amp * sn);
+}
+
 // One sample (i0, i1) of the padded, windowed field.  mode 0: a = interleaved complex U0; mode 1: a = amplitude,
-// b = phase, U0 = a exp(-i b).  Source arrays are [n0][n1]; the padded grid is [(2 pad + 1) n0][(2 pad + 1) n1].
+// b = phase.  Source arrays are [n0][n1]; the padded grid is [(2 pad + 1) n0][(2 pad + 1) n1].  (The kernels compute
+// the same factors once per row / column / source sample instead of once per padded sample.)
 SP_HD void prepare_sample(const double* a, const double* b, int mode, long long n0, long long n1, long long pad,
                           double alpha, long long i0, long long i1, double& re, double& im) {
     const long long s0 = reflect_idx(i0 - pad * n0, n0), s1 = reflect_idx(i1 - pad * n1, n1);
@@ -63,20 +72,16 @@ SP_HD void prepare_sample(const double* a, const double* b, int mode, long long 
         ur = a[2 * src];
         ui = a[2 * src + 1];
     } else {
-        double sn, cs;
-        sincos(b[src], &sn, &cs);
-        ur = a[src] * cs;
-        ui = -(a[src] * sn);
+        u0_from_amp_phase(a[src], b[src], ur, ui);
     }
     const double w = tukey_w(i0, (2 * pad + 1) * n0, alpha) * tukey_w(i1, (2 * pad + 1) * n1, alpha);
     re = ur * w;
     im = ui * w;
 }
 
-// Multiply one spectrum sample by the Fresnel transfer function (and the optional Gaussian PSF, sigma > 0).
-SP_HD void transfer_sample(double& re, double& im, long long k0, long long k1, long long m0, long long m1, double d0,
-                           double d1, double wavelength, double z, double sigma) {
-    const double f0 = fft_freq(k0, m0, d0), f1 = fft_freq(k1, m1, d1);
+// Multiply one spectrum sample by the Fresnel transfer function (and the optional Gaussian PSF, sigma > 0);
+// f0, f1 are the sample's frequencies fft_freq(k, m, d).
+SP_HD void transfer_apply(double& re, double& im, double f0, double f1, double wavelength, double z, double sigma) {
     const double F2 = f0 * f0 + f1 * f1;
     double sn, cs;
     sincos(-(SP_PI * wavelength * z * F2), &sn, &cs);
@@ -89,6 +94,11 @@ SP_HD void transfer_sample(double& re, double& im, long long k0, long long k1, l
     const double r = re * hr - im * hi, i = re * hi + im * hr;
     re = r;
     im = i;
+}
+
+SP_HD void transfer_sample(double& re, double& im, long long k0, long long k1, long long m0, long long m1, double d0,
+                           double d1, double wavelength, double z, double sigma) {
+    transfer_apply(re, im, fft_freq(k0, m0, d0), fft_freq(k1, m1, d1), wavelength, z, sigma);
 }
 
 // Barycentric coordinates of p in triangle (a, b, c); false for a degenerate triangle.

@@ -1733,23 +1733,57 @@ extern "C" int sp_scatter_to_grid(const double* px_dev, const double* py_dev, co
     return SP_OK;
 }
 
-__global__ void k_fresnel_prepare(const double* __restrict__ a, const double* __restrict__ b, int mode, long long n0,
-                                  long long n1, long long pad, double alpha, d2* __restrict__ out) {
-    const long long m0 = (2 * pad + 1) * n0, m1 = (2 * pad + 1) * n1, total = m0 * m1;
-    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
+// U0 = amp exp(-i phase) on the source grid: one sincos per source sample instead of one per padded sample (x25 at pad 2)
+__global__ void k_fresnel_u0(const double* __restrict__ amp, const double* __restrict__ phase, long long n, d2* __restrict__ u0) {
+    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < n; p += (long long)gridDim.x * blockDim.x) {
         d2 u;
-        prepare_sample(a, b, mode, n0, n1, pad, alpha, p / m1, p % m1, u.x, u.y);
-        out[p] = u;
+        u0_from_amp_phase(amp[p], phase[p], u.x, u.y);
+        u0[p] = u;
     }
 }
 
-__global__ void k_fresnel_transfer(d2* __restrict__ spec, long long m0, long long m1, double d0, double d1,
-                                   double wavelength, double z, double sigma) {
-    const long long total = m0 * m1;
-    for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
-        d2 u = spec[p];
-        transfer_sample(u.x, u.y, p / m1, p % m1, m0, m1, d0, d1, wavelength, z, sigma);
-        spec[p] = u;
+// Reflect padding + separable Tukey window.  A CTA writes a tile of FR_ROWS rows x 256 columns: every thread keeps its
+// column's source index and window factor, the first FR_ROWS threads compute the rows', so a padded sample costs one
+// 16-byte gather (the source grid is 1/25 of the output and stays in L2), two multiplies and one coalesced 16-byte store.
+#define FR_ROWS 16
+__global__ void __launch_bounds__(256) k_fresnel_pad(const d2* __restrict__ u0, int n0, int n1, int pad, double alpha,
+                                                     d2* __restrict__ out) {
+    __shared__ double w0s[FR_ROWS];
+    __shared__ int s0s[FR_ROWS];
+    const long long m0 = (2LL * pad + 1) * n0, m1 = (2LL * pad + 1) * n1;
+    const long long c = blockIdx.x * 256LL + threadIdx.x, r0 = blockIdx.y * (long long)FR_ROWS;
+    if (threadIdx.x < FR_ROWS && r0 + threadIdx.x < m0) {
+        w0s[threadIdx.x] = tukey_w(r0 + threadIdx.x, m0, alpha);
+        s0s[threadIdx.x] = (int)reflect_idx(r0 + threadIdx.x - (long long)pad * n0, n0);
+    }
+    __syncthreads();
+    if (c >= m1) return;
+    const double w1 = tukey_w(c, m1, alpha);
+    const long long s1 = reflect_idx(c - (long long)pad * n1, n1);
+    const int rows = (int)((m0 - r0) < FR_ROWS ? (m0 - r0) : FR_ROWS);
+#pragma unroll 4
+    for (int k = 0; k < rows; ++k) {
+        const d2 u = u0[(long long)s0s[k] * n1 + s1];
+        const double w = w0s[k] * w1;
+        d2 o;
+        o.x = u.x * w;
+        o.y = u.y * w;
+        out[(r0 + k) * m1 + c] = o;
+    }
+}
+
+// Transfer function in place, same tiling: the column frequency once per thread, the row frequency once per row.
+__global__ void __launch_bounds__(256) k_fresnel_transfer(d2* __restrict__ spec, int m0, int m1, double d0, double d1,
+                                                          double wavelength, double z, double sigma) {
+    const long long c = blockIdx.x * 256LL + threadIdx.x, r0 = blockIdx.y * (long long)FR_ROWS;
+    if (c >= m1) return;
+    const double f1 = fft_freq(c, m1, d1);
+    const int rows = (int)((m0 - r0) < FR_ROWS ? (m0 - r0) : FR_ROWS);
+#pragma unroll 2
+    for (int k = 0; k < rows; ++k) {
+        d2 u = spec[(r0 + k) * m1 + c];
+        transfer_apply(u.x, u.y, fft_freq(r0 + k, m0, d0), f1, wavelength, z, sigma);
+        spec[(r0 + k) * m1 + c] = u;
     }
 }
 
@@ -1770,10 +1804,21 @@ extern "C" int sp_fresnel_prepare(const double* a_dev, const double* b_dev, int 
     if (!a_dev || !u_pad_dev || (mode == 1 && !b_dev)) return fail(SP_EINVAL, "null argument");
     if (mode != 0 && mode != 1) return fail(SP_EINVAL, "mode must be 0 (complex field) or 1 (amplitude, phase)");
     if (n0 < 1 || n1 < 1 || pad_factor < 0) return fail(SP_EINVAL, "need n0, n1 >= 1 and pad_factor >= 0");
-    const unsigned long long total = (unsigned long long)(2 * pad_factor + 1) * n0 * (2 * pad_factor + 1) * n1;
-    k_fresnel_prepare<<<stream_grid(total), 256, 0, (cudaStream_t)stream>>>(a_dev, b_dev, mode, n0, n1, pad_factor, alpha,
-                                                                           (d2*)u_pad_dev);
+    const long long m0 = (2LL * pad_factor + 1) * n0, m1 = (2LL * pad_factor + 1) * n1;
+    if ((m0 + FR_ROWS - 1) / FR_ROWS > 65535 || m1 > INT32_MAX) return fail(SP_EINVAL, "padded grid too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    const d2* u0 = (const d2*)a_dev;
+    d2* scratch = nullptr;
+    if (mode == 1) {                    // stream-ordered scratch for U0, released after the padding pass has read it
+        CU(cudaMallocAsync((void**)&scratch, (size_t)n0 * n1 * sizeof(d2), st));
+        k_fresnel_u0<<<stream_grid((unsigned long long)n0 * n1), 256, 0, st>>>(a_dev, b_dev, (long long)n0 * n1, scratch);
+        LAUNCH_CHECK();
+        u0 = scratch;
+    }
+    const dim3 grid((unsigned)((m1 + 255) / 256), (unsigned)((m0 + FR_ROWS - 1) / FR_ROWS));
+    k_fresnel_pad<<<grid, 256, 0, st>>>(u0, n0, n1, pad_factor, alpha, (d2*)u_pad_dev);
     LAUNCH_CHECK();
+    if (scratch) CU(cudaFreeAsync(scratch, st));
     return SP_OK;
 }
 
@@ -1781,8 +1826,9 @@ extern "C" int sp_fresnel_transfer(double* spec_dev, int m0, int m1, double d0, 
                                    double psf_sigma, void* stream) {
     if (!spec_dev) return fail(SP_EINVAL, "null argument");
     if (m0 < 1 || m1 < 1 || !(d0 > 0) || !(d1 > 0)) return fail(SP_EINVAL, "need m0, m1 >= 1 and positive sample spacings");
-    k_fresnel_transfer<<<stream_grid((unsigned long long)m0 * m1), 256, 0, (cudaStream_t)stream>>>((d2*)spec_dev, m0, m1, d0, d1,
-                                                                                                  wavelength, z, psf_sigma);
+    if ((m0 + FR_ROWS - 1) / FR_ROWS > 65535) return fail(SP_EINVAL, "grid too large");
+    const dim3 grid((unsigned)((m1 + 255) / 256), (unsigned)((m0 + FR_ROWS - 1) / FR_ROWS));
+    k_fresnel_transfer<<<grid, 256, 0, (cudaStream_t)stream>>>((d2*)spec_dev, m0, m1, d0, d1, wavelength, z, psf_sigma);
     LAUNCH_CHECK();
     return SP_OK;
 }
