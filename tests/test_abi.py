@@ -58,6 +58,9 @@ def test_no_cpu_fallback():
         dom = domain.ScalarDomain([1e-2, 1e-2, 2e-2], 8, ne_type="test_null")
         with pytest.raises(RuntimeError, match="no CPU fallback"):
             propagator.solve(np.zeros((9, 4)), dom, 1e-2)
+        from synthpy_b200 import config
+        with pytest.raises(RuntimeError, match="CUDA device|no CPU path"):
+            config.jax_init()
 
 
 def test_error_codes_without_touching_the_gpu():
