@@ -126,6 +126,19 @@ def _cpu_worker(args):
     return n * (sol.nfev - 2) / 6.0, time.perf_counter() - t0
 
 
+def _cpu_worker_rk4(args):
+    """The GPU arm's own integrator on the CPU: fixed-step RK4 (same step, early exit) around the reference's RHS."""
+    seed, n, h, n_steps = args
+    from oracle import synthpy_oracle as O
+    dom = _CPU["dom"]
+    s0 = O.init_beam(n, BEAM_R, BEAM_DIV, EXTENT, "circular", "z", rng=np.random.RandomState(seed))
+    t0 = time.perf_counter()
+    sf, steps = dom.solve_rk4(s0, n_steps, h=h, early_exit=True)
+    rf, _ = O.ray_to_jones(sf, EXTENT)
+    O.histogram(O.run_chain(rf, O.chain("shadow_two")), bin_scale=1)
+    return float(steps.sum()), time.perf_counter() - t0
+
+
 def _pool_init():
     """One BLAS/OpenMP thread per worker process: the pool already uses every core (the reference's own
     config pins threads to 1 as well, src/simulator/config.py:80-122); without this np.dot inside solve_ivp
@@ -352,12 +365,21 @@ def cpu_baseline(a, dom):
     cpu_setup(ne, a.grid)
     del ne
     ctx = mp.get_context("fork")
+    h = a.ds_frac * (LENGTHS[2] / (a.grid - 1)) / C_LIGHT
+    n_steps = int(np.ceil(np.sqrt(8.0) * EXTENT / C_LIGHT / h))
+    n4 = max(8, a.cpu_rays_per_worker // 16)
     with ctx.Pool(cores, initializer=_pool_init) as pool:
         cpu_pass(pool, cores, 8, 100)
         units, wall = cpu_pass(pool, cores, a.cpu_rays_per_worker, 200)
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker_rk4, [(300 + i, n4, h, n_steps) for i in range(cores)])
+        wall4 = time.perf_counter() - t0
     return {"value": units / wall, "unit": "rays*steps/s", "cores": cores, "kind": "port",
             "sample": f"{cores} workers x {a.cpu_rays_per_worker} rays, joint RK45 (SciPy defaults) + two-lens "
-                      f"shadowgraphy + histogram on the same {a.grid}^3 field; {wall:.1f} s wall"}
+                      f"shadowgraphy + histogram on the same {a.grid}^3 field; {wall:.1f} s wall",
+            "same_integrator": {"value": sum(r[0] for r in res) / wall4, "unit": "rays*steps/s",
+                                "sample": f"{cores} workers x {n4} rays, the GPU arm's fixed-step RK4 (ds = {a.ds_frac:g} cell, early "
+                                          f"exit) around the reference's dsdt; {wall4:.1f} s wall"}}
 
 
 if __name__ == "__main__":
