@@ -337,6 +337,7 @@ def run_ours(a):
                     "see profiles/ for dram__bytes and L2 hit rate"}
     traffic_file = os.path.join(ROOT, "profiles", "traffic_per_launch.json")
     roof["bytes_per_ray_step"] = bytes_per_step
+    roof["frac_of_nominal_8TBps"] = achieved / 8000.0 if achieved else None        # SURVEY.md 8d asks for both denominators
     if os.path.exists(traffic_file) and a.workload == "C2" and a.grid == 512 and n_rays == int(1e7) and not a.fp32:
         try:
             roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
