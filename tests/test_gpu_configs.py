@@ -302,3 +302,33 @@ def test_pvti_field_equals_direct_field_and_driver_example_runs(mods, tmp_path, 
     monkeypatch.setattr(sys, "argv", ["pvti_trace.py", "3e5", str(tmp_path / "drv.pvti"), str(tmp_path / "one_"), "--bin-scale", "8"])
     sh1, r1 = m.main()
     assert np.array_equal(sh1, sh_H) and np.array_equal(r1, r_H)
+
+
+def test_interference_driver_example(mods, tmp_path, monkeypatch):
+    """examples/interference_mpi.py (the reference's interference_MPI.py driver): the coherent sum does not depend on the
+    chunking; --sum-magnitudes reproduces the driver's `sh.H += sh_split.H` accumulation."""
+    import importlib.util
+    import os
+    import sys
+    from synthpy_b200 import handle_filetypes as io
+    n = 48
+    ax = np.linspace(-1, 1, n)
+    X, Y, Z = np.meshgrid(ax, ax, ax, indexing="ij")
+    ne = (2e18 * np.exp(-(X ** 2 + Z ** 2) / 0.4 ** 2)).astype(np.float32)        # x 1e6 below
+    io.export_pvti(ne, fname=str(tmp_path / "f"), extent_x=8e-3, extent_y=8e-3, extent_z=8e-3)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("interference_mpi", os.path.join(root, "examples", "interference_mpi.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+
+    def run(*extra):
+        monkeypatch.setattr(sys, "argv", ["interference_mpi.py", "6e4", "1e6", str(tmp_path / "f.pvti"), str(tmp_path / "o_"),
+                                          "--bin-scale", "16", "--fringes", "10", "--deg", "20", *extra])
+        return m.main()
+    one = run("--chunk", "6e4")
+    three = run("--chunk", "2e4")
+    assert one.shape == (2574 // 16 - 1, 3448 // 16 - 1) and one.max() > 0
+    assert np.abs(one - three).max() <= 1e-9 * one.max()                          # coherent sum: chunking is irrelevant
+    mags = run("--chunk", "2e4", "--sum-magnitudes")
+    assert np.abs(mags - one).max() > 1e-3 * one.max()                            # the driver's accumulation is not
+    assert (mags >= one - 1e-9 * one.max()).all()                                 # |a| + |b| + |c| >= |a + b + c| per plane pair
