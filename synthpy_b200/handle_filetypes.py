@@ -6,7 +6,7 @@ neither is needed here: the VTK XML ImageData format is restated directly (heade
 one appended section; ascii, base64 or raw; optionally zlib-compressed in blocks; UInt32 or UInt64 size headers).
 **Parity unpinned** against vtk itself (vtk / pyvista are not installed in the build image); what is pinned:
 the PVTI wrapper the reference writes by hand (handle_filetypes.py:72-81) and the one the reference ships
-(evaluation/sergio_testing/python_cube.pvti, kept as tests/golden/python_cube.pvti) parse, and the array
+(evaluation/sergio_testing/python_cube.pvti, its layout and attribute values in tests/test_filetypes.py) parse, and the array
 semantics of ``pvti_readin`` (first cell array, Fortran-order reshape to (nx, ny, nz), spacing) are the reference's.
 
 ``pvti_readin(..., device='cuda')`` streams the array into HBM piece by piece through pinned memory and returns a
