@@ -343,6 +343,20 @@ def run_ours(a):
             roof["traffic"] = json.load(open(traffic_file)).get("dram_bytes_per_launch")
         except Exception:
             pass
+    prof = os.path.join(ROOT, "profiles", "r1_v34_k_propagate_ncu_full.json")
+    if roof["traffic"] is not None and os.path.exists(prof):
+        # what actually bounds the kernel: pipe utilisations from the committed ncu capture of this
+        # same command -- static evidence, not measured in this run
+        try:
+            m = json.load(open(prof))
+            pick = {"fp64_pipe_pct": "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+                    "l1tex_lsu_wavefronts_pct": "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+                    "l2_hit_pct": "lts__t_sector_hit_rate.pct", "l1_hit_pct": "l1tex__t_sector_hit_rate.pct",
+                    "dram_throughput_pct": "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"}
+            roof["ncu"] = {k: float(m[v][0]) for k, v in pick.items() if v in m}
+            roof["ncu"]["source"] = "profiles/r1_v34_k_propagate_ncu_full.json"
+        except Exception:
+            pass
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
         cpu = cpu_baseline(a, dom)
