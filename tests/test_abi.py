@@ -108,3 +108,10 @@ def test_integration_stub_matches_binding():
     stub = type("Stub", (ctypes.Structure,), {"_fields_": [(n, getattr(ctypes, "c_" + t)) for n, t in names]})
     assert ctypes.sizeof(stub) == ctypes.sizeof(L.Params)
     assert all(getattr(stub, n).offset == getattr(L.Params, n).offset for n, _ in names)
+
+
+def test_integration_doc_names_every_entry_point():
+    """INTEGRATION.md maps each exported function to the reference interface it replaces."""
+    md = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in declared_symbols() if n not in md]
+    assert not missing, missing
