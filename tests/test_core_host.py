@@ -410,3 +410,24 @@ def test_scatter_to_grid_edge_cases(H):
     # no triangles at all: everything is fill
     out = F.scatter_to_grid(pts[:3, 0], pts[:3, 1], [v[:3]], np.zeros((0, 3), np.int32), gx, gy, fill=1.5)[0]
     assert np.all(out == 1.5)
+
+
+def test_fresnel_primitives_property(H):
+    """reflect_idx == np.pad('reflect') and tukey_w == scipy's window for arbitrary sizes (hypothesis)."""
+    from harness import Fresnel
+    from hypothesis import given, settings, strategies as st
+    from scipy.signal.windows import tukey
+    F = Fresnel(H)
+
+    @settings(max_examples=150, deadline=None)
+    @given(n=st.integers(1, 40), pad=st.integers(0, 130))
+    def reflect(n, pad):
+        a = np.arange(n)
+        assert np.array_equal(a[F.reflect(n, -pad, n + pad)], np.pad(a, pad, mode="reflect"))
+
+    @settings(max_examples=150, deadline=None)
+    @given(M=st.integers(1, 700), alpha=st.one_of(st.just(0.0), st.floats(1e-3, 1.0)))      # scipy itself overflows for denormal alpha
+    def window(M, alpha):
+        assert np.allclose(F.window(M, alpha), tukey(M, alpha), rtol=0, atol=4e-15)
+    reflect()
+    window()

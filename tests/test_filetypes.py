@@ -197,3 +197,24 @@ def test_errors(tmp_path):
     _vti(tmp_path / "nocell.vti", "")
     with pytest.raises(ValueError, match="no cell data"):
         hf.pvti_readin(str(tmp_path / "nocell.vti"))
+
+
+def test_round_trip_property(tmp_path):
+    """Random shapes, dtypes, layouts and extents: what is written is what is read (hypothesis)."""
+    from hypothesis import given, settings, strategies as st, HealthCheck
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(shape=st.tuples(st.integers(2, 9), st.integers(2, 9), st.integers(2, 9)),
+           dtype=st.sampled_from(["f4", "f8", "i4", "u2"]), encoding=st.sampled_from(["raw", "base64"]), compress=st.booleans(),
+           ext=st.tuples(*[st.floats(1e-4, 10.0)] * 3), seed=st.integers(0, 2 ** 16))
+    def run(shape, dtype, encoding, compress, ext, seed):
+        rng = np.random.RandomState(seed)
+        a = (rng.standard_normal(shape) * 1000).astype(dtype)
+        base = str(tmp_path / f"h{seed}")
+        hf.export_pvti(a, fname=base, extent_x=ext[0], extent_y=ext[1], extent_z=ext[2], encoding=encoding, compress=compress)
+        img, dim, spacing = hf.pvti_readin(base + ".pvti")
+        assert dim == shape and img.dtype == a.dtype and np.array_equal(img, a)
+        assert np.array_equal(spacing, hf.cell_spacing(shape, ext))
+        t, _, _ = hf.pvti_readin(base + ".vti", device="cpu")
+        assert t.is_contiguous() and np.array_equal(t.numpy(), a)
+    run()
