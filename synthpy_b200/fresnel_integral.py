@@ -35,6 +35,14 @@ def scatter_to_grid(px, py, values, x, y, fill_value=0.0, simplices=None):
     n = int(px_d.numel())
     if vals.shape[1] != n or py_d.numel() != n:
         raise ValueError("px, py and every value array must have the same length")
+    ok = torch.isfinite(px_d) & torch.isfinite(py_d)
+    if not bool(ok.all()):              # rays rejected by an aperture are NaN columns: Qhull (and upstream) cannot take them
+        if simplices is not None:
+            raise ValueError("NaN sample positions with a caller-supplied triangulation")
+        px_d, py_d, vals = px_d[ok].contiguous(), py_d[ok].contiguous(), vals[:, ok].contiguous()
+        n = int(px_d.numel())
+    if n < 3:
+        raise ValueError("need at least three finite sample positions to triangulate")
     if simplices is None:
         from scipy.spatial import Delaunay
         pts = np.stack([px_d.cpu().numpy(), py_d.cpu().numpy()], axis=1)
