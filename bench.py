@@ -47,13 +47,21 @@ def parse():
     ap.add_argument("--cpu-rays-per-worker", type=int, default=4000)
     ap.add_argument("--fp32", action="store_true")
     ap.add_argument("--ds-frac", type=float, default=0.5, help="RK4 step as a fraction of the cell size along the probing axis")
-    ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4"],
+    ap.add_argument("--workload", default="C2", choices=["C2", "C3", "C4", "C5"],
                     help="C2 shadowgraphy+schlieren (default, the headline); C3 interferometry with phase accumulation; "
-                         "C4 refractometry + knife-edge schlieren with adaptive RK45")
+                         "C4 refractometry + knife-edge schlieren with adaptive RK45; C5 shadowgraphy on a 1024^3 field with "
+                         "1e9 rays over 8 GPUs (--grid 1024 --rays 1.25e8 unless given)")
     ap.add_argument("--bundle", action="store_true", help="C4: one step size per 32-ray bundle instead of per ray")
     ap.add_argument("--rtol", type=float, default=1e-3)
     ap.add_argument("--atol", type=float, default=1e-6)
-    return ap.parse_args()
+    a = ap.parse_args()
+    if a.workload == "C5":                      # BASELINE configs[4]: 1e9 rays through 1024^3, sharded over the GPUs
+        if "--grid" not in sys.argv:
+            a.grid = 1024
+        if "--rays" not in sys.argv:
+            a.rays = 1.25e8
+        a.no_cpu_baseline = True               # the CPU port on a 1024^3 grid needs tens of GB and minutes: C2 carries it
+    return a
 
 
 def peaks():
@@ -205,7 +213,7 @@ def run_reference(a):
 
 def workload_config(a):
     diag = {"C2": "shadowgraphy(two-lens) + schlieren(DF)", "C3": "interferometry(two-lens, phase accumulation, reference beam)",
-            "C4": "refractometry(incoherent) + knife-edge schlieren"}[a.workload]
+            "C4": "refractometry(incoherent) + knife-edge schlieren", "C5": "shadowgraphy(two-lens)"}[a.workload]
     integ = (f"rk4, ds = {a.ds_frac:g} cell, early exit" if a.workload != "C4" else
              f"rk45 {'per 32-ray bundle' if a.bundle else 'per ray'} (SciPy controller), rtol {a.rtol:g} atol {a.atol:g}, early exit")
     return {"workload": f"{a.workload}: {int(a.rays):d} rays/GPU through a {a.grid}^3 turbulent (k^-11/3) n_e field, "
@@ -240,6 +248,8 @@ def run_ours(a):
               ds=a.ds_frac * dom.cell_size())
     if a.workload == "C2":
         specs = [D.spec("shadow_two", bin_scale=a.bin_scale), D.spec("schlieren_DF", bin_scale=a.bin_scale, R_stop=1)]
+    elif a.workload == "C5":       # BASELINE configs[4]: shadowgraphy only, 1024^3 field replicated on every GPU
+        specs = [D.spec("shadow_two", bin_scale=a.bin_scale)]
     elif a.workload == "C3":       # BASELINE configs[2]: phase accumulation + 2-D interferogram (reference beam 10 fringes, 20 deg)
         specs = [D.spec("interf_two", bin_scale=a.bin_scale, interferogram=True, wavelength=LWL, ref_beam=(10, 20))]
     else:                          # BASELINE configs[3]: refractometry + knife-edge schlieren, adaptive RK45 (SciPy controller)
