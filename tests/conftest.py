@@ -12,6 +12,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    # a fresh checkout has no built library (it is git-ignored) and the package refuses to import without it
+    if not os.path.exists(os.path.join(ROOT, "synthpy_b200", "csrc", "libsynthpy_b200.so")):
+        import __graft_entry__
+        __graft_entry__.build()
 
 
 @pytest.fixture(scope="session")

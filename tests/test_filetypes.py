@@ -11,7 +11,7 @@ import zlib
 import numpy as np
 import pytest
 
-hf = pytest.importorskip("synthpy_b200.handle_filetypes")
+from synthpy_b200 import handle_filetypes as hf
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
