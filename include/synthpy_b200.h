@@ -293,6 +293,12 @@ int sp_fresnel_transfer(double* spec_dev, int m0, int m1, double d0, double d1, 
 int sp_fresnel_finish(const double* u_pad_dev, int n0, int n1, int pad_factor, double scale_re, double scale_im,
                       double* out_dev, void* stream);
 
+/* Measurement aid for bench.py's roofline (no reference counterpart: the reference has no device code).  Enqueues
+ * one launch in which every resident thread of every SM runs 8 independent DFMA chains of `iters` links and writes
+ * one double to out_dev[thread] (thread < out_len); *n_dfma_out = DFMA thread-instructions of the launch.  The caller
+ * times it with CUDA events on `stream`: 2 * n_dfma / seconds is the FP64 FMA peak the integrator is held against. */
+int sp_fp64_peak(int iters, double* out_dev, uint64_t out_len, uint64_t* n_dfma_out, void* stream);
+
 /* Number of kernels this library has launched in the calling process (bench.py's gpu_launches). */
 uint64_t sp_launch_count(void);
 

@@ -1,17 +1,24 @@
-import pandas as pd, io, sys
-f=sys.argv[1]
-lines=open(f).read().split('\n')
-df=pd.read_csv(io.StringIO('\n'.join(lines[1:])))
-df['op']=df['Source'].str.strip().str.replace(r'^@!?U?P\d+\s+','',regex=True).str.split().str[0].str.split('.').str[0]
-ie='Instructions Executed'; sm='# Samples'
-tot=df[ie].sum(); ts=df[sm].sum()
-print('total inst',tot,'samples',ts, 'n sass', len(df))
-g=df.groupby('op').agg(inst=(ie,'sum'),samp=(sm,'sum'),thr=('Thread Instructions Executed','sum')).sort_values('inst',ascending=False)
-g['inst%']=100*g.inst/tot; g['samp%']=100*g.samp/ts; g['lanes']=g.thr/g.inst
-print(g.head(30).to_string())
-df['lanes']=df['Avg. Threads Executed']
-for lo,hi in [(0,8),(8,16),(16,24),(24,30),(30,33)]:
-    m=(df.lanes>=lo)&(df.lanes<hi)
-    print(lo,hi,'inst%',100*df[ie][m].sum()/tot,'samp%',100*df[sm][m].sum()/ts)
-st=[c for c in df.columns if c.startswith('stall_') and 'Not Issued' not in c]
-print((df[st].sum()/df[st].sum().sum()*100).sort_values(ascending=False).head(10))
+#!/usr/bin/env python
+"""Static SASS census of one kernel in the built library: instruction mix by pipe-relevant mnemonic.
+usage: sass_stats.py [lib.so] [substring of the mangled kernel name]"""
+import collections, re, subprocess, sys
+
+lib = sys.argv[1] if len(sys.argv) > 1 else "synthpy_b200/csrc/libsynthpy_b200.so"
+pat = sys.argv[2] if len(sys.argv) > 2 else "k_propagateIdLi0ELb0ELb0E"
+out = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+cur, funcs = None, collections.OrderedDict()
+for line in out.splitlines():
+    m = re.search(r"Function : (\S+)", line)
+    if m:
+        cur = m.group(1); funcs[cur] = []
+        continue
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d\s+)?([A-Z0-9_.]+)", line)
+    if m and cur:
+        funcs[cur].append(m.group(1))
+for name, ins in funcs.items():
+    if pat not in name:
+        continue
+    c = collections.Counter(i.split(".")[0] for i in ins)
+    keys = ["DFMA", "DADD", "DMUL", "DSETP", "F2F", "LDG", "LDC", "LDS", "STL", "LDL", "MOV", "IMAD", "ISETP", "BRA", "SHFL", "MUFU"]
+    print(name)
+    print("  total", len(ins), " ".join(f"{k}={c[k]}" for k in keys if c[k]))

@@ -156,6 +156,24 @@ def propagate_kernel_ms():
     return ms.value, n.value
 
 
+def fp64_peak(iters=20000, repeats=5):
+    """Measured FP64 FMA peak of the current GPU in TFLOP/s (2 flops per DFMA): best of ``repeats`` launches of the
+    library's DFMA microbenchmark, CUDA-event timed.  bench.py's roofline denominator for the integrator."""
+    require_cuda()
+    out = torch.empty(148 * 8 * 256 * 2, dtype=torch.float64, device="cuda")
+    n = C.c_uint64()
+    best = None
+    for _ in range(repeats + 1):                                 # first launch = warm-up
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        L.check(L.lib.sp_fp64_peak(int(iters), _ptr(out), out.numel(), C.byref(n), _stream()))
+        e1.record()
+        e1.synchronize()
+        ms = e0.elapsed_time(e1)
+        best = ms if best is None else min(best, ms)
+    return 2.0 * n.value / (best * 1e-3) / 1e12
+
+
 def joint_log():
     """(h, error_norm) arrays of every attempted step of the last 'rk45_joint' solve."""
     n = C.c_int()
