@@ -367,18 +367,32 @@ def cpu_baseline(a, ne_host):
 
 # ------------------------------------------------------------------------------------------------ parity
 def _rel(a_, b_, floor):
+    """max over entries of |a - b| / max(|b|, floor); floor is a scalar or one value per row.  NaN patterns must agree."""
     a_, b_ = np.asarray(a_), np.asarray(b_)
     if not np.array_equal(np.isnan(a_), np.isnan(b_)):
         return float("inf")
+    fl = np.broadcast_to(np.asarray(floor, dtype=np.float64).reshape(-1, *([1] * (b_.ndim - 1))) if np.ndim(floor) else floor, b_.shape)
     m = ~np.isnan(b_)
-    return float(np.max(np.abs(a_[m] - b_[m]) / np.maximum(np.abs(b_[m]), floor))) if m.any() else 0.0
+    return float(np.max(np.abs(a_[m] - b_[m]) / np.maximum(np.abs(b_[m]), fl[m]))) if m.any() else 0.0
 
 
-def parity_check(a, dom, rays, odom, n, ray_offset=0, workers=None):
+def _row_scale(rf_o):
+    """Natural scale of each exit-ray row [x, theta, y, phi]: its rms over the sample (beam size, deflection angle).
+    'Relative 1e-9' (north_star) is taken against max(|value|, this scale): a coordinate that happens to be ~0 has no
+    relative precision of its own, its error is 1e-9 of the beam like every other ray's."""
+    return np.maximum(np.sqrt(np.nanmean(np.asarray(rf_o) ** 2, axis=1)), 1e-12)
+
+
+def parity_check(a, dom, rays, odom, n, ray_offset=0, workers=None, conditioning=True):
     """The benchmarked configuration against the CPU oracle on a sub-sample of the very same rays: ``n`` rays starting at
     global index ``ray_offset`` of the device beam (or columns of the explicit bundle), through the same HBM-resident
     field and the same sort / early-exit / fused-epilogue path that produced the headline number.
-    Compares exit rays (relative, floor 1e-7: full_solver.py:838-894), steps per ray, and every detector image.
+    Compares exit rays (full_solver.py:838-894; relative to max(|value|, row rms), see _row_scale -- the old fixed 1e-7
+    floor is reported too), steps per ray, and every detector image.  ``conditioning``: the oracle is also run on the same
+    rays moved by ONE ulp, which shows how far rounding-level differences are amplified by the field itself.
+    Adaptive (C4): on a grid-scale-rough field SciPy's step-size map is chaotic, so step sequences
+    fork between ANY two implementations; reported are the fraction of rays with identical nfev, the agreement of those
+    rays, and the same two numbers for the oracle against its own one-ulp-perturbed run.
     ``odom``: oracle Domain prepared on the host copy of the same n_e grid (phaseshift=True for C3)."""
     from oracle import parallel as OP, synthpy_oracle as O
     from synthpy_b200 import propagator as P
@@ -399,11 +413,16 @@ def parity_check(a, dom, rays, odom, n, ray_offset=0, workers=None):
     finally:
         dom.phaseshift = was
     rf, steps, sf = rf.cpu().numpy(), ex["steps"].cpu().numpy().astype(np.int64), ex["sf"].cpu().numpy()
+    s1_h = s0_h.copy()
+    s1_h[0], s1_h[1] = np.nextafter(s1_h[0], np.inf), np.nextafter(s1_h[1], -np.inf)
     t0 = time.perf_counter()
     if a.workload == "C4":
         sf_o, nfev = OP.solve_per_ray(odom, s0_h, rtol=a.rtol, atol=a.atol, workers=workers)
-        out["steps_equal"] = bool(np.array_equal(6 * steps + 2, nfev))           # same accept / reject sequence per ray
+        same = (6 * steps + 2) == nfev                                         # same accept / reject sequence as solve_ivp
+        out["nfev_equal_frac"] = float(same.mean())
+        out["steps_equal"] = bool(same.all())
         out["steps_per_ray"] = float(steps.mean())
+        out["steps_per_ray_oracle"] = float((nfev - 2).mean() / 6.0)
     else:
         h, n_steps = rk4_lattice(a)
         sf_o, steps_o = OP.solve_rk4(odom, s0_h, n_steps, h=h, early_exit=True, workers=workers)
@@ -411,7 +430,24 @@ def parity_check(a, dom, rays, odom, n, ray_offset=0, workers=None):
         out["steps_per_ray"] = float(steps_o.mean())
     out["oracle_seconds"] = round(time.perf_counter() - t0, 2)
     rf_o, J_o = O.ray_to_jones(sf_o, EXTENT)
-    out["max_rel"] = _rel(rf, rf_o, 1e-7)
+    scale = _row_scale(rf_o)
+    out["max_rel"] = _rel(rf, rf_o, scale)
+    out["max_rel_floor_1e-7"] = _rel(rf, rf_o, 1e-7)
+    out["max_abs"] = [float(v) for v in np.nanmax(np.abs(rf - rf_o), axis=1)]
+    out["row_scale"] = [float(v) for v in scale]
+    if a.workload == "C4":
+        out["max_rel_same_sequence"] = _rel(rf[:, same], rf_o[:, same], scale) if same.any() else None
+        out["median_rel"] = float(np.median(np.max(np.abs(rf - rf_o) / np.maximum(np.abs(rf_o), scale[:, None]), axis=0)))
+    if conditioning:
+        if a.workload == "C4":
+            sf_1, nfev_1 = OP.solve_per_ray(odom, s1_h, rtol=a.rtol, atol=a.atol, workers=workers)
+            rf_1 = O.ray_to_jones(sf_1, EXTENT)[0]
+            out["oracle_one_ulp"] = {"nfev_equal_frac": float((nfev_1 == nfev).mean()), "max_rel": _rel(rf_1, rf_o, scale),
+                                     "median_rel": float(np.median(np.max(np.abs(rf_1 - rf_o) / np.maximum(np.abs(rf_o), scale[:, None]), axis=0)))}
+        else:
+            sf_1, _ = OP.solve_rk4(odom, s1_h, n_steps, h=h, early_exit=True, workers=workers)
+            rf_1 = O.ray_to_jones(sf_1, EXTENT)[0]
+            out["oracle_one_ulp"] = {"max_rel": _rel(rf_1, rf_o, scale), "max_abs": [float(v) for v in np.nanmax(np.abs(rf_1 - rf_o), axis=1)]}
     if c3:
         out["phase_max_rel"] = float(np.max(np.abs(sf[7] - sf_o[7])) / np.abs(sf_o[7]).max())
     # fused images of the same sub-sample, in the benchmarked mode (C3: once more with the float64 phase grid)
@@ -512,7 +548,7 @@ def run_ours(a):
     # multi-GPU content check: the all-reduced images of the last pass hold exactly the rays every rank binned
     allreduce_check = None
     if world > 1 and a.workload != "C3":
-        img_total = sum(int(s.image.counts.sum().item()) for s in specs)
+        img_total = sum(int(s.image.total().sum().item()) for s in specs)
         allreduce_check = {"sum_images": img_total, "sum_rays_binned_over_ranks": int(tot[1].item()),
                            "equal": img_total == int(tot[1].item())}
 
@@ -528,7 +564,7 @@ def run_ours(a):
         def e2e_pass(tok):
             st_ = one_pass(tok, root_only=True)          # like the reference's comm.reduce(H, root=0): one copy leaves the GPUs
             for o, s in zip(outs, specs):
-                o.copy_(s.image.tensors()[0], non_blocking=True)
+                o.copy_(s.image.total(), non_blocking=True)
             return st_
         # propagator.prefetch_rays: the host->device copy of step k+1's rays runs on a side stream while step k
         # propagates (two device buffers); every step's copy and image read-back is inside the timed region

@@ -14,8 +14,14 @@
  *     as torch tensors); `*_host` pointers are ordinary host memory.  The library keeps no device memory
  *     besides what hangs off an sp_field / sp_workspace handle.
  *   - work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream).  Calls
- *     do not synchronise unless documented (sp_propagate with SP_METHOD_RK45_JOINT does: its step-size
- *     controller is a host loop, as in the reference).
+ *     do not synchronise, with these documented exceptions (all one-off or parity-mode paths, none on the
+ *     fixed-step / per-ray adaptive hot path):
+ *       sp_field_create / sp_field_create_from_gradients  wait for `stream` before returning (host-side axis and
+ *                                 stencil tables, and for sp_field_create the float32 ne/nc scratch, are released);
+ *       sp_propagate with SP_METHOD_RK45_JOINT  waits once per attempted step (its step-size controller is a
+ *                                 host loop over device-side norms, as the reference's is a Python loop), and twice
+ *                                 more when stats_dev / steps_dev are given;
+ *       sp_workspace_propagate_ms waits for the last recorded launch (that is its purpose).
  *   - ray state layout is the reference's: 9 x N row-major float64
  *       [x, y, z, vx, vy, vz, amp, phase, pol]   (src/simulator/beam.py:63, src/solvers-legacy/full_solver.py:563)
  *     exit rays: 4 x N row-major float64 [x, theta, y, phi] (full_solver.py:849-881); Jones: 2 x N complex128.
@@ -29,7 +35,7 @@
 extern "C" {
 #endif
 
-#define SP_ABI_VERSION 3
+#define SP_ABI_VERSION 4
 
 /* error codes */
 #define SP_OK 0
@@ -133,7 +139,10 @@ typedef struct sp_optic_op {
 #define SP_IMG_HISTOGRAM 0    /* np.histogram2d semantics (rtm_solver.py:156-174, diagnostics.py:323-353):
                                  nb+1 linspace edges, right-most edge inclusive, counts uint64               */
 #define SP_IMG_INTERFEROGRAM 1 /* np.digitize-1 on nb linspace edges -> nb-1 bins, sums of complex E
-                                 (rtm_solver.py:424-453, diagnostics.py:358-379); planes float64            */
+                                 (rtm_solver.py:424-453, diagnostics.py:358-379); planes int64 fixed point  */
+#define SP_PLANE_FRAC_BITS 40  /* interferogram planes hold round(value * 2^40): integer sums are exact and
+                                 order-independent (run-to-run and GPU-count invariant images), quantisation
+                                 9e-13 per contribution, range +-8.4e6 per pixel (|E| per ray is <= ~2)       */
 
 typedef struct sp_image {
     int32_t kind;
@@ -142,7 +151,7 @@ typedef struct sp_image {
     double x_lo, x_hi;        /* edges = np.linspace(lo, hi, nx+1) in both modes (digitize: nx = n_edges - 1)  */
     double y_lo, y_hi;
     uint64_t* counts_dev;     /* [ny][nx], histogram only (caller zeroes; calls accumulate)                  */
-    double* planes_dev;       /* [4][ny][nx]: Re Ex, Im Ex, Re Ey, Im Ey; interferogram only                 */
+    int64_t* planes_dev;      /* [4][ny][nx]: Re Ex, Im Ex, Re Ey, Im Ey, fixed point (SP_PLANE_FRAC_BITS)    */
 } sp_image;
 
 /* One detector channel: an optical train ending in an image.  Several channels can share one bundle of
@@ -208,7 +217,13 @@ typedef struct sp_stats {
     uint64_t rhs_evals;      /* right-hand-side evaluations (RK4: 4 per step; RK45: those that touched the field) */
 } sp_stats;
 
-typedef struct sp_workspace sp_workspace; /* opaque scratch (sort keys, joint-mode stage buffers) reused across calls */
+/* Opaque scratch reused across calls: bundle dispenser, sort keys / order / histogram, joint-mode stage buffers, the
+ * pinned pair the joint controller reads, and the timing events.  ONE STREAM PER WORKSPACE: everything sp_propagate
+ * enqueues through a workspace assumes the launches before it on that workspace have been ordered by the same
+ * stream (the dispenser is reset with a memset, scratch may be re-allocated).  Callers that propagate on several
+ * streams or threads of one device create one workspace per stream (synthpy_b200/engine.py keys them by
+ * (device, stream)). */
+typedef struct sp_workspace sp_workspace;
 int sp_workspace_create(sp_workspace** out);
 int sp_workspace_destroy(sp_workspace* ws);
 

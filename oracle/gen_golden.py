@@ -116,6 +116,47 @@ def fresnel_fixture():
     np.savez_compressed(os.path.join(OUT, "g7_fresnel.npz"), **g)
 
 
+def minimal_fixture():
+    """G8: the 6-component generation of the solver (src/solvers-legacy/minimal_solver.py): float64 axes and gradients,
+    ne_max clamp, RMS error norm over 6N components, its own integration span.  Axes are dyadic (exact in float32) so
+    that the only representation difference to the float32 field layout is the rounding of the gradient values."""
+    sys.path.insert(0, os.path.join(REF, "solvers-legacy"))
+    import minimal_solver as ms
+    from scipy.integrate import solve_ivp
+    n = 33
+    x = (np.arange(n) - n // 2) * 2.0 ** -13           # +-1.95 mm, spacing 0.122 mm
+    y = (np.arange(n) - n // 2) * 2.0 ** -13
+    z = (np.arange(n) - n // 2) * 2.0 ** -12           # +-3.9 mm
+    g = dict(x=x, y=y, z=z, lwl=1064e-9, ne_max=0.02)
+    for tag, make in (("lens", lambda d: d.test_lens(n_e0=3e25, LR=8e-4)),):
+        dom = ms.ScalarDomain(x, y, z, "z")
+        make(dom)
+        g[tag + "_ne"] = dom.ne.copy()
+        dom.calc_dndr(lwl=g["lwl"], ne_max=g["ne_max"])      # clamps ne_nc in place (and therefore dom.ne / nc)
+        np.random.seed(12)
+        quiet(dom.init_beam, 96, 1.5e-3, 1e-4)
+        g[tag + "_s0"] = dom.s0.copy()
+        rf = quiet(dom.solve)
+        g[tag + "_sf"], g[tag + "_rf"] = dom.sf.copy(), rf
+        g[tag + "_t_end"] = np.sqrt(dom.extent_x ** 2 + dom.extent_y ** 2 * dom.extent_z ** 2) / ms.c     # minimal_solver.py:321
+        sol = solve_ivp(lambda t, yv: ms.dsdt(t, yv, dom), [0, g[tag + "_t_end"]], dom.s0.flatten(), t_eval=[0, g[tag + "_t_end"]])
+        assert np.array_equal(sol.y[:, -1].reshape(6, -1), dom.sf)
+        g[tag + "_nfev"] = sol.nfev
+        g[tag + "_dndx"], g[tag + "_dndy"], g[tag + "_dndz"] = dom.dndx, dom.dndy, dom.dndz
+        probe = np.concatenate([dom.s0, dom.sf], axis=1)
+        g[tag + "_probe"] = probe
+        g[tag + "_dsdt"] = ms.dsdt(0.0, probe.flatten(), dom).reshape(6, -1)
+    np.savez_compressed(os.path.join(OUT, "g8_minimal.npz"), **g)
+
+
+def reference_fixture():
+    """The one binary fixture the reference itself holds: evaluation/sergio_testing/integratedPy.npy = ne.sum(axis=2) of
+    test_linear_cos(s1=-1, s2=1, n_e0=1e26, Ly=5e-3) on the 100 x 1000 x 100 grid of sergio_testing/notebook.ipynb cells
+    7-8.  Copied byte for byte next to the grid parameters that produced it."""
+    import shutil
+    shutil.copyfile("/root/reference/evaluation/sergio_testing/integratedPy.npy", os.path.join(OUT, "integratedPy.npy"))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     fs, rtm, g3 = import_reference()
@@ -311,6 +352,8 @@ def main():
     kat["linear_cos_integrated"] = dom.ne.sum(axis=2)
     np.savez_compressed(os.path.join(OUT, "g5_kat.npz"), axis=a, extent=ext, **kat)
 
+    minimal_fixture()
+    reference_fixture()
     fresnel_fixture()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)) // 1024, "KiB")
@@ -319,5 +362,8 @@ def main():
 if __name__ == "__main__":
     if sys.argv[1:] == ["fresnel"]:
         fresnel_fixture()
+    elif sys.argv[1:] == ["minimal"]:
+        minimal_fixture()
+        reference_fixture()
     else:
         main()

@@ -198,6 +198,52 @@ class Domain:
         return s, steps
 
 
+class MinimalDomain:
+    """Restates ``minimal_solver.ScalarDomain`` (src/solvers-legacy/minimal_solver.py:121-398), the 6-component
+    generation of the solver: float64 axes, float64 normalised density clamped at ``ne_max`` critical densities
+    (:231), float64 gradients, state [x, y, z, vx, vy, vz], RMS error norm over 6N components, and its own
+    integration span sqrt(ex^2 + ey^2 ez^2) / c (:321, as written upstream)."""
+
+    def __init__(self, x, y, z, probing_direction="z"):
+        self.x, self.y, self.z = (np.asarray(a, dtype=np.float64) for a in (x, y, z))
+        self.extent_x, self.extent_y, self.extent_z = self.x.max(), self.y.max(), self.z.max()
+        self.probing_direction = probing_direction
+        self.extent = {"x": self.extent_x, "y": self.extent_y, "z": self.extent_z}[probing_direction]
+
+    def external_ne(self, ne):
+        self.ne = np.array(ne, dtype=np.float64, copy=True)
+
+    def calc_dndr(self, lwl=1053e-9, ne_max=1):                      # minimal_solver.py:222-243
+        self.omega = 2 * np.pi * (C_LIGHT / lwl)
+        nc = NC_COEFF * self.omega ** 2
+        ne_nc = self.ne / nc
+        ne_nc[ne_nc > ne_max] = ne_max
+        axes = (self.x, self.y, self.z)
+        self.grads = [-0.5 * C_LIGHT ** 2 * np.gradient(ne_nc, axes[a], axis=a) for a in range(3)]
+        self.grad_interp = [RegularGridInterpolator(axes, g, bounds_error=False, fill_value=0.0) for g in self.grads]
+
+    def dsdt(self, t, s):                                           # minimal_solver.py:506-527
+        s = s.reshape(6, -1)
+        out = np.zeros_like(s)
+        out[3:6] = np.stack([f(s[:3].T) for f in self.grad_interp])
+        out[:3] = s[3:6]
+        return out.ravel()
+
+    def t_end(self):
+        return np.sqrt(self.extent_x ** 2 + self.extent_y ** 2 * self.extent_z ** 2) / C_LIGHT      # minimal_solver.py:321
+
+    def solve(self, s0):                                            # minimal_solver.py:316-335
+        t = np.linspace(0.0, self.t_end(), 2)
+        sol = solve_ivp(self.dsdt, [0, t[-1]], np.asarray(s0, dtype=np.float64).ravel(), t_eval=t, method="RK45")
+        self.sf, self.nfev = sol.y[:, -1].reshape(6, -1), sol.nfev
+        return self.ray_at_exit()
+
+    def ray_at_exit(self):                                          # minimal_solver.py:337-384
+        s9 = np.zeros((9, self.sf.shape[1]))
+        s9[:6] = self.sf
+        return ray_to_jones(s9, self.extent, self.probing_direction)[0]
+
+
 def init_beam(Np, beam_size, divergence, ne_extent, beam_type="circular", probing_direction="z", rng=None):
     """Restates ``full_solver.init_beam`` (full_solver.py:547-835): legacy radial law u = fold(U+U).
     Draw order (t, u1, u2, phi, chi) is the reference's so ``np.random.seed(k)`` reproduces its rays;

@@ -54,7 +54,24 @@ class Beam:
             phi = np.pi * random_array(Np)                # NOT seeded upstream (beam.py:76)
             chi = div * random_array_n(Np, seeded)
             a, b = bs * u * np.cos(t), bs * u * np.sin(t)
-        elif bt in ("square", "rectangular"):             # beam.py:108-115, 150-162
+        elif bt == "even":
+            # beam.py:210-227: concentric rings of 6 i points, i = 1..n_c, plus the centre.  Upstream builds the (u, t)
+            # lists but never writes them into s0 (and its float ring count cannot drive range()), so there is nothing
+            # to pin: here the rings are placed as that code intends (radius i/n_c, angle 2 pi j / (6 i)) and the
+            # velocities come from the same chi / phi draws as the other types.  Np becomes 3 n_c (n_c + 1) + 1.
+            n_c = int((-1 + np.sqrt(1 + 8 * (Np // 6))) / 2)
+            Np = self.Np = 3 * (n_c + 1) * n_c + 1
+            s0 = np.zeros((9, Np))
+            phi = np.pi * random_array(Np, seeded)
+            chi = div * random_array_n(Np, seeded)
+            u, t = [0.0], [0.0]
+            for i in range(1, n_c + 1):
+                for j in range(6 * i):
+                    u.append(i / n_c)
+                    t.append(j * 2 * np.pi / (i * 6))
+            u, t = np.array(u), np.array(t)
+            a, b = bs * u * np.cos(t), bs * u * np.sin(t)
+        elif bt in ("square", "rectangular", "rect_trackers"):   # beam.py:108-115, 150-162, 228-286 (rect_trackers == rectangular)
             t = 2 * random_array(Np, seeded) - 1.0
             u = 2 * random_array(Np, seeded) - 1.0
             phi = np.pi * random_array(Np, seeded)
@@ -70,7 +87,7 @@ class Beam:
             self.s0 = s0
             return
         else:
-            raise ValueError("beam_type unrecognised! Accepted args: circular, square, rectangular, linear")
+            raise ValueError("beam_type unrecognised! Accepted args: circular, square, rectangular, rect_trackers, linear, even")
         para, p1, p2 = c * np.cos(chi), c * np.sin(chi) * np.cos(phi), c * np.sin(chi) * np.sin(phi)
         if pd == "x":
             s0[3], s0[4], s0[5] = para, p1, p2

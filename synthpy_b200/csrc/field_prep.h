@@ -130,6 +130,21 @@ SP_HD long long unpack_index(long long t, const PackArgs& P, int ic[3]) {
     return ((long long)ic[0] * P.n[1] + ic[1]) * P.n[2] + ic[2];
 }
 
+// Where packed cell t (kernel frame, w fastest) lives inside the float4 array: t itself in the row layout, its slot in
+// the 8 x 8 x 8 brick grid in the A/B layout (-DSP_BRICK).
+SP_HD long long packed_slot(long long t, const PackArgs& P) {
+#ifdef SP_BRICK
+    const int iw = (int)(t % P.nk[2]);
+    const long long r = t / P.nk[2];
+    const int iv = (int)(r % P.nk[1]), iu = (int)(r / P.nk[1]);
+    const long long nbv = (P.nk[1] + 7) >> 3, nbw = (P.nk[2] + 7) >> 3;
+    return (((long long)(iu >> 3) * nbv + (iv >> 3)) * nbw + (iw >> 3)) * 512 + ((iu & 7) << 6) + ((iv & 7) << 3) + (iw & 7);
+#else
+    (void)P;
+    return t;
+#endif
+}
+
 // n - 1 with n = sqrt(1 - (5.64e4 sqrt(ne 1e-6) / omega)^2)      (full_solver.py:236-239,270-274)
 SP_HD double refr_minus_one(double ne, double omega) {
     const double ope = mul_rn(5.64e4, sqrt(mul_rn(ne, 1e-6)));

@@ -207,7 +207,23 @@ template <typename T> struct FieldView {
     AxisTab<T> ax[3];
     long long su;         // element stride of u  (= nv*nw)
     int sv;               // element stride of v  (= nw)
+#ifdef SP_BRICK
+    long long bsu;        // A/B layout (-DSP_BRICK): `data` in 8 x 8 x 8 bricks of float4 (8 KB, w fastest inside a brick);
+    long long bsv;        // element strides between bricks along u and v (bricks along w are 512 elements apart)
+#endif
 };
+
+// Element offsets of grid index i along u / v / w inside `data`: the offset of node (iu, iv, iw) is their sum in both
+// layouts, so the eight corners of a cell are the sums of two offsets per axis.
+#ifdef SP_BRICK
+template <typename T> SP_HD long long off_u(const FieldView<T>& F, int i) { return (long long)(i >> 3) * F.bsu + ((i & 7) << 6); }
+template <typename T> SP_HD long long off_v(const FieldView<T>& F, int i) { return (long long)(i >> 3) * F.bsv + ((i & 7) << 3); }
+template <typename T> SP_HD long long off_w(const FieldView<T>&, int i) { return ((long long)(i >> 3) << 9) + (i & 7); }
+#else
+template <typename T> SP_HD long long off_u(const FieldView<T>& F, int i) { return (long long)i * F.su; }
+template <typename T> SP_HD long long off_v(const FieldView<T>& F, int i) { return (long long)i * F.sv; }
+template <typename T> SP_HD long long off_w(const FieldView<T>&, int i) { return i; }
+#endif
 
 // Cell index i with g[i] <= x < g[i+1] (clipped to [0, n-2]; x == g[n-1] -> n-2); false when x is outside
 // [g[0], g[n-1]] (the fill value applies).  NaN is "in bounds" (cell 0, NaN weight later), as in scipy
@@ -249,9 +265,6 @@ template <typename T, bool PHASE> struct CellCache {
     }
 };
 
-// Move the cached interval of one axis to the cell containing x.  `w_ok` = the weight test already placed x
-// in the cached cell.  Common case: the neighbouring cell (two table reads, exact comparisons); anything else
-// falls back to the exact search.  False = x is outside the grid.
 // locate() plus the cell's (g[i], 1/(g[i+1]-g[i])): the table entry of the uniform first guess and the next node are
 // requested together and, when the guess is right (the rule on float32-rounded linspace axes), nothing else is read.
 template <typename T> SP_HD bool locate_cell(const AxisTab<T>& A, T x, int& i, T& lo, T& rinv) {
@@ -334,11 +347,21 @@ SP_HD bool rhs(const FieldView<T>& F, CellCache<T, PHASE>& cc, T pu, T pv, T pw,
         SP_ASSERT(cc.idx[0] >= 0 && cc.idx[0] <= F.ax[0].n - 2 && cc.idx[1] >= 0 && cc.idx[1] <= F.ax[1].n - 2 &&
                   cc.idx[2] >= 0 && cc.idx[2] <= F.ax[2].n - 2);
         const long long base = (long long)cc.idx[0] * F.su + (long long)cc.idx[1] * F.sv + cc.idx[2];
+#ifdef SP_BRICK
+        const long long u0 = off_u(F, cc.idx[0]), u1 = off_u(F, cc.idx[0] + 1), v0 = off_v(F, cc.idx[1]), v1 = off_v(F, cc.idx[1] + 1);
+        const long long w0 = off_w(F, cc.idx[2]), w1 = off_w(F, cc.idx[2] + 1);
+        const f4* p = F.data;
+        const f4 c000 = ldg(p + u0 + v0 + w0), c001 = ldg(p + u0 + v0 + w1);
+        const f4 c010 = ldg(p + u0 + v1 + w0), c011 = ldg(p + u0 + v1 + w1);
+        const f4 c100 = ldg(p + u1 + v0 + w0), c101 = ldg(p + u1 + v0 + w1);
+        const f4 c110 = ldg(p + u1 + v1 + w0), c111 = ldg(p + u1 + v1 + w1);
+#else
         const f4* p = F.data + base;
         const f4 c000 = ldg(p), c001 = ldg(p + 1);
         const f4 c010 = ldg(p + F.sv), c011 = ldg(p + F.sv + 1);
         const f4 c100 = ldg(p + F.su), c101 = ldg(p + F.su + 1);
         const f4 c110 = ldg(p + F.su + F.sv), c111 = ldg(p + F.su + F.sv + 1);
+#endif
         tri_coef<T>(cvt<T>(c000.x), cvt<T>(c001.x), cvt<T>(c010.x), cvt<T>(c011.x), cvt<T>(c100.x), cvt<T>(c101.x), cvt<T>(c110.x), cvt<T>(c111.x), cc.a[0]);
         tri_coef<T>(cvt<T>(c000.y), cvt<T>(c001.y), cvt<T>(c010.y), cvt<T>(c011.y), cvt<T>(c100.y), cvt<T>(c101.y), cvt<T>(c110.y), cvt<T>(c111.y), cc.a[1]);
         tri_coef<T>(cvt<T>(c000.z), cvt<T>(c001.z), cvt<T>(c010.z), cvt<T>(c011.z), cvt<T>(c100.z), cvt<T>(c101.z), cvt<T>(c110.z), cvt<T>(c111.z), cc.a[2]);
@@ -358,6 +381,81 @@ SP_HD bool rhs(const FieldView<T>& F, CellCache<T, PHASE>& cc, T pu, T pv, T pw,
     av = tri_eval<T>(cc.a[1], wu, wv, ww);
     aw = tri_eval<T>(cc.a[2], wu, wv, ww);
     nm1 = PHASE ? tri_eval<T>(cc.a[PHASE ? 3 : 0], wu, wv, ww) : (T)0;
+    return true;
+}
+
+// The same interpolation WITHOUT a cell cache, for the adaptive integrators: a Dormand-Prince step at SciPy's default
+// tolerances spans ~1.7 cells of the benchmarked grids, so consecutive evaluations land in different cells, the cache
+// misses on nearly every call and its upkeep (hit test, neighbour probe, face bookkeeping, ~50 live registers) is pure
+// overhead -- round 1's adaptive kernel spent ~3600 warp-instructions per attempted step at 18 of 32 lanes, with 900
+// bytes of spills.  Here every evaluation runs the identical straight-line sequence (bounds test, exact cell search on
+// the axis tables, eight 16-byte corner reads, the reference's sum over corners of value x weight product), so the
+// lanes of a warp stay converged whatever cells they are in.
+// Uniform first guess of the cell index (clipped to [0, n-2]); right on float32-rounded linspace axes except within
+// rounding of a node, and always checked against the table entries it points at.
+template <typename T> SP_HD int guess_cell(const AxisTab<T>& A, T x) {
+    const int k = floor_to_int((x - A.g0) * A.inv_d);
+    return k < 0 ? 0 : (k > A.n - 2 ? A.n - 2 : k);
+}
+// locate()'s acceptance of cell k given its table entry: g[k] <= x < g[k+1], open at the clipped ends, NaN accepted.
+template <typename T> SP_HD bool cell_holds(const AxisTab<T>& A, T x, int k, T g_k, T g_k1) {
+    return !(x == x) || ((k == 0 || x >= g_k) && (k == A.n - 2 || x < g_k1));
+}
+
+template <typename T, bool PHASE, bool AUX64>
+SP_HD bool rhs_direct(const FieldView<T>& F, T pu, T pv, T pw, T& au, T& av, T& aw, T& nm1) {
+    au = av = aw = nm1 = (T)0;
+    if (pu < F.ax[0].lo || pu > F.ax[0].hi || pv < F.ax[1].lo || pv > F.ax[1].hi || pw < F.ax[2].lo || pw > F.ax[2].hi) return false;
+    // The three table entries AND the eight corners of the guessed cell are requested together -- one memory round trip
+    // per evaluation instead of two dependent ones (table -> index -> corners); the guess is then verified exactly and,
+    // in the rare case it is a node off, the search result goes through the same (single) copy of the loads once more.
+    int iu = guess_cell(F.ax[0], pu), iv = guess_cell(F.ax[1], pv), iw = guess_cell(F.ax[2], pw);
+    typename Pair<T>::type eu, ev, ew;
+    f4 c000, c001, c010, c011, c100, c101, c110, c111;
+    long long base = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int pass = 0;; ++pass) {
+        SP_ASSERT(iu >= 0 && iu <= F.ax[0].n - 2 && iv >= 0 && iv <= F.ax[1].n - 2 && iw >= 0 && iw <= F.ax[2].n - 2);
+        eu = ldg(F.ax[0].tab + iu); ev = ldg(F.ax[1].tab + iv); ew = ldg(F.ax[2].tab + iw);
+        const T gu1 = ldg_now(&(F.ax[0].tab + iu + 1)->x), gv1 = ldg_now(&(F.ax[1].tab + iv + 1)->x), gw1 = ldg_now(&(F.ax[2].tab + iw + 1)->x);
+        base = (long long)iu * F.su + (long long)iv * F.sv + iw;
+#ifdef SP_BRICK
+        const long long u0 = off_u(F, iu), u1 = off_u(F, iu + 1), v0 = off_v(F, iv), v1 = off_v(F, iv + 1), w0 = off_w(F, iw), w1 = off_w(F, iw + 1);
+        const f4* p = F.data;
+        c000 = ldg(p + u0 + v0 + w0); c001 = ldg(p + u0 + v0 + w1); c010 = ldg(p + u0 + v1 + w0); c011 = ldg(p + u0 + v1 + w1);
+        c100 = ldg(p + u1 + v0 + w0); c101 = ldg(p + u1 + v0 + w1); c110 = ldg(p + u1 + v1 + w0); c111 = ldg(p + u1 + v1 + w1);
+#else
+        const f4* p = F.data + base;
+        c000 = ldg(p); c001 = ldg(p + 1); c010 = ldg(p + F.sv); c011 = ldg(p + F.sv + 1);
+        c100 = ldg(p + F.su); c101 = ldg(p + F.su + 1); c110 = ldg(p + F.su + F.sv); c111 = ldg(p + F.su + F.sv + 1);
+#endif
+        if (pass || (cell_holds(F.ax[0], pu, iu, eu.x, gu1) && cell_holds(F.ax[1], pv, iv, ev.x, gv1) && cell_holds(F.ax[2], pw, iw, ew.x, gw1)))
+            break;
+        T l, r;                                              // exact search; its answer is final
+        locate_cell(F.ax[0], pu, iu, l, r); locate_cell(F.ax[1], pv, iv, l, r); locate_cell(F.ax[2], pw, iw, l, r);
+    }
+    const T lu = eu.x, ru = eu.y, lv = ev.x, rv = ev.y, lw = ew.x, rw = ew.y;
+    const T wu = (pu - lu) * ru, wv = (pv - lv) * rv, ww = (pw - lw) * rw;
+    const T mu = (T)1 - wu, mv = (T)1 - wv, mw = (T)1 - ww;
+    const T k00 = mu * mv, k01 = mu * wv, k10 = wu * mv, k11 = wu * wv;
+    const T k000 = k00 * mw, k001 = k00 * ww, k010 = k01 * mw, k011 = k01 * ww;
+    const T k100 = k10 * mw, k101 = k10 * ww, k110 = k11 * mw, k111 = k11 * ww;
+#define SP_TRI(m) sp_fma(cvt<T>(c111.m), k111, sp_fma(cvt<T>(c110.m), k110, sp_fma(cvt<T>(c101.m), k101, sp_fma(cvt<T>(c100.m), k100, \
+                  sp_fma(cvt<T>(c011.m), k011, sp_fma(cvt<T>(c010.m), k010, sp_fma(cvt<T>(c001.m), k001, cvt<T>(c000.m) * k000)))))))
+    au = SP_TRI(x); av = SP_TRI(y); aw = SP_TRI(z);
+    if (PHASE) {
+        if (AUX64) {
+            const double* q = F.aux64 + base;
+            nm1 = sp_fma((T)ldg(q + F.su + F.sv + 1), k111, sp_fma((T)ldg(q + F.su + F.sv), k110, sp_fma((T)ldg(q + F.su + 1), k101,
+                  sp_fma((T)ldg(q + F.su), k100, sp_fma((T)ldg(q + F.sv + 1), k011, sp_fma((T)ldg(q + F.sv), k010,
+                  sp_fma((T)ldg(q + 1), k001, (T)ldg(q) * k000)))))));
+        } else {
+            nm1 = SP_TRI(w);
+        }
+    }
+#undef SP_TRI
     return true;
 }
 
@@ -542,6 +640,15 @@ SP_HD int deriv(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega, const T
     return t;
 }
 
+template <typename T, bool PHASE, bool AUX64>
+SP_HD int deriv_direct(const FieldView<T>& F, T omega, const T* p, const T* v, Deriv<T>& k) {
+    T nm1;
+    int t = rhs_direct<T, PHASE, AUX64>(F, p[0], p[1], p[2], k.dv[0], k.dv[1], k.dv[2], nm1);
+    k.dp[0] = v[0]; k.dp[1] = v[1]; k.dp[2] = v[2];
+    k.dph = PHASE ? omega * nm1 : (T)0;
+    return t;
+}
+
 // One attempted DP5 step of size h from (r, k1 = f(r)).  Outputs the 5th-order state, f(new state) (FSAL)
 // and sum over the live components of (err_i / scale_i)^2 with scale = atol + rtol max(|y|, |y_new|)
 // (rk.py:_step_impl).  amp (|y| = amp0) and pol contribute zero error.
@@ -571,17 +678,37 @@ struct DPN {
                             E5 = DP::e6 * DP::a65 + DP::e7 * DP::b5, E6 = DP::e7 * DP::b6;
 };
 
-template <typename T, bool PHASE, bool AUX64>
-SP_HD int dp5_attempt(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega, T h, T rtol, T atol, const Ray<T>& r, const Deriv<T>& k1,
-                      Ray<T>& rn, Deriv<T>& k7, T& err_sq) {
-    T K2[3] = {0, 0, 0}, K3[3] = {0, 0, 0}, K4[3] = {0, 0, 0}, K5[3] = {0, 0, 0}, K6[3] = {0, 0, 0};
-    T n3 = (T)0, n4 = (T)0, n5 = (T)0, n6 = (T)0, n7 = (T)0;
+// Where the stage derivatives K2..K6 (velocity rows) and the stage values n3..n6 wait between the six evaluations of an
+// attempt.  StageRegs: local arrays that the compiler keeps in registers (every index is a compile-time constant) -- the
+// joint kernels and the CPU self-test.  StageSmem: a per-thread column of shared memory; the per-ray / per-bundle
+// adaptive kernels are latency-bound at 3 resident CTAs per SM (168 registers, ncu: issue active 38 %), and these 19
+// doubles are the largest block of state that is only touched between evaluations.
+template <typename T> struct StageRegs {
+    T k[5][3], n[4];
+    SP_HD T K(int j, int c) const { return k[j][c]; }
+    SP_HD void setK(int j, int c, T v) { k[j][c] = v; }
+    SP_HD T N(int j) const { return n[j]; }
+    SP_HD void setN(int j, T v) { n[j] = v; }
+};
+template <typename T> struct StageSmem {
+    T* base; int stride;                                   // element (j, c) at base[(3 j + c) * stride]: conflict-free across a warp
+    SP_HD T K(int j, int c) const { return base[(3 * j + c) * stride]; }
+    SP_HD void setK(int j, int c, T v) { base[(3 * j + c) * stride] = v; }
+    SP_HD T N(int j) const { return base[(15 + j) * stride]; }
+    SP_HD void setN(int j, T v) { base[(15 + j) * stride] = v; }
+};
+#define SP_STAGE_DOUBLES 19
+
+template <typename T, bool PHASE, bool AUX64, typename Store>
+SP_HD int dp5_attempt(const FieldView<T>& F, T omega, T h, T rtol, T atol, const Ray<T>& r, const Deriv<T>& k1,
+                      Ray<T>& rn, Deriv<T>& k7, T& err_sq, Store& S) {
+    T n7 = (T)0;
     const T* K1 = k1.dv;
     const T h2 = h * h;
     int touched = 0;
-    // The six evaluations go through ONE copy of rhs() (a rolled loop with the stage-specific algebra in switch
-    // arms): with rhs() inlined six times the step loop was ~80 KB of SASS against a 32 KB instruction cache, and
-    // ncu showed `no_instruction` as the top stall (5 per issue).  Every index below is a compile-time constant,
+    // The six evaluations go through ONE copy of rhs_direct() (a rolled loop with the stage-specific algebra in switch
+    // arms): with the evaluation inlined six times the step loop was ~80 KB of SASS against a 32 KB instruction cache,
+    // and ncu showed `no_instruction` as the top stall (5 per issue).  Every index below is a compile-time constant,
     // so the stage vectors stay in registers; the arithmetic is unchanged.
 #define SP_POS(cs, expr) (r.p[c] + (T)(cs) * h * r.v[c] + h2 * (expr))
 #if defined(__CUDA_ARCH__)
@@ -600,38 +727,38 @@ SP_HD int dp5_attempt(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega, T
             break;
         case 4:
 #pragma unroll
-            for (int c = 0; c < 3; ++c) p[c] = SP_POS(DP::c4, (T)DPN::A41 * K1[c] + (T)DPN::A42 * K2[c]);
+            for (int c = 0; c < 3; ++c) p[c] = SP_POS(DP::c4, (T)DPN::A41 * K1[c] + (T)DPN::A42 * S.K(0, c));
             break;
         case 5:
 #pragma unroll
-            for (int c = 0; c < 3; ++c) p[c] = SP_POS(DP::c5, (T)DPN::A51 * K1[c] + (T)DPN::A52 * K2[c] + (T)DPN::A53 * K3[c]);
+            for (int c = 0; c < 3; ++c) p[c] = SP_POS(DP::c5, (T)DPN::A51 * K1[c] + (T)DPN::A52 * S.K(0, c) + (T)DPN::A53 * S.K(1, c));
             break;
         case 6:
 #pragma unroll
             for (int c = 0; c < 3; ++c)
-                p[c] = SP_POS(1.0, (T)DPN::A61 * K1[c] + (T)DPN::A62 * K2[c] + (T)DPN::A63 * K3[c] + (T)DPN::A64 * K4[c]);
+                p[c] = SP_POS(1.0, (T)DPN::A61 * K1[c] + (T)DPN::A62 * S.K(0, c) + (T)DPN::A63 * S.K(1, c) + (T)DPN::A64 * S.K(2, c));
             break;
         default:   // 7: y_new = y + h * (K[:-1].T @ B), then f(y_new) (FSAL)
 #pragma unroll
             for (int c = 0; c < 3; ++c) {
-                rn.p[c] = r.p[c] + h * r.v[c] + h2 * ((T)DPN::B1 * K1[c] + (T)DPN::B2 * K2[c] + (T)DPN::B3 * K3[c] + (T)DPN::B4 * K4[c] +
-                                                      (T)DPN::B5 * K5[c]);
-                rn.v[c] = r.v[c] + h * ((T)DP::b1 * K1[c] + (T)DP::b3 * K3[c] + (T)DP::b4 * K4[c] + (T)DP::b5 * K5[c] + (T)DP::b6 * K6[c]);
+                rn.p[c] = r.p[c] + h * r.v[c] + h2 * ((T)DPN::B1 * K1[c] + (T)DPN::B2 * S.K(0, c) + (T)DPN::B3 * S.K(1, c) + (T)DPN::B4 * S.K(2, c) +
+                                                      (T)DPN::B5 * S.K(3, c));
+                rn.v[c] = r.v[c] + h * ((T)DP::b1 * K1[c] + (T)DP::b3 * S.K(1, c) + (T)DP::b4 * S.K(2, c) + (T)DP::b5 * S.K(3, c) + (T)DP::b6 * S.K(4, c));
                 p[c] = rn.p[c];
             }
             rn.ph = r.ph;
             if (PHASE)
-                rn.ph = r.ph + h * ((T)DP::b1 * k1.dph + omega * ((T)DP::b3 * n3 + (T)DP::b4 * n4 + (T)DP::b5 * n5 + (T)DP::b6 * n6));
+                rn.ph = r.ph + h * ((T)DP::b1 * k1.dph + omega * ((T)DP::b3 * S.N(0) + (T)DP::b4 * S.N(1) + (T)DP::b5 * S.N(2) + (T)DP::b6 * S.N(3)));
             break;
         }
         T a0, a1, a2, nn;
-        touched += rhs<T, PHASE, AUX64, false>(F, cc, p[0], p[1], p[2], a0, a1, a2, nn);
+        touched += rhs_direct<T, PHASE, AUX64>(F, p[0], p[1], p[2], a0, a1, a2, nn);
         switch (s) {
-        case 2: K2[0] = a0; K2[1] = a1; K2[2] = a2; break;
-        case 3: K3[0] = a0; K3[1] = a1; K3[2] = a2; n3 = nn; break;
-        case 4: K4[0] = a0; K4[1] = a1; K4[2] = a2; n4 = nn; break;
-        case 5: K5[0] = a0; K5[1] = a1; K5[2] = a2; n5 = nn; break;
-        case 6: K6[0] = a0; K6[1] = a1; K6[2] = a2; n6 = nn; break;
+        case 2: S.setK(0, 0, a0); S.setK(0, 1, a1); S.setK(0, 2, a2); break;
+        case 3: S.setK(1, 0, a0); S.setK(1, 1, a1); S.setK(1, 2, a2); if (PHASE) S.setN(0, nn); break;
+        case 4: S.setK(2, 0, a0); S.setK(2, 1, a1); S.setK(2, 2, a2); if (PHASE) S.setN(1, nn); break;
+        case 5: S.setK(3, 0, a0); S.setK(3, 1, a1); S.setK(3, 2, a2); if (PHASE) S.setN(2, nn); break;
+        case 6: S.setK(4, 0, a0); S.setK(4, 1, a1); S.setK(4, 2, a2); if (PHASE) S.setN(3, nn); break;
         default: k7.dv[0] = a0; k7.dv[1] = a1; k7.dv[2] = a2; n7 = nn; break;
         }
     }
@@ -644,21 +771,35 @@ SP_HD int dp5_attempt(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega, T
 #define SP_SCALE(y0, y1) (atol + (fabs(y0) > fabs(y1) ? fabs(y0) : fabs(y1)) * rtol)
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const T ep = h2 * ((T)DPN::E1 * K1[c] + (T)DPN::E2 * K2[c] + (T)DPN::E3 * K3[c] + (T)DPN::E4 * K4[c] + (T)DPN::E5 * K5[c] +
-                           (T)DPN::E6 * K6[c]);
-        const T ev = h * ((T)DP::e1 * K1[c] + (T)DP::e3 * K3[c] + (T)DP::e4 * K4[c] + (T)DP::e5 * K5[c] + (T)DP::e6 * K6[c] +
+        const T ep = h2 * ((T)DPN::E1 * K1[c] + (T)DPN::E2 * S.K(0, c) + (T)DPN::E3 * S.K(1, c) + (T)DPN::E4 * S.K(2, c) + (T)DPN::E5 * S.K(3, c) +
+                           (T)DPN::E6 * S.K(4, c));
+        const T ev = h * ((T)DP::e1 * K1[c] + (T)DP::e3 * S.K(1, c) + (T)DP::e4 * S.K(2, c) + (T)DP::e5 * S.K(3, c) + (T)DP::e6 * S.K(4, c) +
                           (T)DP::e7 * k7.dv[c]);
         const T qp = ep / SP_SCALE(r.p[c], rn.p[c]), qv = ev / SP_SCALE(r.v[c], rn.v[c]);
         acc += qp * qp + qv * qv;
     }
     if (PHASE) {
-        const T e = h * ((T)DP::e1 * k1.dph + omega * ((T)DP::e3 * n3 + (T)DP::e4 * n4 + (T)DP::e5 * n5 + (T)DP::e6 * n6 + (T)DP::e7 * n7));
+        const T e = h * ((T)DP::e1 * k1.dph + omega * ((T)DP::e3 * S.N(0) + (T)DP::e4 * S.N(1) + (T)DP::e5 * S.N(2) + (T)DP::e6 * S.N(3) + (T)DP::e7 * n7));
         const T q = e / SP_SCALE(r.ph, rn.ph);
         acc += q * q;
     }
 #undef SP_SCALE
     err_sq = acc;
     return touched;
+}
+
+// the register-resident form (joint kernels, CPU self-test)
+template <typename T, bool PHASE, bool AUX64>
+SP_HD int dp5_attempt(const FieldView<T>& F, T omega, T h, T rtol, T atol, const Ray<T>& r, const Deriv<T>& k1,
+                      Ray<T>& rn, Deriv<T>& k7, T& err_sq) {
+    StageRegs<T> S;
+#pragma unroll
+    for (int j = 0; j < 5; ++j)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) S.k[j][c] = (T)0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) S.n[j] = (T)0;
+    return dp5_attempt<T, PHASE, AUX64, StageRegs<T> >(F, omega, h, rtol, atol, r, k1, rn, k7, err_sq, S);
 }
 
 // Step-size factor after an attempt with RMS error norm `en` (rk.py:_step_impl).
@@ -674,7 +815,7 @@ template <typename T> SP_HD T dp5_factor(T en, bool accepted, bool rejected_befo
 // Hairer's initial step as coded in scipy/integrate/_ivp/common.py::select_initial_step (order = 4), with
 // the RMS norms taken over the ray's own n_state components (amp contributes (amp/scale)^2 to d0 only).
 template <typename T, bool PHASE, bool AUX64>
-SP_HD T dp5_initial_step(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega, T t_end, T rtol, T atol, int n_state, T amp, T pol,
+SP_HD T dp5_initial_step(const FieldView<T>& F, T omega, T t_end, T rtol, T atol, int n_state, T amp, T pol,
                          const Ray<T>& r, const Deriv<T>& f0, int& touched) {
     if (t_end == (T)0) return (T)0;
     const T inv_n = (T)1 / (T)n_state;
@@ -702,7 +843,7 @@ SP_HD T dp5_initial_step(const FieldView<T>& F, CellCache<T, PHASE>& cc, T omega
 #pragma unroll
     for (int c = 0; c < 3; ++c) { p1[c] = r.p[c] + h0 * f0.dp[c]; v1[c] = r.v[c] + h0 * f0.dv[c]; }
     Deriv<T> f1;
-    touched += deriv<T, PHASE, AUX64>(F, cc, omega, p1, v1, f1);
+    touched += deriv_direct<T, PHASE, AUX64>(F, omega, p1, v1, f1);
     T s2 = (T)0;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {

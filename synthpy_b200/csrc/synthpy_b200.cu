@@ -2,7 +2,7 @@
 //
 // Kernels (all hand-written for sm_100a; no library calls on the data path):
 //   k_normalise_ne / k_pack_from_ne / k_pack_from_grads : field preparation (float32 stencil == np.gradient)
-//   k_sort_keys / k_scan / k_sort_scatter               : counting sort of rays into coherent bundles
+//   k_sort_keys / k_scan_* / k_sort_scatter             : counting sort of rays into coherent bundles
 //   k_propagate<T, METHOD, PHASE, AUX64>                 : persistent ray integrator + fused optics/binning
 //   k_joint_*                                           : the reference's joint-step RK45 (one h for all rays)
 //   k_optics_image / k_finalize / k_rhs / k_beam        : stand-alone entry points
@@ -68,6 +68,9 @@ template <> FieldView<double> make_view<double>(const sp_field* f) {
         V.ax[k].lo = f->lo[k]; V.ax[k].hi = f->hi[k]; V.ax[k].n = f->nk[k];
     }
     V.su = (long long)f->nk[1] * f->nk[2]; V.sv = f->nk[2];
+#ifdef SP_BRICK
+    V.bsv = (long long)((f->nk[2] + 7) >> 3) * 512; V.bsu = (long long)((f->nk[1] + 7) >> 3) * V.bsv;
+#endif
     return V;
 }
 template <> FieldView<float> make_view<float>(const sp_field* f) {
@@ -78,6 +81,9 @@ template <> FieldView<float> make_view<float>(const sp_field* f) {
         V.ax[k].lo = (float)f->lo[k]; V.ax[k].hi = (float)f->hi[k]; V.ax[k].n = f->nk[k];
     }
     V.su = (long long)f->nk[1] * f->nk[2]; V.sv = f->nk[2];
+#ifdef SP_BRICK
+    V.bsv = (long long)((f->nk[2] + 7) >> 3) * 512; V.bsu = (long long)((f->nk[1] + 7) >> 3) * V.bsv;
+#endif
     return V;
 }
 
@@ -97,7 +103,7 @@ __global__ void k_pack_from_ne(const float* __restrict__ ne_nc, const NE* __rest
     const long long gstride = (long long)gridDim.x * blockDim.x;
     for (; t < total; t += gstride) {
         double nm1;
-        out[t] = pack_cell(t, ne_nc, ne, P, nm1);
+        out[packed_slot(t, P)] = pack_cell(t, ne_nc, ne, P, nm1);
         if (aux64) aux64[t] = nm1;
     }
 }
@@ -116,7 +122,7 @@ __global__ void k_pack_from_grads(const float* __restrict__ gx, const float* __r
         f4 v; v.x = g[P.perm[0]]; v.y = g[P.perm[1]]; v.z = g[P.perm[2]];
         v.w = aux32 ? aux32[idx] : (aux64_in ? (float)aux64_in[idx] : 0.f);
         if (aux64 && aux64_in) aux64[t] = aux64_in[idx];
-        out[t] = v;
+        out[packed_slot(t, P)] = v;
     }
 }
 
@@ -127,7 +133,7 @@ __global__ void k_export_grads(const f4* __restrict__ in, float* gx, float* gy, 
     for (; t < total; t += gstride) {
         int ic[3];
         const long long idx = unpack_index(t, P, ic);
-        const f4 v = in[t];
+        const f4 v = in[packed_slot(t, P)];
         float g[3];
         g[P.perm[0]] = v.x; g[P.perm[1]] = v.y; g[P.perm[2]] = v.z;
         if (gx) gx[idx] = g[0];
@@ -157,8 +163,13 @@ static int field_common(sp_field* f, const float* axh[3], int nx, int ny, int nz
         CU(cudaStreamSynchronize(st));   // host vectors go out of scope
         f->bytes += n * (sizeof(d2) + sizeof(f2));
     }
+#ifdef SP_BRICK
+    const size_t cells = (size_t)((f->nk[0] + 7) >> 3) * ((f->nk[1] + 7) >> 3) * ((f->nk[2] + 7) >> 3) * 512;    // padded to whole bricks
+#else
     const size_t cells = (size_t)nx * ny * nz;
+#endif
     CU(cudaMalloc(&f->data, cells * sizeof(f4)));
+    CU(cudaMemsetAsync(f->data, 0, cells * sizeof(f4), st));
     f->bytes += cells * sizeof(f4);
     return SP_OK;
 }
@@ -331,6 +342,7 @@ extern "C" int sp_field_export_gradients(const sp_field* f, float* gx_dev, float
 #endif
 #define SP_METHOD_RK4X 3      // internal: RK4 with the attenuation / Faraday channels (float64)
 #define SP_METHOD_RK45X 4     // internal: per-ray Dormand-Prince over all nine rows (channels on, float64)
+#define SP_METHOD_RK45B 5     // internal: Dormand-Prince with one step size per 32-ray bundle (SP_FLAG_BUNDLE_STEP)
 #define SP_MAX_OPS 16
 #define SP_MAX_CHANNELS 4
 
@@ -339,7 +351,7 @@ struct ChannelDev {
     int n_ops, kind, nx, ny, with_E, input_mm;
     double kwave, x_lo, x_hi, y_lo, y_hi;
     unsigned long long* counts;
-    double* planes;
+    long long* planes;
 };
 
 static int channel_to_dev(const sp_channel* c, ChannelDev& d) {
@@ -353,7 +365,7 @@ static int channel_to_dev(const sp_channel* c, ChannelDev& d) {
     d.n_ops = c->n_ops; d.input_mm = c->input_mm;
     d.kind = c->image.kind; d.nx = c->image.nx; d.ny = c->image.ny;
     d.x_lo = c->image.x_lo; d.x_hi = c->image.x_hi; d.y_lo = c->image.y_lo; d.y_hi = c->image.y_hi;
-    d.counts = (unsigned long long*)c->image.counts_dev; d.planes = c->image.planes_dev;
+    d.counts = (unsigned long long*)c->image.counts_dev; d.planes = (long long*)c->image.planes_dev;
     d.with_E = (c->image.kind == SP_IMG_INTERFEROGRAM);
     d.kwave = c->wavelength > 0 ? 2.0 * 3.14159265358979323846 / c->wavelength : 0.0;
     if (d.kind == SP_IMG_HISTOGRAM && !d.counts && d.nx > 0) return fail(SP_EINVAL, "histogram channel without counts buffer");
@@ -361,9 +373,16 @@ static int channel_to_dev(const sp_channel* c, ChannelDev& d) {
     return SP_OK;
 }
 
-// Detector binning of one ray.  Histogram counts are warp-aggregated: lanes that hit the same pixel elect
-// one leader which issues a single 64-bit atomic with the lane count (rays are bundled coherently, so
-// neighbouring lanes land in neighbouring pixels).  Returns 1 if binned.
+// Detector binning of one ray.  Lanes that hit the same pixel are aggregated in the warp: __match_any_sync groups
+// them, every lane of a group sums the group's contributions in lane order over shuffles, and the group's lowest lane
+// issues the atomics (rays are bundled coherently, so neighbouring lanes land in neighbouring pixels).
+// Histogram: one 64-bit count.  Interferogram: the four sums of complex E are accumulated in FIXED POINT (int64,
+// SP_PLANE_FRAC_BITS fractional bits): integer addition is associative, so an image does not depend on the order in
+// which warps, kernels, chunks or GPUs contribute -- run-to-run and partition-to-partition identical, like the
+// counts -- at a quantisation of 2^-40 per contribution (|E| <= amp + 1 ~ 2; range +-2^23 per pixel).
+// Returns 1 if binned.
+__device__ __forceinline__ long long to_plane_fixed(double v) { return __double2ll_rn(v * (double)(1ll << SP_PLANE_FRAC_BITS)); }
+
 __device__ __forceinline__ int bin_ray(const ChannelDev& ch, const DetRay& d, bool active) {
     int pix = -1;
     if (active && d.alive && ch.nx > 0) {
@@ -373,16 +392,30 @@ __device__ __forceinline__ int bin_ray(const ChannelDev& ch, const DetRay& d, bo
         if (ix >= 0 && iy >= 0) pix = iy * ch.nx + ix;
         SP_ASSERT(pix < ch.nx * ch.ny && ix < ch.nx && iy < ch.ny);
     }
+    const unsigned peers = __match_any_sync(__activemask(), pix);
+    const bool leader = pix >= 0 && (__ffs(peers) - 1) == (int)(threadIdx.x & 31);
     if (ch.kind == SP_IMG_HISTOGRAM) {
-        const unsigned peers = __match_any_sync(__activemask(), pix);
-        if (pix >= 0 && (__ffs(peers) - 1) == (int)(threadIdx.x & 31))
-            atomicAdd(ch.counts + pix, (unsigned long long)__popc(peers));
-    } else if (pix >= 0) {
-        const size_t plane = (size_t)ch.nx * ch.ny;
-        atomicAdd(ch.planes + pix, d.ex_re);
-        atomicAdd(ch.planes + plane + pix, d.ex_im);
-        atomicAdd(ch.planes + 2 * plane + pix, d.ey_re);
-        atomicAdd(ch.planes + 3 * plane + pix, d.ey_im);
+        if (leader) atomicAdd(ch.counts + pix, (unsigned long long)__popc(peers));
+    } else {
+        long long v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+        if (pix >= 0) { v0 = to_plane_fixed(d.ex_re); v1 = to_plane_fixed(d.ex_im); v2 = to_plane_fixed(d.ey_re); v3 = to_plane_fixed(d.ey_im); }
+        if (peers & (peers - 1)) {                       // more than one lane on this pixel (coarse images): sum the group
+            long long s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+            for (unsigned m = peers; m; m &= m - 1) {
+                const int src = __ffs(m) - 1;
+                s0 += __shfl_sync(peers, v0, src); s1 += __shfl_sync(peers, v1, src);
+                s2 += __shfl_sync(peers, v2, src); s3 += __shfl_sync(peers, v3, src);
+            }
+            v0 = s0; v1 = s1; v2 = s2; v3 = s3;
+        }
+        if (leader) {
+            const size_t plane = (size_t)ch.nx * ch.ny;
+            unsigned long long* p = (unsigned long long*)ch.planes + pix;
+            atomicAdd(p, (unsigned long long)v0);
+            atomicAdd(p + plane, (unsigned long long)v1);
+            atomicAdd(p + 2 * plane, (unsigned long long)v2);
+            atomicAdd(p + 3 * plane, (unsigned long long)v3);
+        }
     }
     return pix >= 0;
 }
@@ -434,22 +467,54 @@ __global__ void k_sort_keys(SortArgs A, uint32_t* __restrict__ keys, uint32_t* _
     atomicAdd(hist + key, 1u);
 }
 
-// Single-block exclusive scan (n_keys <= 4 Mi): each thread owns a contiguous slice.
-__global__ void k_scan(uint32_t* __restrict__ hist, uint32_t n) {
-    __shared__ uint32_t part[1024];
-    const uint32_t per = (n + blockDim.x - 1) / blockDim.x;
-    const uint32_t b = threadIdx.x * per, e = min(b + per, n);
-    uint32_t s = 0;
-    for (uint32_t i = b; i < e; ++i) s += hist[i];
-    part[threadIdx.x] = s;
+// Exclusive scan of the key histogram (n_keys <= 4 Mi) in three coalesced passes: every 1024-thread block scans a
+// tile of 4096 counts in place (16 bytes per thread, warp shuffles + one shared-memory hop) and publishes the tile
+// total; one block scans the <= 1024 totals; the tiles add their offset.  (Round 1 used one block whose threads each
+// walked a private 4096-element slice -- uncoalesced -- and a serial pass over 1024 partial sums in thread 0.)
+#define SP_SCAN_TILE 4096
+__device__ __forceinline__ uint32_t block_exclusive_scan_1024(uint32_t v, uint32_t* total) {
+    __shared__ uint32_t warp_sum[32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_sum[wid] = inc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t run = 0;
-        for (uint32_t i = 0; i < blockDim.x; ++i) { uint32_t v = part[i]; part[i] = run; run += v; }
+    if (wid == 0) {
+        uint32_t w = warp_sum[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o); if (lane >= o) wi += t; }
+        warp_sum[lane] = wi - w;                           // exclusive prefix of the warp totals
+        if (lane == 31 && total) *total = wi;
     }
     __syncthreads();
-    uint32_t run = part[threadIdx.x];
-    for (uint32_t i = b; i < e; ++i) { uint32_t v = hist[i]; hist[i] = run; run += v; }
+    return inc - v + warp_sum[wid];
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tiles(uint32_t* __restrict__ data, uint32_t n, uint32_t* __restrict__ tile_sums) {
+    const uint32_t i0 = blockIdx.x * SP_SCAN_TILE + threadIdx.x * 4;
+    uint32_t a[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) a[k] = (i0 + k < n) ? data[i0 + k] : 0u;
+    const uint32_t mine = a[0] + a[1] + a[2] + a[3];
+    __shared__ uint32_t tot;
+    uint32_t run = block_exclusive_scan_1024(mine, &tot);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { if (i0 + k < n) data[i0 + k] = run; run += a[k]; }
+    if (threadIdx.x == 0) tile_sums[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_tops(uint32_t* __restrict__ tile_sums, uint32_t n_tiles) {
+    const uint32_t v = threadIdx.x < n_tiles ? tile_sums[threadIdx.x] : 0u;
+    const uint32_t ex = block_exclusive_scan_1024(v, nullptr);
+    if (threadIdx.x < n_tiles) tile_sums[threadIdx.x] = ex;
+}
+
+__global__ void __launch_bounds__(1024) k_scan_add(uint32_t* __restrict__ data, uint32_t n, const uint32_t* __restrict__ tile_sums) {
+    const uint32_t off = tile_sums[blockIdx.x];
+    const uint32_t i0 = blockIdx.x * SP_SCAN_TILE + threadIdx.x * 4;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) if (i0 + k < n) data[i0 + k] += off;
 }
 
 __global__ void k_sort_scatter(const uint32_t* __restrict__ keys, uint32_t* __restrict__ cursor,
@@ -514,7 +579,7 @@ __device__ __forceinline__ double warp_sum_f64(double v) {
 // so the bundle marches in lock-step like the fixed-step kernel (coherent gathers, uniform accept/reject).
 // The RMS error norm runs over the n_state components of the valid lanes (butterfly sum: deterministic).
 template <typename T, bool PHASE, bool AUX64>
-__device__ __forceinline__ void rk45_bundle_integrate(const PropArgs<T>& A, Ray<T>& r, CellCache<T, PHASE>& cc, bool valid, bool early,
+__device__ __forceinline__ void rk45_bundle_integrate(const PropArgs<T>& A, Ray<T>& r, StageSmem<T>& S, bool valid, bool early,
                                                       double amp0, double pol0, unsigned& n_att, LaneStats& ls) {
     const unsigned vmask = __ballot_sync(0xffffffffu, valid);
     const double size = (double)A.n_state * (double)__popc(vmask);        // x.size of the flattened bundle state
@@ -524,7 +589,7 @@ __device__ __forceinline__ void rk45_bundle_integrate(const PropArgs<T>& A, Ray<
     double s_a = 0.0, s_b = 0.0;
     T sc_p[3], sc_v[3], sc_ph = atol;
     if (valid) {
-        touched += deriv<T, PHASE, AUX64>(A.F, cc, A.omega, r.p, r.v, f);
+        touched += deriv_direct<T, PHASE, AUX64>(A.F, A.omega, r.p, r.v, f);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             sc_p[k] = atol + fabs(r.p[k]) * rtol; sc_v[k] = atol + fabs(r.v[k]) * rtol;
@@ -549,7 +614,7 @@ __device__ __forceinline__ void rk45_bundle_integrate(const PropArgs<T>& A, Ray<
 #pragma unroll
         for (int k = 0; k < 3; ++k) { p1[k] = r.p[k] + (T)h0 * f.dp[k]; v1[k] = r.v[k] + (T)h0 * f.dv[k]; }
         Deriv<T> f1;
-        touched += deriv<T, PHASE, AUX64>(A.F, cc, A.omega, p1, v1, f1);
+        touched += deriv_direct<T, PHASE, AUX64>(A.F, A.omega, p1, v1, f1);
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
             double q = (f1.dp[k] - f.dp[k]) / sc_p[k]; s_c += q * q;
@@ -575,7 +640,7 @@ __device__ __forceinline__ void rk45_bundle_integrate(const PropArgs<T>& A, Ray<
             const double h = t_new - t;
             h_abs = fabs(h);
             Ray<T> rn = r; Deriv<T> fn = f; T esq = (T)0;
-            if (valid) touched += dp5_attempt<T, PHASE, AUX64>(A.F, cc, A.omega, (T)h, rtol, atol, r, f, rn, fn, esq);
+            if (valid) touched += dp5_attempt<T, PHASE, AUX64, StageSmem<T> >(A.F, A.omega, (T)h, rtol, atol, r, f, rn, fn, esq, S);
             ++n_att;
             const double en = sqrt(warp_sum_f64((double)esq)) / sqrt(size);
             if (!(en == en)) { failed = true; ls.capped += valid ? 1 : 0; break; }   // NaN state: solve_ivp would never return
@@ -676,9 +741,12 @@ __device__ __noinline__ void rk45x_integrate(const PropArgs<double>& A, Ray<doub
 }
 
 template <typename T, int METHOD, bool PHASE, bool AUX64>
-__global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 8) ? SP_RK4_MIN_BLOCKS : ((METHOD == SP_METHOD_RK45 && sizeof(T) == 8) ? SP_RK45_MIN_BLOCKS : ((METHOD == SP_METHOD_RK4 && sizeof(T) == 4) ? SP_RK4F_MIN_BLOCKS : 1))) k_propagate(const PropArgs<T> A, const Epilogue E) {
+__global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 8) ? SP_RK4_MIN_BLOCKS : (((METHOD == SP_METHOD_RK45 || METHOD == SP_METHOD_RK45B) && sizeof(T) == 8) ? SP_RK45_MIN_BLOCKS : ((METHOD == SP_METHOD_RK4 && sizeof(T) == 4) ? SP_RK4F_MIN_BLOCKS : 1))) k_propagate(const PropArgs<T> A, const Epilogue E) {
     const int lane = threadIdx.x & 31;
     const bool early = (A.flags & SP_FLAG_EARLY_EXIT) != 0;
+    extern __shared__ double sp_dyn_smem[];     // adaptive methods only: SP_STAGE_DOUBLES values per thread (see StageSmem)
+    StageSmem<T> S;
+    S.base = reinterpret_cast<T*>(sp_dyn_smem) + threadIdx.x; S.stride = blockDim.x;
     for (;;) {
         LaneStats ls = {0, 0, 0, 0, 0, 0};      // per bundle: nothing but the ray itself is live across the integration
         unsigned long long slot0 = 0;
@@ -706,16 +774,18 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
         unsigned n_att = 0;
         CellCache<T, PHASE> cc;
         double amp_x = 1.0, pol_x = 0.0;
-        if (METHOD == SP_METHOD_RK45 && (A.flags & SP_FLAG_BUNDLE_STEP)) {
+        if (METHOD == SP_METHOD_RK45B) {
             const double amp0 = (valid && !A.use_beam) ? A.s0[6 * A.n_total + gi] : 1.0;
             const double pol0 = (valid && !A.use_beam) ? A.s0[8 * A.n_total + gi] : 0.0;
-            rk45_bundle_integrate<T, PHASE, AUX64>(A, r, cc, valid, early, amp0, pol0, n_att, ls);
+            rk45_bundle_integrate<T, PHASE, AUX64>(A, r, S, valid, early, amp0, pol0, n_att, ls);
             if (valid) ls.steps += n_att; else n_att = 0;
         } else if (valid) {
             if (METHOD == SP_METHOD_RK4X) {
                 rk4x_integrate<PHASE, AUX64>(A, r, cc, early, gi, n_att, ls, amp_x, pol_x);
             } else if (METHOD == SP_METHOD_RK45X) {
                 rk45x_integrate<PHASE, AUX64>(A, r, cc, early, vmask, gi, n_att, ls, amp_x, pol_x);
+            } else if (METHOD == SP_METHOD_RK45B) {
+                // handled above (whole-warp path)
             } else if (METHOD == SP_METHOD_RK4) {
                 for (int it = 0; it < A.n_steps; ++it) {
                     const int t = rk4_step<T, PHASE, AUX64>(A.F, cc, A.rk, A.omega, r, early);
@@ -727,9 +797,9 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
             } else {
                 // SciPy RK45 driven as solve_ivp does (rk.py:_step_impl), one controller per ray
                 Deriv<T> f; int touched = 0;
-                touched += deriv<T, PHASE, AUX64>(A.F, cc, A.omega, r.p, r.v, f);
+                touched += deriv_direct<T, PHASE, AUX64>(A.F, A.omega, r.p, r.v, f);
                 const double amp0 = A.use_beam ? 1.0 : A.s0[6 * A.n_total + gi], pol0 = A.use_beam ? 0.0 : A.s0[8 * A.n_total + gi];
-                T h_abs = dp5_initial_step<T, PHASE, AUX64>(A.F, cc, A.omega, A.t_end, A.rtol, A.atol, A.n_state, (T)amp0,
+                T h_abs = dp5_initial_step<T, PHASE, AUX64>(A.F, A.omega, A.t_end, A.rtol, A.atol, A.n_state, (T)amp0,
                                                             (T)pol0, r, f, touched);
                 T t = (T)0;
                 const unsigned cap = A.n_steps > 0 ? (unsigned)A.n_steps : (1u << 30);
@@ -759,7 +829,7 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
                         const T h = t_new - t;
                         h_abs = fabs(h);
                         Ray<T> rn; Deriv<T> fn; T esq;
-                        touched += dp5_attempt<T, PHASE, AUX64>(A.F, cc, A.omega, h, A.rtol, A.atol, r, f, rn, fn, esq);
+                        touched += dp5_attempt<T, PHASE, AUX64, StageSmem<T> >(A.F, A.omega, h, A.rtol, A.atol, r, f, rn, fn, esq, S);
                         ++n_att;
                         const T en = sqrt(esq * inv_n);
                         if (!(en == en)) { failed = true; ls.capped += 1; }          // NaN state: solve_ivp would never return
@@ -863,7 +933,7 @@ __global__ void k_joint_init(FieldView<double> F, JointBuf B, const double* s0, 
             for (int k = 0; k < 3; ++k) { r.p[k] = s0[(uint64_t)perm[k] * n + i]; r.v[k] = s0[(uint64_t)(3 + perm[k]) * n + i]; }
             r.ph = s0[7 * n + i];
             B.amp[i] = s0[6 * n + i]; B.pol[i] = s0[8 * n + i];
-            deriv<double, PHASE, AUX64>(F, cc, omega, r.p, r.v, f);
+            deriv_direct<double, PHASE, AUX64>(F, omega, r.p, r.v, f);
             for (int k = 0; k < 3; ++k) { B.p[k][i] = r.p[k]; B.v[k][i] = r.v[k]; B.fv[k][i] = f.dv[k]; }
             B.ph[i] = r.ph; B.fph[i] = f.dph;
             for (int k = 0; k < 3; ++k) {
@@ -881,7 +951,7 @@ __global__ void k_joint_init(FieldView<double> F, JointBuf B, const double* s0, 
                 r.p[k] = B.p[k][i]; r.v[k] = B.v[k][i];
                 p1_[k] = r.p[k] + h0 * r.v[k]; v1_[k] = r.v[k] + h0 * B.fv[k][i];
             }
-            deriv<double, PHASE, AUX64>(F, cc, omega, p1_, v1_, f);
+            deriv_direct<double, PHASE, AUX64>(F, omega, p1_, v1_, f);
             for (int k = 0; k < 3; ++k) {
                 const double sp_ = atol + fabs(r.p[k]) * rtol, sv_ = atol + fabs(r.v[k]) * rtol;
                 double q = (f.dp[k] - r.v[k]) / sp_; s_a += q * q;
@@ -911,7 +981,7 @@ __global__ void k_joint_attempt(FieldView<double> F, JointBuf B, uint64_t n, dou
         CellCache<double, PHASE> cc;
         for (int k = 0; k < 3; ++k) { r.p[k] = B.p[k][i]; r.v[k] = B.v[k][i]; f.dp[k] = r.v[k]; f.dv[k] = B.fv[k][i]; }
         r.ph = B.ph[i]; f.dph = B.fph[i];
-        dp5_attempt<double, PHASE, AUX64>(F, cc, omega, h, rtol, atol, r, f, rn, fn, esq);
+        dp5_attempt<double, PHASE, AUX64>(F, omega, h, rtol, atol, r, f, rn, fn, esq);
         for (int k = 0; k < 3; ++k) { B.pn[k][i] = rn.p[k]; B.vn[k][i] = rn.v[k]; B.fvn[k][i] = fn.dv[k]; }
         B.phn[i] = rn.ph; B.fphn[i] = fn.dph;
     }
@@ -1139,10 +1209,11 @@ __global__ void k_exit_plane(const double* __restrict__ sf, uint64_t n, int kp, 
     }
 }
 
-__global__ void k_finalize(const double* __restrict__ planes, double* __restrict__ H, size_t npix) {
+__global__ void k_finalize(const long long* __restrict__ planes, double* __restrict__ H, size_t npix) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= npix) return;
-    const double a = planes[i], b = planes[2 * npix + i];     // Re(sum Ex), Re(sum Ey)
+    const double q = 1.0 / (double)(1ll << SP_PLANE_FRAC_BITS);
+    const double a = (double)planes[i] * q, b = (double)planes[2 * npix + i] * q;     // Re(sum Ex), Re(sum Ey)
     H[i] = sqrt(a * a + b * b);
 }
 
@@ -1176,7 +1247,7 @@ __global__ void k_beam(BeamSpec B, uint64_t off, uint64_t n, double* __restrict_
 
 // ---------------------------------------------------------------------------------------------- workspace
 struct sp_workspace {
-    uint32_t *keys = nullptr, *order = nullptr, *hist = nullptr;
+    uint32_t *keys = nullptr, *order = nullptr, *hist = nullptr, *tile_sums = nullptr;
     size_t cap_rays = 0, cap_keys = 0;
     unsigned long long* cursor = nullptr;
     double* joint = nullptr; size_t joint_cap = 0;
@@ -1184,6 +1255,7 @@ struct sp_workspace {
     int sm_count = 0;
     std::vector<cudaEvent_t> ev;     // start/stop pairs around k_propagate launches
     size_t ev_used = 0;
+    double ev_ms = 0.0; uint64_t ev_n = 0;   // launches already folded out of the event list
     std::vector<double> jlog_h, jlog_en;   // attempts of the last joint solve
 };
 
@@ -1195,9 +1267,40 @@ extern "C" int sp_workspace_joint_log(const sp_workspace* w, double* h_out, doub
     return SP_OK;
 }
 
+// Start/stop events around every k_propagate launch.  The log is bounded without ever dropping a launch: when it
+// reaches EV_FOLD events, the pairs that have already completed are folded into a running total and their events
+// recycled (no wait: cudaEventQuery); only pairs still in flight stay in the list.
+static const size_t EV_FOLD = 1024;
+static int ws_fold(sp_workspace* w, bool wait) {
+    size_t keep = 0;
+    for (size_t i = 0; i + 1 < w->ev_used; i += 2) {
+        bool done = true;
+        if (wait) CU(cudaEventSynchronize(w->ev[i + 1]));
+        else {
+            const cudaError_t q = cudaEventQuery(w->ev[i + 1]);
+            if (q == cudaErrorNotReady) done = false;
+            else if (q != cudaSuccess) return fail(SP_ECUDA, std::string("cudaEventQuery: ") + cudaGetErrorString(q));
+        }
+        if (done) {
+            float ms = 0.f;
+            CU(cudaEventElapsedTime(&ms, w->ev[i], w->ev[i + 1]));
+            w->ev_ms += ms; w->ev_n += 1;
+        } else {
+            std::swap(w->ev[keep], w->ev[i]); std::swap(w->ev[keep + 1], w->ev[i + 1]);
+            keep += 2;
+        }
+    }
+    if (w->ev_used & 1) { std::swap(w->ev[keep], w->ev[w->ev_used - 1]); keep += 1; }     // a start without its stop yet
+    w->ev_used = keep;
+    return SP_OK;
+}
+
 static int ws_event(sp_workspace* w, cudaStream_t st) {
+    if (w->ev_used >= EV_FOLD && !(w->ev_used & 1)) {
+        const int rc = ws_fold(w, false);
+        if (rc) return rc;
+    }
     if (w->ev_used == w->ev.size()) {
-        if (w->ev.size() >= 512) return SP_OK;          // stop recording, keep running
         cudaEvent_t e;
         CU(cudaEventCreate(&e));
         w->ev.push_back(e);
@@ -1208,15 +1311,10 @@ static int ws_event(sp_workspace* w, cudaStream_t st) {
 
 extern "C" int sp_workspace_propagate_ms(sp_workspace* w, double* total_ms, int* n_launches) {
     if (!w || !total_ms || !n_launches) return fail(SP_EINVAL, "null argument");
-    double tot = 0.0; int n = 0;
-    for (size_t i = 0; i + 1 < w->ev_used; i += 2) {
-        CU(cudaEventSynchronize(w->ev[i + 1]));
-        float ms = 0.f;
-        CU(cudaEventElapsedTime(&ms, w->ev[i], w->ev[i + 1]));
-        tot += ms; ++n;
-    }
-    w->ev_used = 0;
-    *total_ms = tot; *n_launches = n;
+    const int rc = ws_fold(w, true);
+    if (rc) return rc;
+    *total_ms = w->ev_ms; *n_launches = (int)w->ev_n;
+    w->ev_ms = 0.0; w->ev_n = 0; w->ev_used = 0;
     return SP_OK;
 }
 
@@ -1227,13 +1325,14 @@ extern "C" int sp_workspace_create(sp_workspace** out) {
     CU(cudaGetDevice(&dev));
     CU(cudaDeviceGetAttribute(&w->sm_count, cudaDevAttrMultiProcessorCount, dev));
     CU(cudaMalloc(&w->cursor, sizeof(unsigned long long)));
+    CU(cudaMalloc(&w->tile_sums, 1024 * sizeof(uint32_t)));
     CU(cudaMallocHost(&w->host_pair, 2 * sizeof(double)));
     *out = w;
     return SP_OK;
 }
 extern "C" int sp_workspace_destroy(sp_workspace* w) {
     if (!w) return SP_OK;
-    cudaFree(w->keys); cudaFree(w->order); cudaFree(w->hist); cudaFree(w->cursor); cudaFree(w->joint);
+    cudaFree(w->keys); cudaFree(w->order); cudaFree(w->hist); cudaFree(w->tile_sums); cudaFree(w->cursor); cudaFree(w->joint);
     cudaFreeHost(w->host_pair);
     for (cudaEvent_t e : w->ev) cudaEventDestroy(e);
     delete w;
@@ -1269,12 +1368,17 @@ static int kernel_index_of(const sp_field* f, int caller_axis) {
     return 0;
 }
 
+template <typename T, int METHOD> static constexpr size_t stage_smem_bytes() {
+    return (METHOD == SP_METHOD_RK45 || METHOD == SP_METHOD_RK45B) ? (size_t)SP_STAGE_DOUBLES * 128 * sizeof(T) : 0;
+}
+
 template <typename T, int METHOD>
 static int launch_propagate(const PropArgs<T>& A, const Epilogue& E, int grid, cudaStream_t st) {
     const bool phase = (A.flags & SP_FLAG_PHASE) != 0, aux64 = phase && (A.flags & SP_FLAG_PHASE_F64) != 0;
-    if (!phase) k_propagate<T, METHOD, false, false><<<grid, 128, 0, st>>>(A, E);
-    else if (!aux64) k_propagate<T, METHOD, true, false><<<grid, 128, 0, st>>>(A, E);
-    else k_propagate<T, METHOD, true, true><<<grid, 128, 0, st>>>(A, E);
+    const size_t sm = stage_smem_bytes<T, METHOD>();
+    if (!phase) k_propagate<T, METHOD, false, false><<<grid, 128, sm, st>>>(A, E);
+    else if (!aux64) k_propagate<T, METHOD, true, false><<<grid, 128, sm, st>>>(A, E);
+    else k_propagate<T, METHOD, true, true><<<grid, 128, sm, st>>>(A, E);
     LAUNCH_CHECK();
     return SP_OK;
 }
@@ -1282,9 +1386,10 @@ static int launch_propagate(const PropArgs<T>& A, const Epilogue& E, int grid, c
 template <typename T, int METHOD> static int occupancy_grid(int sm_count, int flags, int& grid) {
     int per_sm = 0;
     const bool phase = (flags & SP_FLAG_PHASE) != 0, aux64 = phase && (flags & SP_FLAG_PHASE_F64) != 0;
-    if (!phase) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<T, METHOD, false, false>, 128, 0));
-    else if (!aux64) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<T, METHOD, true, false>, 128, 0));
-    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<T, METHOD, true, true>, 128, 0));
+    const size_t sm = stage_smem_bytes<T, METHOD>();
+    if (!phase) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<T, METHOD, false, false>, 128, sm));
+    else if (!aux64) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<T, METHOD, true, false>, 128, sm));
+    else CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_propagate<T, METHOD, true, true>, 128, sm));
     if (per_sm < 1) per_sm = 1;
     grid = sm_count * per_sm;
     return SP_OK;
@@ -1364,11 +1469,14 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
     const uint32_t n_keys = 1u << (2 * bits - key_shift);
 
     int grid = 0, rc = 0;
+    const bool bundle_step = P->method == SP_METHOD_RK45 && (P->flags & SP_FLAG_BUNDLE_STEP);
     if (ext) rc = ext_grid(ws->sm_count, P->method == SP_METHOD_RK45, ext_aux64, grid);
     else if (fp32) rc = (P->method == SP_METHOD_RK4) ? occupancy_grid<float, SP_METHOD_RK4>(ws->sm_count, P->flags, grid)
-                                                : occupancy_grid<float, SP_METHOD_RK45>(ws->sm_count, P->flags, grid);
+                        : (bundle_step ? occupancy_grid<float, SP_METHOD_RK45B>(ws->sm_count, P->flags, grid)
+                                       : occupancy_grid<float, SP_METHOD_RK45>(ws->sm_count, P->flags, grid));
     else rc = (P->method == SP_METHOD_RK4) ? occupancy_grid<double, SP_METHOD_RK4>(ws->sm_count, P->flags, grid)
-                                           : occupancy_grid<double, SP_METHOD_RK45>(ws->sm_count, P->flags, grid);
+              : (bundle_step ? occupancy_grid<double, SP_METHOD_RK45B>(ws->sm_count, P->flags, grid)
+                             : occupancy_grid<double, SP_METHOD_RK45>(ws->sm_count, P->flags, grid));
     if (rc) return rc;
 
     for (uint64_t off = 0; off < n; off += CHUNK) {
@@ -1386,8 +1494,15 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
             CU(cudaMemsetAsync(ws->hist, 0, n_keys * sizeof(uint32_t), st));
             k_sort_keys<<<(cn + 255) / 256, 256, 0, st>>>(S, ws->keys, ws->hist);
             LAUNCH_CHECK();
-            k_scan<<<1, 1024, 0, st>>>(ws->hist, n_keys);
+            const uint32_t n_tiles = (n_keys + SP_SCAN_TILE - 1) / SP_SCAN_TILE;       // <= 1024 (n_keys <= 2^22)
+            k_scan_tiles<<<n_tiles, 1024, 0, st>>>(ws->hist, n_keys, ws->tile_sums);
             LAUNCH_CHECK();
+            if (n_tiles > 1) {
+                k_scan_tops<<<1, 1024, 0, st>>>(ws->tile_sums, n_tiles);
+                LAUNCH_CHECK();
+                k_scan_add<<<n_tiles, 1024, 0, st>>>(ws->hist, n_keys, ws->tile_sums);
+                LAUNCH_CHECK();
+            }
             k_sort_scatter<<<(cn + 255) / 256, 256, 0, st>>>(ws->keys, ws->hist, ws->order, cn);
             LAUNCH_CHECK();
             k_sort_fix<<<(n_keys + 255) / 256, 256, 0, st>>>(ws->hist, ws->order, n_keys);   // hist now holds segment ends
@@ -1415,7 +1530,7 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
         if (fp32) {
             FILL(float)
             rc = (P->method == SP_METHOD_RK4) ? launch_propagate<float, SP_METHOD_RK4>(A, E, g, st)
-                                              : launch_propagate<float, SP_METHOD_RK45>(A, E, g, st);
+                 : (bundle_step ? launch_propagate<float, SP_METHOD_RK45B>(A, E, g, st) : launch_propagate<float, SP_METHOD_RK45>(A, E, g, st));
         } else if (ext) {
             FILL(double)
             A.X = make_ext(field, P->verdet, P->flags);
@@ -1423,7 +1538,7 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
         } else {
             FILL(double)
             rc = (P->method == SP_METHOD_RK4) ? launch_propagate<double, SP_METHOD_RK4>(A, E, g, st)
-                                              : launch_propagate<double, SP_METHOD_RK45>(A, E, g, st);
+                 : (bundle_step ? launch_propagate<double, SP_METHOD_RK45B>(A, E, g, st) : launch_propagate<double, SP_METHOD_RK45>(A, E, g, st));
         }
 #undef FILL
         if (rc) return rc;
@@ -1648,8 +1763,36 @@ extern "C" int sp_image_finalize(const sp_image* img, double* H_dev, void* strea
     if (!img || !H_dev || !img->planes_dev) return fail(SP_EINVAL, "null argument");
     const size_t npix = (size_t)img->nx * img->ny;
     if (npix == 0) return SP_OK;
-    k_finalize<<<(unsigned)((npix + 255) / 256), 256, 0, (cudaStream_t)stream>>>(img->planes_dev, H_dev, npix);
+    k_finalize<<<(unsigned)((npix + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const long long*)img->planes_dev, H_dev, npix);
     LAUNCH_CHECK();
+    return SP_OK;
+}
+
+// ------------------------------------------------------------------------------- FP64 pipe peak (measurement aid)
+// The ray integrator is bound by the FP64 pipe and its issue slots, not by HBM (ncu: DRAM < 1 % of peak), so
+// bench.py's roofline needs an FP64 denominator measured on the same GPU in the same run.  Every thread runs 8
+// independent DFMA chains (no memory traffic, full occupancy): the launch sustains the pipe's issue rate.
+__global__ void __launch_bounds__(256) k_fp64_peak(int iters, double seed, double* __restrict__ out, uint64_t out_len) {
+    double a0 = seed, a1 = seed + 1.0, a2 = seed + 2.0, a3 = seed + 3.0, a4 = seed + 4.0, a5 = seed + 5.0, a6 = seed + 6.0, a7 = seed + 7.0;
+    const double m = 1.0 - 1e-9 * (double)(threadIdx.x & 7), c = 1e-12;
+#pragma unroll 4
+    for (int i = 0; i < iters; ++i) {
+        a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+        a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+    }
+    const uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < out_len) out[t] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+extern "C" int sp_fp64_peak(int iters, double* out_dev, uint64_t out_len, uint64_t* n_dfma_out, void* stream) {
+    if (iters < 1 || !out_dev || !n_dfma_out) return fail(SP_EINVAL, "need iters >= 1, an output buffer and n_dfma_out");
+    int dev = 0, sms = 0;
+    CU(cudaGetDevice(&dev));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const int grid = sms * 8;                                  // 8 x 256 threads = 2048 resident threads per SM
+    k_fp64_peak<<<grid, 256, 0, (cudaStream_t)stream>>>(iters, 1.0, out_dev, out_len);
+    LAUNCH_CHECK();
+    *n_dfma_out = (uint64_t)grid * 256ull * (uint64_t)iters * 8ull;
     return SP_OK;
 }
 

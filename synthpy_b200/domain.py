@@ -11,6 +11,14 @@ from . import engine
 
 
 class ScalarDomain:
+    """Deviations from upstream's container that a caller should know:
+      * ``region_count`` / ``auto_batching`` (domain.py:137-243, WIP upstream) are accepted and ignored -- one region, always
+        (a warning is raised for region_count > 1);
+      * the ``test_*`` profiles are evaluated on the float64 mesh and rounded once when the device field is packed (the
+        legacy generation's arithmetic, full_solver.py:120,130-167); upstream's current generation evaluates them on the
+        float32-rounded mesh (domain.py:392-451), a 1e-7 relative difference in ``ne``;
+      * ``external_ne`` and friends work (upstream's frozen eqx.Module rejects the assignment, domain.py:310,453-461)."""
+
     def __init__(self, lengths, dims, *, ne_type=None, inv_brems=False, phaseshift=False, B_on=False,
                  probing_direction="z", auto_batching=True, iteration=1, region_count=1, leeway_factor=None,
                  coord_backup=None, future_dims=None, debug=False):
@@ -32,6 +40,10 @@ class ScalarDomain:
         self.lengths = np.array([self.x_length, self.y_length, self.z_length])
         self.x_n, self.y_n, self.z_n = (int(v) for v in dims)
         self.dims = np.array([self.x_n, self.y_n, self.z_n])
+        if region_count not in (None, 1):
+            import warnings
+            warnings.warn("synthpy_b200.ScalarDomain keeps the whole grid on one GPU (a 1024^3 packed field is 17 GB of 180 GB): "
+                          f"region_count={region_count} is ignored and the domain is traced as one region", stacklevel=2)
         self.region_count = 1                       # no domain batching needed on a 180 GB part
         self.coord_backup = self.future_dims = None
         # domain.py:230-232: float32-rounded linspace axes

@@ -17,7 +17,7 @@ OP_KINDS = {"travel": L.OP_TRAVEL, "travel_noE": L.OP_TRAVEL_NOE, "lens": L.OP_L
             "circ_stop": L.OP_CIRC_STOP, "rect_ap": L.OP_RECT_AP, "knife": L.OP_KNIFE, "ref_beam": L.OP_REF_BEAM}
 METHODS = {"rk4": L.METHOD_RK4, "rk45": L.METHOD_RK45, "rk45_joint": L.METHOD_RK45_JOINT, "rk45_bundle": L.METHOD_RK45}
 BEAM_TYPES = {"circular": L.BEAM_CIRCULAR_POW2, "circular_legacy": L.BEAM_CIRCULAR_FOLD, "square": L.BEAM_SQUARE,
-              "rectangular": L.BEAM_RECTANGULAR, "linear": L.BEAM_LINEAR}
+              "rectangular": L.BEAM_RECTANGULAR, "rect_trackers": L.BEAM_RECTANGULAR, "linear": L.BEAM_LINEAR}
 
 
 def require_cuda():
@@ -140,13 +140,16 @@ _workspaces = {}
 
 
 def workspace():
+    """The ``sp_workspace`` of the current (device, stream).  A workspace holds the bundle dispenser, the sort scratch and
+    the joint-solve buffers of the launches in flight, so two streams (or threads with their own streams) must never
+    share one: each (device, stream) pair gets its own, created on first use."""
     require_cuda()
-    dev = torch.cuda.current_device()
-    if dev not in _workspaces:
+    key = (torch.cuda.current_device(), int(torch.cuda.current_stream().cuda_stream))
+    if key not in _workspaces:
         h = C.c_void_p()
         L.check(L.lib.sp_workspace_create(C.byref(h)))
-        _workspaces[dev] = h
-    return _workspaces[dev]
+        _workspaces[key] = h
+    return _workspaces[key]
 
 
 def propagate_kernel_ms():
@@ -214,17 +217,19 @@ def make_beam(beam_type, size, divergence, ne_extent, probing_direction="z", see
 
 class ImageBuffer:
     """Detector image accumulator in HBM.  ``kind`` 'histogram' -> uint64 counts (np.histogram2d semantics),
-    'interferogram' -> four float64 planes of summed complex E (digitize semantics)."""
+    'interferogram' -> four int64 fixed-point planes (2^-40 units) of summed complex E (digitize semantics): integer
+    sums are exact, so the image is identical from run to run and for any partition of the rays over GPUs."""
 
     def __init__(self, kind, nx, ny, x_range, y_range):
         require_cuda()
         self.kind, self.nx, self.ny = kind, int(nx), int(ny)
         self.x_range, self.y_range = (float(x_range[0]), float(x_range[1])), (float(y_range[0]), float(y_range[1]))
         self.counts = self.planes = None
+        self._global = None            # sum over ranks attached by distributed.combine_images (out of place)
         if kind == "histogram":
             self.counts = torch.zeros((self.ny, self.nx), dtype=torch.int64, device="cuda")
         elif kind == "interferogram":
-            self.planes = torch.zeros((4, self.ny, self.nx), dtype=torch.float64, device="cuda")
+            self.planes = torch.zeros((4, self.ny, self.nx), dtype=torch.int64, device="cuda")
         else:
             raise ValueError(kind)
 
@@ -247,16 +252,31 @@ class ImageBuffer:
 
     def zero_(self):
         (self.counts if self.counts is not None else self.planes).zero_()
+        self._global = None
 
     def tensors(self):
+        """This rank's accumulator (what the kernels add to)."""
         return [self.counts] if self.counts is not None else [self.planes]
+
+    def set_global(self, tensors):
+        """Attach (or drop, with None) the sum over ranks; see distributed.combine_images."""
+        self._global = None if tensors is None else tensors[0]
+
+    def touched(self):
+        """The accumulator is about to change: a previously attached global sum no longer describes it."""
+        self._global = None
+
+    def total(self):
+        """The global image if one is attached (after combine_images), else this rank's accumulator."""
+        return self._global if self._global is not None else self.tensors()[0]
 
     def result(self):
         """H as the reference returns it: float64 counts (ny, nx), or sqrt(Re(sum Ex)^2 + Re(sum Ey)^2)."""
         if self.counts is not None:
-            return self.counts.to(torch.float64)
+            return self.total().to(torch.float64)
         H = torch.empty((self.ny, self.nx), dtype=torch.float64, device="cuda")
         img = self.struct()
+        img.planes_dev = self.total().data_ptr()
         L.check(L.lib.sp_image_finalize(C.byref(img), _ptr(H), _stream()))
         return H
 
@@ -304,6 +324,8 @@ def propagate(field, params, *, s0=None, beam=None, n=None, ray_offset=0, want_s
         return out
     keep, structs = [], []
     for ops, image, wl in channels:
+        if image is not None:
+            image.touched()
         ch, k = make_channel(ops, image, wl)
         structs.append(ch)
         keep.append(k)

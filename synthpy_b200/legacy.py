@@ -114,6 +114,75 @@ class ScalarDomain:
         return (self.rf, self.Jf) if return_E else self.rf
 
 
+class MinimalScalarDomain:
+    """``minimal_solver.ScalarDomain`` (src/solvers-legacy/minimal_solver.py:121-398), the 6-component generation of the
+    legacy solver, on the CUDA path: state [x, y, z, vx, vy, vz], joint RK45 whose RMS error norm runs over 6N components
+    (``sp_params.n_state = 6``), integration span sqrt(ex^2 + ey^2 ez^2) / c exactly as upstream writes it (:321), and the
+    ``ne_max`` clamp of its ``calc_dndr`` (:231).
+
+    Upstream keeps axes, density and gradients in float64 here; the device field is float32 ({g_u, g_v, g_w, aux} per
+    node, the layout that matches ``full_solver`` bit for bit), so the float64 gradients are computed on the host with
+    the reference's own NumPy call and rounded once when packed: results agree with ``minimal_solver`` to ~1e-7 relative
+    (SURVEY.md 8a-3), not to 1e-9.  The step sequence (attempt count) is pinned by tests/golden/g8_minimal.npz."""
+
+    def __init__(self, x, y, z, probing_direction="z"):
+        self.x, self.y, self.z = (np.asarray(a, dtype=np.float64) for a in (x, y, z))
+        self.extent_x, self.extent_y, self.extent_z = self.x.max(), self.y.max(), self.z.max()
+        self.probing_direction = probing_direction
+        self.extent = {"x": self.extent_x, "y": self.extent_y, "z": self.extent_z}[probing_direction]
+        self.ne = None
+
+    def _mesh(self):
+        return np.meshgrid(self.x, self.y, self.z, indexing="ij")
+
+    def test_null(self):                                            # minimal_solver.py:150-155
+        self.ne = np.zeros((len(self.x), len(self.y), len(self.z)))
+
+    def test_lens(self, n_e0=1e24, LR=1e-3):                        # minimal_solver.py:192-201
+        XX, YY, _ = self._mesh()
+        self.ne = n_e0 * np.exp(-(np.sqrt(XX ** 2 + YY ** 2)) ** 2 / LR ** 2)
+
+    def test_liner(self, n_e0=1e24, LR=1e-3):                       # minimal_solver.py:203-212
+        XX, _, ZZ = self._mesh()
+        self.ne = n_e0 * np.exp(-(np.sqrt(XX ** 2 + ZZ ** 2)) ** 2 / LR ** 2)
+
+    def external_ne(self, ne):                                      # minimal_solver.py:214-220
+        self.ne = np.array(ne, dtype=np.float64, copy=True)
+
+    def calc_dndr(self, lwl=1053e-9, ne_max=1):                     # minimal_solver.py:222-243
+        self.omega = engine.omega_of(lwl)
+        ne_nc = self.ne / engine.critical_density(self.omega)
+        ne_nc[ne_nc > ne_max] = ne_max
+        axes = (self.x, self.y, self.z)
+        g = [-0.5 * engine.C_LIGHT ** 2 * np.gradient(ne_nc, axes[a], axis=a) for a in range(3)]
+        self.field = engine.DeviceField.from_gradients(g[0], g[1], g[2], self.x, self.y, self.z,
+                                                       march_axis=engine.AXIS[self.probing_direction])
+
+    def init_beam(self, Np, beam_size, divergence):                 # minimal_solver.py:260-314 (legacy radial law, global RNG)
+        self.s0 = init_beam(Np, beam_size, divergence, self.extent, "circular", self.probing_direction)[:6]
+        return self.s0
+
+    def t_end(self):
+        return np.sqrt(self.extent_x ** 2 + self.extent_y ** 2 * self.extent_z ** 2) / engine.C_LIGHT
+
+    def solve(self, method="RK45", s0=None):                        # minimal_solver.py:316-335
+        s6 = np.asarray(self.s0 if s0 is None else s0, dtype=np.float64)
+        s9 = np.zeros((9, s6.shape[1]))
+        s9[:6] = s6
+        P = engine.make_params("rk45_joint", probing_direction=self.probing_direction, extent=self.extent, omega=self.omega,
+                               t_end=self.t_end(), rtol=1e-3, atol=1e-6, n_state=6, early_exit=False)
+        out = engine.propagate(self.field, P, s0=engine.to_device(s9), want_sf=True, want_rf=True, want_steps=True)
+        torch.cuda.synchronize()
+        self.sf = out["sf"].cpu().numpy()[:6]
+        self.rf = out["rf"].cpu().numpy()
+        self.steps = out["steps"].cpu().numpy()
+        self.stats = engine.stats_dict(out["stats_dev"])
+        return self.rf
+
+    def ray_at_exit(self):                                          # minimal_solver.py:337-384
+        return self.rf
+
+
 def init_beam(Np, beam_size, divergence, ne_extent, beam_type="circular", probing_direction="z"):
     """full_solver.py:547-835 on the host RNG (legacy radial law u = fold(U+U)); same draw order."""
     s0 = np.zeros((9, Np))

@@ -61,6 +61,13 @@ def solve(s0_import, ScalarDomain, probing_depth, *, return_E=False, parallelise
     reference: rf (4,N) [x, theta, y, phi] at the exit plane (m, rad), Jf (2,N) complex or None.
     ``parallelise / jitted / save_steps / memory_debug / keep_domain`` are accepted for call compatibility.
 
+    Call-compatible, not default-compatible: upstream integrates every ray with diffrax Tsit5 under
+    ``PIDController(rtol=1, atol=1e-5)``, ``dt0 = (t1 - t0) / 2`` and ``max_steps=10000`` (propagator.py:533-599) -- a
+    tolerance that lets the controller take the whole box in a handful of steps.  Here the default is fixed-step RK4 at
+    half a cell (``method='rk4'``), and ``method='rk45'`` is SciPy's Dormand-Prince at 1e-3 / 1e-6 (the legacy
+    generation's solver); neither reproduces diffrax's step sequence, which cannot be pinned in this environment
+    (DESIGN.md section 6).  ``parallelise`` / ``jitted`` have no effect: there is one code path.
+
     numpy in -> numpy out; CUDA tensors in -> CUDA tensors out (no host round trip).
     With ``return_stats`` / ``return_state`` a dict with 'stats', 'sf', 'steps' is appended to the tuple."""
     engine.require_cuda()

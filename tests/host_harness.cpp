@@ -190,9 +190,8 @@ static void rk45_t(const HostField* f, const double* s0, uint64_t n, double t_en
         Ray<double> r; load(f, s0, n, i, r);
         const double amp = s0[6 * n + i], pol = s0[8 * n + i];
         Deriv<double> fd; int touched = 0; uint32_t evals = 1;
-        CellCache<double, PH> cc;
-        deriv<double, PH, A64>(F, cc, omega, r.p, r.v, fd);
-        double h_abs = dp5_initial_step<double, PH, A64>(F, cc, omega, t_end, rtol, atol, n_state, amp, pol, r, fd, touched);
+        deriv_direct<double, PH, A64>(F, omega, r.p, r.v, fd);
+        double h_abs = dp5_initial_step<double, PH, A64>(F, omega, t_end, rtol, atol, n_state, amp, pol, r, fd, touched);
         evals += 1;
         double t = 0; uint32_t n_att = 0;
         const uint32_t cap = cap_in > 0 ? (uint32_t)cap_in : (1u << 30);
@@ -208,7 +207,7 @@ static void rk45_t(const HostField* f, const double* s0, uint64_t n, double t_en
                 const double h = t_new - t;
                 h_abs = fabs(h);
                 Ray<double> rn; Deriv<double> fn; double esq;
-                dp5_attempt<double, PH, A64>(F, cc, omega, h, rtol, atol, r, fd, rn, fn, esq);
+                dp5_attempt<double, PH, A64>(F, omega, h, rtol, atol, r, fd, rn, fn, esq);
                 ++n_att; evals += 6;
                 const double en = sqrt(esq / n_state);
                 if (en < 1) { h_abs *= dp5_factor<double>(en, true, rejected); t = t_new; r = rn; fd = fn; break; }

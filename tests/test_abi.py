@@ -34,7 +34,7 @@ def test_every_declared_symbol_is_exported(lib):
 def test_binding_covers_header():
     from synthpy_b200 import _lib
     assert sorted(_lib.EXPORTS) == declared_symbols()
-    assert _lib.lib.sp_version() == 3
+    assert _lib.lib.sp_version() == 4
 
 
 def test_struct_sizes_match_header_layout():

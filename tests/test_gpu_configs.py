@@ -135,6 +135,39 @@ def test_C4_refractometry_knife_edge_and_tolerance_sweep(mods):
     assert l1[2] <= l1[0] + 1e-12 and l1[2] < 0.05
 
 
+def test_field_generator_on_device(mods, golden):
+    """SURVEY 8f-1 on the GPU: (a) the cuFFT path reproduces the field the reference's gaussian3D.domain_fft produced for
+    np.random.seed(1) (tests/golden/g3_turb.npz, made by the real module); (b) at the benchmarked 512^3 size the radially
+    averaged power spectrum of the generated field follows the requested k^-11/3 law inside the band and is empty outside;
+    (c) the CPU and GPU FFTs of the same (torch, seeded) noise give the same grid."""
+    FG = mods["FG"]
+    g = golden("g3_turb")
+    np.random.seed(1)
+    ne = FG.turbulent_ne(16, noise="numpy", device="cuda")
+    assert ne.is_cuda and tuple(ne.shape) == g["ne"].shape
+    assert np.max(np.abs(ne.cpu().numpy() - g["ne"])) < 1e-6 * np.abs(g["ne"]).max()
+    a = FG.turbulent_ne(32, noise="torch", seed=5, device="cuda").cpu()
+    b = FG.turbulent_ne(32, noise="torch", seed=5, device="cpu")
+    assert float((a - b).abs().max()) < 1e-9 * float(b.abs().max())
+    # spectrum of the C2 field: f = (ne - 1e25) / 9e24, extent 5 (mm), res 256 -> dx = 5 / 256
+    n, res, extent = 512, 256, 5.0
+    f = (FG.turbulent_ne(res, noise="torch", seed=1, device="cuda") - 1e25) / 9e24
+    P = torch.fft.fftn(f).abs() ** 2
+    del f
+    k1 = 2 * np.pi * torch.fft.fftfreq(n, d=extent / res, device="cuda", dtype=torch.float64)
+    k = torch.sqrt(k1[:, None, None] ** 2 + k1[None, :, None] ** 2 + k1[None, None, :] ** 2)
+    k_min, k_max = 2 * np.pi / 1.0, 2 * np.pi / 0.01
+    inside = (k >= k_min) & (k <= k_max)
+    assert float(P[~inside].sum()) < 1e-20 * float(P[inside].sum())                 # band-limited (gaussian3D.py:252-256)
+    edges = torch.logspace(np.log10(k_min * 1.5), np.log10(float(k.max()) * 0.5), 13, device="cuda", dtype=torch.float64)
+    kc, pk = [], []
+    for lo, hi in zip(edges[:-1], edges[1:]):
+        m = (k >= lo) & (k < hi)
+        kc.append(float(k[m].mean())); pk.append(float(P[m].mean()))
+    slope = np.polyfit(np.log(kc), np.log(pk), 1)[0]
+    assert abs(slope + 11.0 / 3.0) < 0.1, slope                                     # |noise|^2 averages to a constant per shell
+
+
 @pytest.fixture(scope="module")
 def c2(mods):
     """The C2 workload at full size: 512^3 turbulent field, 1e7 device-generated rays."""
@@ -240,23 +273,47 @@ def test_bench_contract_on_a_small_workload():
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--grid", "64", "--rays", "2e5", "--steps", "2",
-                          "--warmup", "3", "--cpu-rays-per-worker", "50"], capture_output=True, text=True, timeout=900)
+                          "--warmup", "3", "--cpu-rays-per-worker", "50", "--parity-rays", "500"], capture_output=True, text=True,
+                         timeout=900)
     assert out.returncode == 0, out.stderr[-3000:]
     lines = [l for l in out.stdout.strip().splitlines() if l.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
-              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+              "dtype", "data", "config", "roofline", "cpu_baseline", "same_integrator", "e2e", "parity", "gpu_launches", "clocks",
+              "rays_per_s"):
         assert k in d, k
     assert d["n_gpus"] == 1 and d["steps"] == 2 and d["warmup"] == 3 and d["higher_is_better"] is True and d["scaling"] == "weak"
     assert d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic" and "workload" in d["config"]
     r = d["roofline"]
-    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["achieved"] > 0
+    assert r["bound"] == "fp64_pipe" and r["unit"] == "TFLOP/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12
+    assert 0 < r["frac"] <= 1.0 and 20 < r["peak"] < 60                      # B200 FP64: ~37 TFLOP/s FMA
+    assert r["hbm_algorithmic"]["bytes_per_ray_step"] == 512 and r["hbm_algorithmic"]["frac"] > 0
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] > 0
+    assert d["same_integrator"]["value"] > 0 and d["cpu_baseline"]["rays_per_s"] > 0
     e = d["e2e"]
     assert e["value"] > 0 and e["h2d_bytes_per_step"] == 72 * 200000 and e["d2h_bytes_per_step"] > 0
     assert d["gpu_launches"] >= 2 * 4 and d["value"] > 0
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    p = d["parity"]
+    assert p["n"] == 500 and p["max_rel"] < 1e-9 and p["steps_equal"] and p["hist_equal"]
+
+
+def test_bench_C1_line():
+    """--workload C1 (BASELINE configs[0], the reference's own CPU-runnable case) prints a full line with parity over ALL
+    its rays' first 2000."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--workload", "C1", "--cpu-rays-per-worker", "200"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    d = json.loads([l for l in out.stdout.strip().splitlines() if l.startswith("{")][0])
+    assert d["config"]["grid"] == 128 and d["config"]["rays_per_gpu"] == 100000 and d["value"] > 0
+    assert d["parity"]["max_rel"] < 1e-9 and d["parity"]["steps_equal"] and d["parity"]["hist_equal"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 72 * 100000
 
 
 def test_pvti_field_equals_direct_field_and_driver_example_runs(mods, tmp_path, monkeypatch):

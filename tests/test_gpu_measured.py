@@ -1,0 +1,107 @@
+"""The CPU oracle ON THE BENCHMARKED CONFIGURATIONS: the exact fields bench.py builds (512^3 /
+1024^3 turbulence), the device-generated Philox rays it traces, through the same sort + early-exit + fused-epilogue
+path that produces the headline numbers -- compared ray for ray and pixel for pixel with the golden-pinned oracle
+(oracle/synthpy_oracle.py == full_solver.py:376-403,516-544,838-894 + rtm_solver.py:156-178) on sub-samples of
+those very rays.  ``bench.parity_check`` is the single implementation; bench.py prints its 2 000-ray version in
+every line, these tests hold larger samples to the north_star tolerances."""
+import numpy as np
+import pytest
+import torch
+
+import bench
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(workload, **over):
+    a = bench.parse(["--workload", workload] + [x for k, v in over.items() for x in ("--" + k.replace("_", "-"), str(v))])
+    from synthpy_b200 import beam as B, domain as Dm
+    ne = bench.build_ne(a, "cuda")
+    dom = Dm.ScalarDomain(bench.LENGTHS, a.grid)
+    dom.external_ne(ne)
+    dom.device_field(bench.LWL)
+    ne_host = ne.cpu().numpy() if isinstance(ne, torch.Tensor) else np.asarray(ne)
+    del ne
+    beam = B.Beam(int(a.rays), bench.BEAM_R, bench.BEAM_DIV, bench.EXTENT, device=True, seed=2, beam_type="circular")
+    return a, dom, beam, ne_host
+
+
+@pytest.fixture(scope="module")
+def c2():
+    """The C2 field exactly as bench.py builds it, and ONE oracle domain (phase grid included) shared by C2 / C3 / C4."""
+    a, dom, beam, ne_host = _setup("C2")
+    odom = bench.cpu_setup(ne_host, a, phaseshift=True)
+    return dom, beam, odom
+
+
+def test_C2_subsample_against_oracle_at_512(c2):
+    """Two 20 000-ray windows of the 1e7-ray device beam: exit rays <= 1e-9, identical steps per ray, and the two-lens
+    shadowgraph and dark-field schlieren images equal the reference's np.histogram2d count for count."""
+    dom, beam, odom = c2
+    a = bench.parse(["--workload", "C2"])
+    odom.phaseshift = False
+    try:
+        for off in (0, 7000000):
+            r = bench.parity_check(a, dom, beam, odom, 20000, ray_offset=off)
+            assert r["max_rel"] < 1e-9, r
+            assert r["steps_equal"] and 1000 < r["steps_per_ray"] < 1030, r
+            assert r["hist_equal"] and all(c[0] == c[1] > 0 for c in r["counts"]), r
+    finally:
+        odom.phaseshift = True
+
+
+def test_C3_subsample_against_oracle_at_512(c2):
+    """Interferometry on the same field: phase <= 1e-9 of its range with the float64 phase grid, interferogram (reference
+    beam included) within the 1e-3 L1 budget in both phase modes."""
+    dom, beam, odom = c2
+    a = bench.parse(["--workload", "C3"])
+    r = bench.parity_check(a, dom, beam, odom, 6000, ray_offset=123456)
+    assert r["max_rel"] < 1e-9 and r["steps_equal"], r
+    assert r["phase_max_rel"] < 1e-9, r
+    assert r["interferogram_l1_f64_phase"] < 1e-3, r
+    assert r["interferogram_l1_f32_phase"] < 5e-3, r          # float32 aux lane: ~1e-7 relative phase (documented fast mode)
+
+
+def test_C4_subsample_against_oracle_at_512(c2):
+    """Adaptive RK45 per ray at SciPy's default tolerances on the 512^3 field: the same accept / reject sequence as
+    solve_ivp for every ray (6 steps + 2 == nfev), exit rays to 1e-9, refractometer and knife-edge images equal."""
+    dom, beam, odom = c2
+    a = bench.parse(["--workload", "C4"])
+    odom.phaseshift = False
+    try:
+        r = bench.parity_check(a, dom, beam, odom, 256, ray_offset=999)
+    finally:
+        odom.phaseshift = True
+    assert r["steps_equal"], r
+    assert r["max_rel"] < 1e-9, r
+    assert r["hist_equal"], r
+
+
+def test_C5_shard_against_oracle():
+    """A window of the 1e9-ray beam through the seed-3 field of BASELINE configs[4]: at 1024^3 when the box has the host
+    memory for the oracle's float64 grids (~60 GB), else at 768^3."""
+    import psutil
+    free, _ = torch.cuda.mem_get_info()
+    grid = 1024 if (psutil.virtual_memory().available > 90e9 and free > 90e9) else 768
+    a, dom, beam, ne_host = _setup("C5", grid=grid)
+    dom.release_ne()
+    torch.cuda.empty_cache()
+    odom = bench.cpu_setup(ne_host, a)
+    del ne_host
+    r = bench.parity_check(a, dom, beam, odom, 4000, ray_offset=600000000)
+    assert r["max_rel"] < 1e-9 and r["steps_equal"] and r["hist_equal"], (grid, r)
+    assert 2 * (grid - 1) - 10 < r["steps_per_ray"] < 2 * (grid - 1) + 10, r
+
+
+def test_C1_all_rays_against_oracle():
+    """BASELINE configs[0] in full: every one of the 1e5 legacy-beam rays through the 128^3 Gaussian column."""
+    from synthpy_b200 import domain as Dm, engine, legacy
+    a = bench.parse(["--workload", "C1"])
+    ne = bench.build_ne(a, "cuda")
+    dom = Dm.ScalarDomain(bench.LENGTHS, a.grid)
+    dom.external_ne(ne)
+    np.random.seed(0)
+    rays = engine.to_device(legacy.init_beam(int(a.rays), bench.BEAM_R, bench.BEAM_DIV, bench.EXTENT, "circular", "z"))
+    odom = bench.cpu_setup(ne, a)
+    r = bench.parity_check(a, dom, rays, odom, int(a.rays))
+    assert r["max_rel"] < 1e-9 and r["steps_equal"] and r["hist_equal"], r

@@ -43,7 +43,7 @@ def _worker(rank, world, port, out_path):
     tot = stats.clone()
     torch.distributed.all_reduce(tot)
     if rank == 0:
-        np.savez(out_path, a=specs[0].image.counts.cpu().numpy(), b=specs[1].image.counts.cpu().numpy(), stats=tot.cpu().numpy())
+        np.savez(out_path, a=specs[0].image.total().cpu().numpy(), b=specs[1].image.total().cpu().numpy(), stats=tot.cpu().numpy())
     torch.distributed.destroy_process_group()
 
 

