@@ -69,6 +69,9 @@ def parse(argv=None):
                     help="start the device beam this many cells further out along the probing axis (free flight outside the grid: "
                          "same physical rays, shifted fixed-step lattice)")
     ap.add_argument("--bundle", action="store_true", help="C4: one step size per 32-ray bundle instead of per ray")
+    ap.add_argument("--extra-c5", choices=["auto", "on", "off"], default="auto",
+                    help="after the timed region also run two passes of BASELINE configs[4] (1024^3, 1.25e8 rays per GPU) and "
+                         "report them under extra.c5; auto = when 8 GPUs run the default C2 workload")
     ap.add_argument("--rtol", type=float, default=1e-3)
     ap.add_argument("--atol", type=float, default=1e-6)
     a = ap.parse_args(argv)
@@ -476,6 +479,54 @@ def parity_check(a, dom, rays, odom, n, ray_offset=0, workers=None, conditioning
 
 
 # ------------------------------------------------------------------------------------------------- our arm
+def run_c5_passes(a, rank, world, barrier, passes=2):
+    """BASELINE configs[4] as a side measurement of a multi-GPU run: 1024^3 seed-3 field replicated on every GPU,
+    1.25e8 device rays per GPU, two-lens shadowgraphy, images all-reduced; one warm-up pass, ``passes`` timed (device
+    events, max over ranks).  Returns the dict printed under extra.c5."""
+    import torch
+    import torch.distributed as dist
+    from synthpy_b200 import beam as B, distributed as SD, domain as Dm, engine, propagator as P
+    c5 = parse(["--workload", "C5"])
+    ne = build_ne(c5, "cuda")
+    dom = Dm.ScalarDomain(LENGTHS, c5.grid)
+    dom.external_ne(ne)
+    dom.device_field(LWL)
+    del ne
+    dom.release_ne()
+    torch.cuda.empty_cache()
+    n_rays = int(c5.rays)
+    beam = B.Beam(n_rays * world, BEAM_R, BEAM_DIV, EXTENT, device=True, seed=2, beam_type="circular")
+    specs = make_specs(c5)
+    kw = solve_kw(c5, dom)
+
+    def one():
+        for s_ in specs:
+            s_.image.zero_()
+        st_, _ = P.solve_and_image(dom, beam, EXTENT, specs, n_rays=n_rays, ray_offset=rank * n_rays, sync=False, **kw)
+        if world > 1:
+            SD.combine_images([s_.image for s_ in specs])
+        return st_
+    st_ = one()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(passes):
+        st_ = one()
+    e1.record()
+    barrier()
+    stats = engine.stats_dict(st_)
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    tot = torch.tensor([float(stats["ray_steps"]) * passes, float(stats["rays_binned"])], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    ms = float(t.item())
+    img = int(specs[0].image.total().sum().item())
+    return {"config": workload_config(c5), "value": float(tot[0].item()) / (ms * 1e-3), "unit": "rays*steps/s", "n_gpus": world,
+            "passes": passes, "ms_per_pass": ms / passes, "rays_per_s": n_rays * world * passes / (ms * 1e-3),
+            "allreduce_check": {"sum_image": img, "sum_rays_binned_over_ranks": int(tot[1].item()), "equal": img == int(tot[1].item())}}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -589,6 +640,11 @@ def run_ours(a):
                       "distributed.combine_images(root=0) -> image read-back on rank 0", "numa_bind": numa}
         del s0_host
 
+    # ---- BASELINE configs[4] beside the headline when the whole box is there: 1e9 rays through 1024^3 over 8 GPUs
+    extra = None
+    if a.extra_c5 == "on" or (a.extra_c5 == "auto" and world == 8 and a.workload == "C2"):
+        extra = {"c5": run_c5_passes(a, rank, world, barrier)}
+
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -660,7 +716,7 @@ def run_ours(a):
             "rays_per_s": n_rays * world * a.steps / (ms * 1e-3),
             "roofline": roof, "cpu_baseline": cpu, "same_integrator": cpu["same_integrator"] if cpu else None,
             "e2e": e2e, "parity": parity, "allreduce_check": allreduce_check,
-            "gpu_launches": int(launches), "clocks": clk,
+            "gpu_launches": int(launches), "clocks": clk, "extra": extra,
             "ray_steps_per_pass_per_gpu": int(steps_per_pass), "rays_binned_last_pass": stats["rays_binned"]}
     print(json.dumps(line))
     if world > 1:

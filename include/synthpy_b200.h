@@ -180,6 +180,11 @@ int sp_image_finalize(const sp_image* img, double* H_dev, void* stream);
 #define SP_METHOD_RK45 1       /* Dormand-Prince 5(4), SciPy's controller, step size chosen PER RAY           */
 #define SP_METHOD_RK45_JOINT 2 /* the reference as shipped: ONE step size for the whole bundle from the RMS
                                   error norm over all 9N components (full_solver.py:391)                     */
+#define SP_METHOD_TSIT5 6      /* the current generation's solver: Tsitouras 5(4) per ray under diffrax's PID
+                                  controller in normalised time (src/simulator/propagator.py:533-599).  params: h =
+                                  dt0 in units of t_end, t_end = the normalisation T, rtol / atol, n_steps =
+                                  max_steps.  PARITY UNPINNED (jax / diffrax absent here): published method +
+                                  documented controller defaults.  (3-5 are internal variants.)              */
 
 #define SP_FLAG_PHASE 1      /* integrate d(phase)/dt = omega (n - 1)   (full_solver.py:342-345)             */
 #define SP_FLAG_EARLY_EXIT 2 /* stop a ray once it is outside the grid and moving away (RHS == 0 for good)   */

@@ -198,6 +198,63 @@ class Domain:
         return s, steps
 
 
+# --------------------------------------------------------------------------------------------------
+# Tsit5 + PID controller (the current generation's solver)              PARITY UNPINNED: see below
+# --------------------------------------------------------------------------------------------------
+TSIT5_C = np.array([0.0, 0.161, 0.327, 0.9, 0.9800255409045097, 1.0, 1.0])
+TSIT5_A = np.zeros((7, 7))
+TSIT5_A[1, :1] = [0.161]
+TSIT5_A[2, :2] = [-0.008480655492356989, 0.335480655492357]
+TSIT5_A[3, :3] = [2.8971530571054935, -6.359448489975075, 4.3622954328695815]
+TSIT5_A[4, :4] = [5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525]
+TSIT5_A[5, :5] = [5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383]
+TSIT5_A[6, :6] = [0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081, 2.324710524099774]
+TSIT5_B = TSIT5_A[6].copy()
+TSIT5_BT = np.array([-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995, -0.1447110071732629,
+                     0.5823571654525552, -0.45808210592918697, 0.015151515151515152])
+
+
+def solve_tsit5_per_ray(dom, s0, rtol=1.0, atol=1e-5, save_steps=2, max_steps=10000):
+    """``src/simulator/propagator.py:533-599``: every ray on its own with diffrax ``Tsit5`` under
+    ``PIDController(rtol, atol)`` in normalised time tau = t / T, T = sqrt(8) extent / c, ``dt0 = T / save_steps``
+    (tau units, as upstream writes ``(t1 - t0) * norm_factor / Nt``), ``max_steps = 10000``.
+
+    PARITY UNPINNED: jax / diffrax / equinox are not installable in the build container, so this is a restatement of
+    the published algorithm, not a recording of the library: Tsitouras' 5(4) pair (the tableau above passes the order
+    conditions, tests/test_host_misc.py) in plain 9-vector form around the reference RHS ``Domain.dsdt``, and the
+    controller diffrax documents for its defaults (pcoeff 0, icoeff 1, dcoeff 0; safety 0.9; factor limits 0.2 / 10,
+    the lower one raised to 1 after an accepted step; rms norm of err / (atol + rtol max(|y0|, |y1|))).
+    Returns (9xN state, attempted steps per ray, accepted steps per ray)."""
+    T = dom.t_end()
+    n = s0.shape[1]
+    sf = np.empty((9, n)); att = np.zeros(n, dtype=np.int64); acc = np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        y = np.array(s0[:, i], dtype=np.float64)
+        f = dom.dsdt(0.0, y.copy())
+        tau, dt = 0.0, T / save_steps
+        while tau < 1.0 and att[i] < max_steps:
+            last = tau + dt >= 1.0
+            d = 1.0 - tau if last else dt
+            h = d * T
+            K = np.zeros((7, 9)); K[0] = f
+            for s_ in range(1, 6):
+                K[s_] = dom.dsdt(0.0, y + h * (TSIT5_A[s_, :s_] @ K[:s_]))
+            yn = y + h * (TSIT5_B[:6] @ K[:6])
+            K[6] = dom.dsdt(0.0, yn)
+            err = h * (TSIT5_BT @ K)
+            en = np.sqrt(np.mean((err / (atol + rtol * np.maximum(np.abs(y), np.abs(yn)))) ** 2))
+            att[i] += 1
+            keep = en < 1.0
+            fac = 10.0 if en == 0 else min(10.0, max(1.0 if keep else 0.2, 0.9 * en ** -0.2))
+            dt = d * fac
+            if keep:
+                tau = 1.0 if last else tau + d
+                y, f = yn, K[6]
+                acc[i] += 1
+        sf[:, i] = y
+    return sf, att, acc
+
+
 class MinimalDomain:
     """Restates ``minimal_solver.ScalarDomain`` (src/solvers-legacy/minimal_solver.py:121-398), the 6-component
     generation of the solver: float64 axes, float64 normalised density clamped at ``ne_max`` critical densities

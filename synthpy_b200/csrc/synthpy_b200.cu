@@ -784,6 +784,45 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
                 rk4x_integrate<PHASE, AUX64>(A, r, cc, early, gi, n_att, ls, amp_x, pol_x);
             } else if (METHOD == SP_METHOD_RK45X) {
                 rk45x_integrate<PHASE, AUX64>(A, r, cc, early, vmask, gi, n_att, ls, amp_x, pol_x);
+            } else if (METHOD == SP_METHOD_TSIT5) {
+                // diffrax.diffeqsolve(Tsit5, PIDController) per ray in normalised time tau in [0, 1]: A.t_end = T, A.h = dt0
+                T y[7], f[7], yn[7], fn[7];
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { y[k] = r.p[k]; y[3 + k] = r.v[k]; }
+                y[6] = r.ph;
+                int touched = tsit5_f<T, PHASE, AUX64>(A.F, A.omega, y, f);
+                T tau = (T)0, dt = A.h;
+                const unsigned cap = A.n_steps > 0 ? (unsigned)A.n_steps : 10000u;
+                const T inv_n = (T)1 / (T)A.n_state;
+                bool failed = false;
+                const unsigned lanes = vmask;
+                for (;;) {
+                    bool go = (tau < (T)1) && !failed;
+                    if (go && n_att >= cap) { failed = true; ls.capped += 1; go = false; }
+                    if (!__any_sync(lanes, go)) break;
+                    if (go) {
+                        const bool last = tau + dt >= (T)1;
+                        const T d = last ? (T)1 - tau : dt;
+                        T esq;
+                        touched += tsit5_attempt<T, PHASE, AUX64>(A.F, A.omega, d * A.t_end, A.rtol, A.atol, y, f, yn, fn, esq);
+                        ++n_att;
+                        const T en = sqrt(esq * inv_n);
+                        if (!(en == en)) { failed = true; ls.capped += 1; }
+                        else {
+                            const bool keep = en < (T)1;
+                            dt = d * pid_factor<T>(en, keep);
+                            if (keep) {
+                                tau = last ? (T)1 : tau + d; ls.acc += 1;
+#pragma unroll
+                                for (int i = 0; i < 7; ++i) { y[i] = yn[i]; f[i] = fn[i]; }
+                            }
+                        }
+                    }
+                }
+                ls.evals += touched;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { r.p[k] = y[k]; r.v[k] = y[3 + k]; }
+                r.ph = y[6];
             } else if (METHOD == SP_METHOD_RK45B) {
                 // handled above (whole-warp path)
             } else if (METHOD == SP_METHOD_RK4) {
@@ -1455,7 +1494,10 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
         if (P->flags & SP_FLAG_FP32) return fail(SP_EINVAL, "joint RK45 is float64 only");
         return joint_solve(field, P, ws, s0_dev, n, E, stats_dev, st);
     }
-    if (P->method != SP_METHOD_RK4 && P->method != SP_METHOD_RK45) return fail(SP_EINVAL, "unknown method");
+    if (P->method == SP_METHOD_TSIT5) {
+        if (ext) return fail(SP_EINVAL, "tsit5 does not integrate the attenuation / Faraday channels");
+        if (!(P->h > 0) || !(P->t_end > 0)) return fail(SP_EINVAL, "tsit5 needs h = dt0 > 0 (units of t_end) and t_end > 0");
+    } else if (P->method != SP_METHOD_RK4 && P->method != SP_METHOD_RK45) return fail(SP_EINVAL, "unknown method");
     if (ext && (P->flags & SP_FLAG_BUNDLE_STEP)) return fail(SP_EINVAL, "bundle-step RK45 does not integrate the attenuation / Faraday channels");
     const bool ext_aux64 = ext && (P->flags & SP_FLAG_PHASE) && (P->flags & SP_FLAG_PHASE_F64);
 
@@ -1470,7 +1512,9 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
 
     int grid = 0, rc = 0;
     const bool bundle_step = P->method == SP_METHOD_RK45 && (P->flags & SP_FLAG_BUNDLE_STEP);
-    if (ext) rc = ext_grid(ws->sm_count, P->method == SP_METHOD_RK45, ext_aux64, grid);
+    const bool tsit = P->method == SP_METHOD_TSIT5;
+    if (tsit) rc = fp32 ? occupancy_grid<float, SP_METHOD_TSIT5>(ws->sm_count, P->flags, grid) : occupancy_grid<double, SP_METHOD_TSIT5>(ws->sm_count, P->flags, grid);
+    else if (ext) rc = ext_grid(ws->sm_count, P->method == SP_METHOD_RK45, ext_aux64, grid);
     else if (fp32) rc = (P->method == SP_METHOD_RK4) ? occupancy_grid<float, SP_METHOD_RK4>(ws->sm_count, P->flags, grid)
                         : (bundle_step ? occupancy_grid<float, SP_METHOD_RK45B>(ws->sm_count, P->flags, grid)
                                        : occupancy_grid<float, SP_METHOD_RK45>(ws->sm_count, P->flags, grid));
@@ -1527,7 +1571,13 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
         A.extent = (T)P->extent; A.stats = stats_dev; A.rk = RK4Step<T>((T)P->h);
         rc = ws_event(ws, st);
         if (rc) return rc;
-        if (fp32) {
+        if (tsit && fp32) {
+            FILL(float)
+            rc = launch_propagate<float, SP_METHOD_TSIT5>(A, E, g, st);
+        } else if (tsit) {
+            FILL(double)
+            rc = launch_propagate<double, SP_METHOD_TSIT5>(A, E, g, st);
+        } else if (fp32) {
             FILL(float)
             rc = (P->method == SP_METHOD_RK4) ? launch_propagate<float, SP_METHOD_RK4>(A, E, g, st)
                  : (bundle_step ? launch_propagate<float, SP_METHOD_RK45B>(A, E, g, st) : launch_propagate<float, SP_METHOD_RK45>(A, E, g, st));

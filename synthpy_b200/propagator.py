@@ -11,6 +11,11 @@ Integrators (``method=``):
                (src/solvers-legacy/full_solver.py:391).  Explicit s0 only.
   'rk45_bundle' the same joint controller applied per 32-ray bundle (== the legacy solver called on 32-ray chunks):
                lanes stay in lock-step, ~2.5x the throughput of 'rk45'; results depend on bundle membership.
+  'tsit5'      the current generation's solver (src/simulator/propagator.py:533-599): Tsitouras 5(4) per ray under
+               diffrax's PID controller in normalised time, dt0 = T / save_steps, max_steps = 10000; rtol / atol default
+               to upstream's shipped PIDController(rtol=1, atol=1e-5) -- pass 1e-7 / 1e-9 for the values upstream's
+               evaluation scripts use.  PARITY UNPINNED (jax / diffrax are not installable where this was built): the
+               published method and the controller's documented defaults, held to an independent NumPy restatement.
 """
 from time import time
 
@@ -29,11 +34,18 @@ def _out_axes(probing_direction, convention):
 
 
 def _params(domain, probing_depth, lwl, method, n_steps, ds, rtol, atol, precision, early_exit, phase, phase_f64,
-            sort, convention, max_steps):
+            sort, convention, max_steps, save_steps=2):
     extent = float(probing_depth)
     t_end = np.sqrt(8.0) * extent / c
     h, n = 0.0, 0
-    if method == "rk4":
+    if rtol is None:
+        rtol = 1.0 if method == "tsit5" else 1e-3              # propagator.py:557 / scipy's solve_ivp default
+    if atol is None:
+        atol = 1e-5 if method == "tsit5" else 1e-6
+    if method == "tsit5":
+        h = t_end / max(1, int(save_steps))                    # dt0 = (t1 - t0) * norm_factor / Nt with t1 - t0 = 1 (propagator.py:566)
+        n = int(max_steps or 10000)                            # propagator.py:572
+    elif method == "rk4":
         if ds is None and n_steps is None:
             ds = 0.5 * domain.cell_size()
         if ds is not None:
@@ -54,7 +66,7 @@ def _params(domain, probing_depth, lwl, method, n_steps, ds, rtol, atol, precisi
 
 def solve(s0_import, ScalarDomain, probing_depth, *, return_E=False, parallelise=True, jitted=True, save_steps=2,
           memory_debug=False, lwl=1064e-9, keep_domain=False,
-          method="rk4", n_steps=None, ds=None, rtol=1e-3, atol=1e-6, precision="fp64", early_exit=True,
+          method="rk4", n_steps=None, ds=None, rtol=None, atol=None, precision="fp64", early_exit=True,
           phase_f64=False, sort=True, axis_convention="current", max_steps=None, return_stats=False,
           return_state=False):
     """Trace rays ``s0_import`` (9,N) through ``ScalarDomain``; returns ``(rf, Jf, duration)`` like the
@@ -65,8 +77,8 @@ def solve(s0_import, ScalarDomain, probing_depth, *, return_E=False, parallelise
     ``PIDController(rtol=1, atol=1e-5)``, ``dt0 = (t1 - t0) / 2`` and ``max_steps=10000`` (propagator.py:533-599) -- a
     tolerance that lets the controller take the whole box in a handful of steps.  Here the default is fixed-step RK4 at
     half a cell (``method='rk4'``), and ``method='rk45'`` is SciPy's Dormand-Prince at 1e-3 / 1e-6 (the legacy
-    generation's solver); neither reproduces diffrax's step sequence, which cannot be pinned in this environment
-    (DESIGN.md section 6).  ``parallelise`` / ``jitted`` have no effect: there is one code path.
+    generation's solver).  ``method='tsit5'`` restates upstream's solve itself (same tableau, controller constants, dt0
+    and max_steps) but cannot be pinned against diffrax in this environment.  ``parallelise`` / ``jitted`` have no effect: there is one code path.
 
     numpy in -> numpy out; CUDA tensors in -> CUDA tensors out (no host round trip).
     With ``return_stats`` / ``return_state`` a dict with 'stats', 'sf', 'steps' is appended to the tuple."""
@@ -76,7 +88,7 @@ def solve(s0_import, ScalarDomain, probing_depth, *, return_E=False, parallelise
     phase = bool(ScalarDomain.phaseshift)
     field = ScalarDomain.device_field(lwl, phase=phase, phase_f64=phase_f64)
     P = _params(ScalarDomain, probing_depth, lwl, method, n_steps, ds, rtol, atol, precision, early_exit, phase,
-                phase_f64, sort, axis_convention, max_steps)
+                phase_f64, sort, axis_convention, max_steps, save_steps)
     torch.cuda.synchronize()
     start = time()
     out = engine.propagate(field, P, s0=s0, want_rf=True, want_jf=return_E, want_sf=return_state,
@@ -97,7 +109,7 @@ def solve(s0_import, ScalarDomain, probing_depth, *, return_E=False, parallelise
 
 
 def solve_and_image(ScalarDomain, rays, probing_depth, diagnostics, *, lwl=1064e-9, n_rays=None, ray_offset=0,
-                    method="rk4", n_steps=None, ds=None, rtol=1e-3, atol=1e-6, precision="fp64", early_exit=True,
+                    method="rk4", n_steps=None, ds=None, rtol=None, atol=None, precision="fp64", early_exit=True,
                     phase_f64=False, sort=True, axis_convention="current", max_steps=None, sync=True):
     """Fused hot path: rays -> ODE -> exit plane -> optics -> detector images, in one kernel per chunk.
 

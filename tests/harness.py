@@ -193,6 +193,16 @@ class HField:
                            C.c_int(n_state), C.c_int(cap), _p(sf), _p(att), _p(nfev))
         return sf, att, nfev
 
+    def tsit5(self, s0, T_norm, dt0, rtol=1.0, atol=1e-5, n_state=9, cap=0, aux64=None):
+        s0 = np.ascontiguousarray(s0, dtype=np.float64)
+        sf = np.empty_like(s0)
+        att = np.empty(s0.shape[1], dtype=np.uint32)
+        acc = np.empty(s0.shape[1], dtype=np.uint32)
+        self.H.lib.hh_tsit5(self.h, _p(s0), C.c_uint64(s0.shape[1]), C.c_double(T_norm), C.c_double(dt0), C.c_double(rtol),
+                            C.c_double(atol), C.c_double(self.omega), C.c_int(int(self.phase)),
+                            C.c_int(int(self.f64 if aux64 is None else aux64)), C.c_int(n_state), C.c_int(cap), _p(sf), _p(att), _p(acc))
+        return sf, att, acc
+
     def exit(self, sf, p, a, b, extent):
         sf = np.ascontiguousarray(sf, dtype=np.float64)
         rf = np.empty((4, sf.shape[1]))

@@ -228,6 +228,47 @@ extern "C" void hh_rk45(void* h, const double* s0, uint64_t n, double t_end, dou
     else rk45_t<true, true>(f, s0, n, t_end, rtol, atol, omega, n_state, cap, sf, attempts, nfev);
 }
 
+// per-ray Tsit5 + PID controller: the loop of the SP_METHOD_TSIT5 branch of k_propagate
+template <bool PH, bool A64>
+static void tsit5_t(const HostField* f, const double* s0, uint64_t n, double T_norm, double dt0, double rtol, double atol, double omega,
+                    int n_state, int cap_in, double* sf, uint32_t* attempts, uint32_t* accepted) {
+    FieldView<double> F = f->view64();
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray<double> r; load(f, s0, n, i, r);
+        double y[7], fy[7], yn[7], fn[7];
+        for (int k = 0; k < 3; ++k) { y[k] = r.p[k]; y[3 + k] = r.v[k]; }
+        y[6] = r.ph;
+        tsit5_f<double, PH, A64>(F, omega, y, fy);
+        double tau = 0.0, dt = dt0;
+        uint32_t n_att = 0, n_acc = 0;
+        const uint32_t cap = cap_in > 0 ? (uint32_t)cap_in : 10000u;
+        while (tau < 1.0 && n_att < cap) {
+            const bool last = tau + dt >= 1.0;
+            const double d = last ? 1.0 - tau : dt;
+            double esq;
+            tsit5_attempt<double, PH, A64>(F, omega, d * T_norm, rtol, atol, y, fy, yn, fn, esq);
+            ++n_att;
+            const double en = sqrt(esq / (double)n_state);
+            if (!(en == en)) break;
+            const bool keep = en < 1.0;
+            dt = d * pid_factor<double>(en, keep);
+            if (keep) { tau = last ? 1.0 : tau + d; ++n_acc; for (int k = 0; k < 7; ++k) { y[k] = yn[k]; fy[k] = fn[k]; } }
+        }
+        for (int k = 0; k < 3; ++k) { r.p[k] = y[k]; r.v[k] = y[3 + k]; }
+        r.ph = y[6];
+        store(f, sf, s0, n, i, r);
+        attempts[i] = n_att; accepted[i] = n_acc;
+    }
+}
+
+extern "C" void hh_tsit5(void* h, const double* s0, uint64_t n, double T_norm, double dt0, double rtol, double atol, double omega, int phase,
+                         int aux64, int n_state, int cap, double* sf, uint32_t* attempts, uint32_t* accepted) {
+    const HostField* f = (const HostField*)h;
+    if (!phase) tsit5_t<false, false>(f, s0, n, T_norm, dt0, rtol, atol, omega, n_state, cap, sf, attempts, accepted);
+    else if (!aux64) tsit5_t<true, false>(f, s0, n, T_norm, dt0, rtol, atol, omega, n_state, cap, sf, attempts, accepted);
+    else tsit5_t<true, true>(f, s0, n, T_norm, dt0, rtol, atol, omega, n_state, cap, sf, attempts, accepted);
+}
+
 // exit projection in the caller frame: kp/ka/kb are caller axes
 extern "C" void hh_exit(void* h, const double* sf, uint64_t n, int p, int a, int b, double extent, double* rf) {
     const HostField* f = (const HostField*)h;

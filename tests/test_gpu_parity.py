@@ -220,6 +220,30 @@ def test_rk45_per_ray(sp, golden):
     assert np.all(np.abs(rf[:, :8] - rf_conv).max(axis=1) <= 3 * np.abs(rf_ref[:, :8] - rf_conv).max(axis=1) + 1e-12)
 
 
+def test_tsit5_pid_flavour(sp, golden):
+    """method='tsit5': the current generation's solve (diffrax Tsit5 + PIDController in normalised time, dt0 = T / 2,
+    max_steps 10000; src/simulator/propagator.py:533-599) through the public `solve`.  PARITY UNPINNED (no jax / diffrax
+    here): held to the oracle's independent NumPy restatement of the published method -- same number of attempted steps
+    per ray and exit rays to 1e-9 at upstream's shipped controller setting (rtol 1, atol 1e-5) and to 1e-7 at 1e-3 / 1e-6."""
+    from synthpy_b200 import domain as Dm, propagator as P
+    g = golden("g2_expcos")
+    lwl, ext = float(g["lwl"]), float(g["extent"])
+    dom = Dm.ScalarDomain([10e-3, 10e-3, 20e-3], [40, 36, 48], phaseshift=True)
+    dom.external_ne(g["ne"])
+    o = O.Domain(g["x"], g["y"], g["z"], ext, phaseshift=True)
+    o.external_ne(g["ne"])
+    o.calc_dndr(lwl)
+    s0 = g["s0"][:, :40]
+    for kw, tol in (({}, 1e-9), (dict(rtol=1e-3, atol=1e-6), 1e-7)):
+        rf, Jf, _, ex = P.solve(s0, dom, ext, lwl=lwl, method="tsit5", return_E=True, return_state=True, phase_f64=True,
+                                axis_convention="legacy", **kw)
+        sf_o, att_o, _ = O.solve_tsit5_per_ray(o, s0, kw.get("rtol", 1.0), kw.get("atol", 1e-5))
+        assert np.array_equal(ex["steps"].astype(np.int64), att_o)
+        assert rel_err(rf, O.ray_to_jones(sf_o, ext)[0], floor=1e-6) < 100 * tol
+        assert np.max(np.abs(ex["sf"][:3] - sf_o[:3])) < tol * ext and np.max(np.abs(ex["sf"][3:6] - sf_o[3:6])) < tol * C_LIGHT
+    assert ex["stats"]["rays_capped"] == 0
+
+
 def test_rk45_bundle_is_the_shipped_solver_on_32_ray_chunks(sp, golden):
     """method='rk45_bundle': one step size per 32-ray bundle == full_solver.ScalarDomain.solve called on 32-ray chunks
     (the reference's own drivers chunk their rays).  With sort=False bundles are consecutive rays."""
