@@ -672,7 +672,7 @@ def run_ours(a):
                                 "frac_of_nominal_8TBps": hbm_alg / 8000.0 if hbm_alg else None,
                                 "bytes_per_ray_step": gather_b, "peak_source": peak_src,
                                 "note": "SURVEY.md 8d gather bytes over the HBM copy peak; gathers are served from registers / L1 / L2 "
-                                        "(one fetch per cell face, not per evaluation), so this exceeds 1 and is NOT the bound"},
+                                        "(one fetch per cell, not per evaluation), so this exceeds 1 and is NOT the bound"},
             "dram_compulsory_bytes_per_launch": 16 * a.grid ** 3,
             "note": "achieved = algorithmic FP64 flops per ray.step (DESIGN.md section 3) x ray.steps per launch / event-timed launch "
                     "duration; frac < 1 is what reload divergence, address / control instructions and latency cost"}

@@ -31,24 +31,28 @@ def main():
     ap.add_argument("--max-steps", type=int, default=200000,
                     help="attempt cap per ray: below the float64 noise floor (rtol 1e-9) a few rays collapse to the minimum step, "
                          "exactly as solve_ivp would; the cap bounds the time the rest of their warp waits")
+    ap.add_argument("--reps", type=int, default=2, help="passes per setting (the last one is timed); 1 for the 1e8-ray runs, "
+                    "whose kernels last seconds to minutes and need no warm-up")
+    ap.add_argument("--tolerances", default=None, help="comma-separated subset of sweep indices 0..3")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     n = int(a.rays)
-    ne = bench.build_ne(a.grid, "cuda")
+    ne = bench.build_ne(bench.parse(["--workload", "C4", "--grid", str(a.grid)]), "cuda")
     dom = Dm.ScalarDomain(bench.LENGTHS, a.grid)
     dom.external_ne(ne)
     dom.device_field(bench.LWL)
     del ne
     beam = B.Beam(n, bench.BEAM_R, bench.BEAM_DIV, bench.EXTENT, device=True, seed=2, beam_type="circular")
     rows, images = [], []
-    for rtol, atol in [(None, None)] + SWEEP:              # first row: the fixed-step production mode, for comparison
+    sweep = SWEEP if a.tolerances is None else [SWEEP[int(i)] for i in a.tolerances.split(",")]
+    for rtol, atol in [(None, None)] + sweep:              # first row: the fixed-step production mode, for comparison
         specs = [D.spec("refracto_incoherent", bin_scale=a.bin_scale),
                  D.spec("schlieren_knife", bin_scale=a.bin_scale, offset=0.1, axis=2, direction=1)]
         if rtol is None:
             kw = dict(lwl=bench.LWL, method="rk4", ds=0.5 * dom.cell_size())
         else:
             kw = dict(lwl=bench.LWL, method="rk45_bundle" if a.bundle else "rk45", rtol=rtol, atol=atol, max_steps=a.max_steps)
-        for rep in range(2):                              # first pass warms caches / clocks, second is timed
+        for rep in range(max(1, a.reps)):                 # earlier passes warm caches / clocks, the last is timed
             for s in specs:
                 s.image.zero_()
             engine.propagate_kernel_ms()

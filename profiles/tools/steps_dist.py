@@ -4,7 +4,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 import bench
 from synthpy_b200 import engine as E, _lib as L
 grid=512
-ne=bench.build_ne(grid,'cuda')
+ne=bench.build_ne(bench.parse(['--grid',str(grid)]),'cuda')
 c=299792458.0; lwl=1064e-9; om=2*np.pi*c/lwl
 axes=[np.float32(np.linspace(-l/2,l/2,grid)) for l in bench.LENGTHS]
 fld=E.DeviceField.from_ne(ne, axes[0], axes[1], axes[2], om, march_axis=2)

@@ -242,6 +242,19 @@ template <typename T> SP_HD bool locate(const AxisTab<T>& A, T x, int& i) {
     return true;
 }
 
+// Uniform first guess of the cell index (clipped to [0, n-2]); right on float32-rounded linspace axes except within
+// rounding of a node, and always checked against the table entries it points at.
+template <typename T> SP_HD int guess_cell(const AxisTab<T>& A, T x) {
+    const int k = floor_to_int((x - A.g0) * A.inv_d);
+    return k < 0 ? 0 : (k > A.n - 2 ? A.n - 2 : k);
+}
+// locate()'s acceptance of cell k given its table entry, for a point already known to satisfy lo <= x <= hi:
+// g[k] <= x < g[k+1], with x == hi belonging to the last cell.  (A NaN fails here and is sorted out by the exact search.)
+template <typename T> SP_HD bool cell_holds(const AxisTab<T>& A, T x, int k, T g_k, T g_k1) {
+    (void)k;
+    return x >= g_k && (x < g_k1 || x >= A.hi);
+}
+
 // Per-ray register cache of the cell the ray is in.  A ray takes ~8 RHS evaluations per cell (two RK4 steps
 // of four stages), so the 8 corner reads, the float32->float64 conversions and the axis-table lookups are
 // done once per cell instead of once per evaluation; ncu on the uncached kernel showed the L1 data pipe
@@ -399,17 +412,6 @@ SP_HD bool rhs(const FieldView<T>& F, CellCache<T, PHASE>& cc, T pu, T pv, T pw,
 // bytes of spills.  Here every evaluation runs the identical straight-line sequence (bounds test, exact cell search on
 // the axis tables, eight 16-byte corner reads, the reference's sum over corners of value x weight product), so the
 // lanes of a warp stay converged whatever cells they are in.
-// Uniform first guess of the cell index (clipped to [0, n-2]); right on float32-rounded linspace axes except within
-// rounding of a node, and always checked against the table entries it points at.
-template <typename T> SP_HD int guess_cell(const AxisTab<T>& A, T x) {
-    const int k = floor_to_int((x - A.g0) * A.inv_d);
-    return k < 0 ? 0 : (k > A.n - 2 ? A.n - 2 : k);
-}
-// locate()'s acceptance of cell k given its table entry: g[k] <= x < g[k+1], open at the clipped ends, NaN accepted.
-template <typename T> SP_HD bool cell_holds(const AxisTab<T>& A, T x, int k, T g_k, T g_k1) {
-    return !(x == x) || ((k == 0 || x >= g_k) && (k == A.n - 2 || x < g_k1));
-}
-
 template <typename T, bool PHASE, bool AUX64>
 SP_HD bool rhs_direct(const FieldView<T>& F, T pu, T pv, T pw, T& au, T& av, T& aw, T& nm1) {
     au = av = aw = nm1 = (T)0;
@@ -810,14 +812,17 @@ SP_HD int dp5_attempt(const FieldView<T>& F, T omega, T h, T rtol, T atol, const
     return dp5_attempt<T, PHASE, AUX64, StageRegs<T> >(F, omega, h, rtol, atol, r, k1, rn, k7, err_sq, S);
 }
 
-// Step-size factor after an attempt with RMS error norm `en` (rk.py:_step_impl).
+// Step-size factor after an attempt with RMS error norm `en` (rk.py:_step_impl).  One pow() for both outcomes: the
+// accepting and the rejecting lanes of a warp would otherwise each run their own copy of it (ncu: pow() executed 1.9x
+// per attempt at 13 of 32 lanes, 12 % of the adaptive kernel's instructions).
 template <typename T> SP_HD T dp5_factor(T en, bool accepted, bool rejected_before) {
+    const T g = (en == (T)0) ? (T)DP::MAX_FACTOR : (T)DP::SAFETY * pow(en, (T)-0.2);
     if (accepted) {
-        T f = (en == (T)0) ? (T)DP::MAX_FACTOR : fmin((T)DP::MAX_FACTOR, (T)DP::SAFETY * pow(en, (T)-0.2));
+        T f = fmin((T)DP::MAX_FACTOR, g);
         if (rejected_before) f = fmin((T)1, f);
         return f;
     }
-    return fmax((T)DP::MIN_FACTOR, (T)DP::SAFETY * pow(en, (T)-0.2));
+    return fmax((T)DP::MIN_FACTOR, g);
 }
 
 // Hairer's initial step as coded in scipy/integrate/_ivp/common.py::select_initial_step (order = 4), with

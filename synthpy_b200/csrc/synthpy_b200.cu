@@ -335,7 +335,7 @@ extern "C" int sp_field_export_gradients(const sp_field* f, float* gx_dev, float
 #define SP_RK4F_MIN_BLOCKS 1
 #endif
 #ifndef SP_RK45_MIN_BLOCKS
-#define SP_RK45_MIN_BLOCKS 3
+#define SP_RK45_MIN_BLOCKS 4
 #endif
 #ifndef SP_RK4_MIN_BLOCKS
 #define SP_RK4_MIN_BLOCKS 4
@@ -872,13 +872,11 @@ __global__ void __launch_bounds__(128, (METHOD == SP_METHOD_RK4 && sizeof(T) == 
                         ++n_att;
                         const T en = sqrt(esq * inv_n);
                         if (!(en == en)) { failed = true; ls.capped += 1; }          // NaN state: solve_ivp would never return
-                        else if (en < (T)1) {
-                            h_abs *= dp5_factor<T>(en, true, rejected);
-                            t = t_new; r = rn; f = fn; ls.acc += 1;
-                            fresh = true;
-                        } else {
-                            h_abs *= dp5_factor<T>(en, false, rejected);
-                            rejected = true;
+                        else {
+                            const bool acc_ = en < (T)1;
+                            h_abs *= dp5_factor<T>(en, acc_, rejected);         // one call: the lanes stay converged through pow()
+                            if (acc_) { t = t_new; r = rn; f = fn; ls.acc += 1; fresh = true; }
+                            else rejected = true;
                         }
                     }
                 }

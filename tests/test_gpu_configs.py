@@ -148,7 +148,7 @@ def test_field_generator_on_device(mods, golden):
     assert np.max(np.abs(ne.cpu().numpy() - g["ne"])) < 1e-6 * np.abs(g["ne"]).max()
     a = FG.turbulent_ne(32, noise="torch", seed=5, device="cuda").cpu()
     b = FG.turbulent_ne(32, noise="torch", seed=5, device="cpu")
-    assert float((a - b).abs().max()) < 1e-9 * float(b.abs().max())
+    assert float((a - b).abs().max()) < 1e-6 * float(b.abs().max())      # float32 |k| (gaussian3D.py:240): sqrt differs by an ulp between cuFFT box and host
     # spectrum of the C2 field: f = (ne - 1e25) / 9e24, extent 5 (mm), res 256 -> dx = 5 / 256
     n, res, extent = 512, 256, 5.0
     f = (FG.turbulent_ne(res, noise="torch", seed=1, device="cuda") - 1e25) / 9e24
