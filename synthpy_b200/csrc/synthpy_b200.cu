@@ -527,18 +527,78 @@ __global__ void k_sort_scatter(const uint32_t* __restrict__ keys, uint32_t* __re
 }
 
 // The scatter above fills each key's segment in atomic (i.e. arbitrary) order; sorting every segment by ray index
-// makes the bundle order -- and with it bundle-step results and the order of float64 interferogram sums within a
-// warp -- reproducible from run to run.  Segments are short (rays per cell column), one thread each.
-__global__ void k_sort_fix(const uint32_t* __restrict__ seg_end, uint32_t* __restrict__ order, uint32_t n_keys) {
+// makes the bundle order -- and with it the membership of the bundles of the bundle-step mode -- reproducible from run
+// to run.  Segments are normally short (rays per cell column): one thread each, insertion sort.  Segments longer than
+// SP_LONG_SEGMENT (a pencil beam inside one column, or many rays on a coarse grid) are listed and sorted by
+// k_sort_fix_long below.
+#define SP_LONG_SEGMENT 2048u
+__global__ void k_sort_fix(const uint32_t* __restrict__ seg_end, uint32_t* __restrict__ order, uint32_t n_keys,
+                           uint32_t* __restrict__ long_list, uint32_t* __restrict__ long_count) {
     const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
     if (key >= n_keys) return;
     const uint32_t b = key ? seg_end[key - 1] : 0u, e = seg_end[key];
-    if (e - b > 2048u) return;        // degenerate beams (everything in one column): keep the arbitrary order, stay O(n)
+    if (e - b > SP_LONG_SEGMENT) { long_list[atomicAdd(long_count, 1u)] = key; return; }
     for (uint32_t i = b + 1; i < e; ++i) {
         const uint32_t v = order[i];
         uint32_t j = i;
         while (j > b && order[j - 1] > v) { order[j] = order[j - 1]; --j; }
         order[j] = v;
+    }
+}
+
+// Long segments: one 256-thread block per listed segment runs a stable LSD radix sort of the ray indices (8-bit digits,
+// tiles of 256 elements taken in order; ranks inside a tile from __match_any_sync per warp + an 8 x 256 table of warp
+// counts), ping-ponging between `order` and the same range of `scratch` (the key array, free once the scatter has run).
+// Four passes cover 32-bit indices and leave the result in `order`.  Not a throughput path: it exists so that results
+// that depend on bundle membership are reproducible for degenerate beams too.
+__global__ void __launch_bounds__(256) k_sort_fix_long(const uint32_t* __restrict__ seg_end, uint32_t* __restrict__ order,
+                                                       uint32_t* __restrict__ scratch, const uint32_t* __restrict__ long_list,
+                                                       const uint32_t* __restrict__ long_count) {
+    __shared__ uint32_t base[256];
+    __shared__ uint32_t wcnt[8][256];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (uint32_t j = blockIdx.x; j < *long_count; j += gridDim.x) {
+        const uint32_t key = long_list[j];
+        const uint32_t b = key ? seg_end[key - 1] : 0u, L = seg_end[key] - b;
+        uint32_t* src = order + b;
+        uint32_t* dst = scratch + b;
+        for (int pass = 0; pass < 4; ++pass) {
+            const int shift = 8 * pass;
+            base[threadIdx.x] = 0u;
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < L; i += 256) atomicAdd(&base[(src[i] >> shift) & 255u], 1u);
+            __syncthreads();
+            if (threadIdx.x == 0) {                                   // exclusive scan of 256 counts
+                uint32_t run = 0;
+                for (int d = 0; d < 256; ++d) { const uint32_t c = base[d]; base[d] = run; run += c; }
+            }
+            __syncthreads();
+            for (uint32_t t0 = 0; t0 < L; t0 += 256) {
+                const uint32_t i = t0 + threadIdx.x;
+                const bool have = i < L;
+                const uint32_t v = have ? src[i] : 0u;
+                const uint32_t d = have ? ((v >> shift) & 255u) : 256u;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) wcnt[w][threadIdx.x] = 0u;
+                __syncthreads();
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                const uint32_t rank = __popc(peers & ((1u << lane) - 1u));
+                if (have && rank == 0) wcnt[warp][d] = __popc(peers);
+                __syncthreads();
+                if (have) {
+                    uint32_t off = base[d] + rank;
+                    for (int w = 0; w < warp; ++w) off += wcnt[w][d];
+                    dst[off] = v;
+                }
+                __syncthreads();
+                uint32_t add = 0;
+#pragma unroll
+                for (int w = 0; w < 8; ++w) add += wcnt[w][threadIdx.x];
+                base[threadIdx.x] += add;
+                __syncthreads();
+            }
+            uint32_t* t = src; src = dst; dst = t;
+        }
     }
 }
 
@@ -1284,7 +1344,7 @@ __global__ void k_beam(BeamSpec B, uint64_t off, uint64_t n, double* __restrict_
 
 // ---------------------------------------------------------------------------------------------- workspace
 struct sp_workspace {
-    uint32_t *keys = nullptr, *order = nullptr, *hist = nullptr, *tile_sums = nullptr;
+    uint32_t *keys = nullptr, *order = nullptr, *hist = nullptr, *tile_sums = nullptr, *long_list = nullptr, *long_count = nullptr;
     size_t cap_rays = 0, cap_keys = 0;
     unsigned long long* cursor = nullptr;
     double* joint = nullptr; size_t joint_cap = 0;
@@ -1363,13 +1423,15 @@ extern "C" int sp_workspace_create(sp_workspace** out) {
     CU(cudaDeviceGetAttribute(&w->sm_count, cudaDevAttrMultiProcessorCount, dev));
     CU(cudaMalloc(&w->cursor, sizeof(unsigned long long)));
     CU(cudaMalloc(&w->tile_sums, 1024 * sizeof(uint32_t)));
+    CU(cudaMalloc(&w->long_count, sizeof(uint32_t)));
     CU(cudaMallocHost(&w->host_pair, 2 * sizeof(double)));
     *out = w;
     return SP_OK;
 }
 extern "C" int sp_workspace_destroy(sp_workspace* w) {
     if (!w) return SP_OK;
-    cudaFree(w->keys); cudaFree(w->order); cudaFree(w->hist); cudaFree(w->tile_sums); cudaFree(w->cursor); cudaFree(w->joint);
+    cudaFree(w->keys); cudaFree(w->order); cudaFree(w->hist); cudaFree(w->tile_sums); cudaFree(w->long_list); cudaFree(w->long_count);
+    cudaFree(w->cursor); cudaFree(w->joint);
     cudaFreeHost(w->host_pair);
     for (cudaEvent_t e : w->ev) cudaEventDestroy(e);
     delete w;
@@ -1378,9 +1440,10 @@ extern "C" int sp_workspace_destroy(sp_workspace* w) {
 
 static int ws_reserve_sort(sp_workspace* w, size_t rays, size_t keys) {
     if (rays > w->cap_rays) {
-        cudaFree(w->keys); cudaFree(w->order); w->keys = w->order = nullptr; w->cap_rays = 0;
+        cudaFree(w->keys); cudaFree(w->order); cudaFree(w->long_list); w->keys = w->order = w->long_list = nullptr; w->cap_rays = 0;
         CU(cudaMalloc(&w->keys, rays * sizeof(uint32_t)));
         CU(cudaMalloc(&w->order, rays * sizeof(uint32_t)));
+        CU(cudaMalloc(&w->long_list, (rays / SP_LONG_SEGMENT + 2) * sizeof(uint32_t)));
         w->cap_rays = rays;
     }
     if (keys > w->cap_keys) {
@@ -1547,7 +1610,10 @@ extern "C" int sp_propagate(const sp_field* field, const sp_params* P, sp_worksp
             }
             k_sort_scatter<<<(cn + 255) / 256, 256, 0, st>>>(ws->keys, ws->hist, ws->order, cn);
             LAUNCH_CHECK();
-            k_sort_fix<<<(n_keys + 255) / 256, 256, 0, st>>>(ws->hist, ws->order, n_keys);   // hist now holds segment ends
+            CU(cudaMemsetAsync(ws->long_count, 0, sizeof(uint32_t), st));
+            k_sort_fix<<<(n_keys + 255) / 256, 256, 0, st>>>(ws->hist, ws->order, n_keys, ws->long_list, ws->long_count);   // hist now holds segment ends
+            LAUNCH_CHECK();
+            k_sort_fix_long<<<ws->sm_count, 256, 0, st>>>(ws->hist, ws->order, ws->keys, ws->long_list, ws->long_count);
             LAUNCH_CHECK();
             order = ws->order;
         }

@@ -220,6 +220,30 @@ def test_rk45_per_ray(sp, golden):
     assert np.all(np.abs(rf[:, :8] - rf_conv).max(axis=1) <= 3 * np.abs(rf_ref[:, :8] - rf_conv).max(axis=1) + 1e-12)
 
 
+def test_degenerate_beam_long_key_segments(sp, golden):
+    """A pencil beam: 40 000 rays inside ONE cell column, i.e. one sort key with a segment far longer than the
+    insertion-sort limit (k_sort_fix_long: stable block radix sort).  The ray order must be a permutation (sorted and
+    unsorted images identical) and deterministic (the bundle-step mode, whose results depend on which 32 rays share a
+    bundle, is bit-reproducible from run to run and equals the unsorted = natural-order run)."""
+    from synthpy_b200 import beam as B, diagnostics as D, domain as Dm, propagator as P
+    g = golden("g2_expcos")
+    lwl, ext = float(g["lwl"]), float(g["extent"])
+    dom = Dm.ScalarDomain([10e-3, 10e-3, 20e-3], [40, 36, 48])
+    dom.external_ne(g["ne"])
+    beam = B.Beam(40000, 2e-5, 1e-3, ext, device=True, seed=4)                # radius 20 um << cell size 256 um
+    s0 = beam.materialise()
+    def image(**kw):
+        sp_ = D.spec("shadow_single", bin_scale=8)
+        P.solve_and_image(dom, beam, ext, [sp_], lwl=lwl, **kw)
+        return sp_.image.counts.clone()
+    a, b = image(), image(sort=False)
+    assert torch.equal(a, b) and int(a.sum()) > 0
+    r1 = P.solve(s0, dom, ext, lwl=lwl, method="rk45_bundle")[0]
+    r2 = P.solve(s0, dom, ext, lwl=lwl, method="rk45_bundle")[0]
+    r3 = P.solve(s0, dom, ext, lwl=lwl, method="rk45_bundle", sort=False)[0]
+    assert torch.equal(r1, r2) and torch.equal(r1, r3)       # one key: sorted by ray index == natural order
+
+
 def test_tsit5_pid_flavour(sp, golden):
     """method='tsit5': the current generation's solve (diffrax Tsit5 + PIDController in normalised time, dt0 = T / 2,
     max_steps 10000; src/simulator/propagator.py:533-599) through the public `solve`.  PARITY UNPINNED (no jax / diffrax
