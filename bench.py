@@ -478,6 +478,38 @@ def parity_check(a, dom, rays, odom, n, ray_offset=0, workers=None, conditioning
     return out
 
 
+def attach_ncu_static(roof, a, n_rays):
+    """Static ncu evidence of the same command (profiles/r2_<workload>_k_propagate_ncu_full.json, written by
+    profiles/tools/ncu_extract.py --stamp): attached to the roofline only while the hash of the kernel sources equals the
+    one stored in the capture, and its DRAM bytes reported as ``traffic`` only when the profiled launch had as many rays as
+    a launch of this run -- so stale or mismatched evidence cannot ride on a changed kernel."""
+    wd = workload_defaults(a.workload)
+    ncu_file = os.path.join(ROOT, "profiles", f"r2_{a.workload.lower()}_k_propagate_ncu_full.json")
+    if os.path.exists(ncu_file) and a.grid == wd[0] and not a.fp32 and not a.bundle:
+        try:                                  # static evidence of the same command, attached only while the kernel source is unchanged
+            m = json.load(open(ncu_file))
+            if m.get("source_sha16") == source_sha16():
+                unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
+                g = lambda k: float(str(m[k][0]).replace(",", "")) if k in m else None
+                gb = lambda k: g(k) * unit.get(m[k][1], 1.0) if k in m else 0.0
+                cap_rays = m.get("rays_per_launch")
+                chunk = min(n_rays, 1 << 25)                                         # sp_propagate launches chunks of 2^25 rays
+                if cap_rays == chunk:                                                # traffic is per launch: only a same-size launch counts
+                    roof["traffic"] = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum") or None
+                roof["ncu_static"] = {"source": os.path.relpath(ncu_file, ROOT), "source_sha16": m["source_sha16"],
+                                      "rays_of_profiled_launch": cap_rays,
+                                      "dram_bytes_of_profiled_launch": gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum"),
+                                      "fp64_pipe_pct": g("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                                      "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                                      "l2_hit_pct": g("lts__t_sector_hit_rate.pct"), "l1_hit_pct": g("l1tex__t_sector_hit_rate.pct"),
+                                      "dram_throughput_pct": g("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                                      "lanes_per_instruction": g("smsp__thread_inst_executed_per_inst_executed.ratio")}
+            else:
+                roof["ncu_static"] = {"stale": True, "source": os.path.relpath(ncu_file, ROOT)}
+        except Exception:
+            pass
+
+
 # ------------------------------------------------------------------------------------------------- our arm
 def run_c5_passes(a, rank, world, barrier, passes=2):
     """BASELINE configs[4] as a side measurement of a multi-GPU run: 1024^3 seed-3 field replicated on every GPU,
@@ -692,31 +724,7 @@ def run_ours(a):
                     "duration; frac < 1 is what reload divergence, address / control instructions and latency cost"}
     if a.fp32:
         roof["fp32_note"] = "fp32 mode: the same operation count runs on the FP32 pipe; the FP64 peak is kept as the common denominator"
-    wd = workload_defaults(a.workload)
-    ncu_file = os.path.join(ROOT, "profiles", f"r2_{a.workload.lower()}_k_propagate_ncu_full.json")
-    if os.path.exists(ncu_file) and a.grid == wd[0] and not a.fp32 and not a.bundle:
-        try:                                  # static evidence of the same command, attached only while the kernel source is unchanged
-            m = json.load(open(ncu_file))
-            if m.get("source_sha16") == source_sha16():
-                unit = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
-                g = lambda k: float(str(m[k][0]).replace(",", "")) if k in m else None
-                gb = lambda k: g(k) * unit.get(m[k][1], 1.0) if k in m else 0.0
-                cap_rays = m.get("rays_per_launch")
-                chunk = min(n_rays, 1 << 25)                                         # sp_propagate launches chunks of 2^25 rays
-                if cap_rays == chunk:                                                # traffic is per launch: only a same-size launch counts
-                    roof["traffic"] = gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum") or None
-                roof["ncu_static"] = {"source": os.path.relpath(ncu_file, ROOT), "source_sha16": m["source_sha16"],
-                                      "rays_of_profiled_launch": cap_rays,
-                                      "dram_bytes_of_profiled_launch": gb("dram__bytes_read.sum") + gb("dram__bytes_write.sum"),
-                                      "fp64_pipe_pct": g("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
-                                      "issue_active_pct": g("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                                      "l2_hit_pct": g("lts__t_sector_hit_rate.pct"), "l1_hit_pct": g("l1tex__t_sector_hit_rate.pct"),
-                                      "dram_throughput_pct": g("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
-                                      "lanes_per_instruction": g("smsp__thread_inst_executed_per_inst_executed.ratio")}
-            else:
-                roof["ncu_static"] = {"stale": True, "source": os.path.relpath(ncu_file, ROOT)}
-        except Exception:
-            pass
+    attach_ncu_static(roof, a, n_rays)
     # ---- CPU legs (rank 0): baseline timing and the oracle parity of the benchmarked configuration
     cpu, parity = None, None
     want_cpu = world == 1 and not a.no_cpu_baseline

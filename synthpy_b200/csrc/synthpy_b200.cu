@@ -381,7 +381,13 @@ static int channel_to_dev(const sp_channel* c, ChannelDev& d) {
 // which warps, kernels, chunks or GPUs contribute -- run-to-run and partition-to-partition identical, like the
 // counts -- at a quantisation of 2^-40 per contribution (|E| <= amp + 1 ~ 2; range +-2^23 per pixel).
 // Returns 1 if binned.
-__device__ __forceinline__ long long to_plane_fixed(double v) { return __double2ll_rn(v * (double)(1ll << SP_PLANE_FRAC_BITS)); }
+// (a NaN amplitude contributes nothing -- the reference would poison the pixel with NaN -- and values beyond the
+// per-contribution range +-2^22 saturate instead of wrapping)
+__device__ __forceinline__ long long to_plane_fixed(double v) {
+    const double lim = 4194304.0;
+    v = (v == v) ? fmin(fmax(v, -lim), lim) : 0.0;
+    return __double2ll_rn(v * (double)(1ll << SP_PLANE_FRAC_BITS));
+}
 
 __device__ __forceinline__ int bin_ray(const ChannelDev& ch, const DetRay& d, bool active) {
     int pix = -1;

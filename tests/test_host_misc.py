@@ -134,3 +134,28 @@ def test_beam_types_rect_trackers_and_even():
     assert r[0] == 0 and abs(r.max() - 1e-3) < 1e-15 and np.all(e.s0[2] == -5e-3) and np.all(e.s0[6] == 1.0)
     rings = np.round(r / 1e-3 * n_c).astype(int)
     assert all((rings == i).sum() == 6 * i for i in range(1, n_c + 1))
+
+
+def test_bench_ncu_evidence_is_tied_to_the_kernel_source(tmp_path, monkeypatch):
+    """static ncu numbers in the bench line must not survive a kernel change.  attach_ncu_static accepts a
+    capture only while its stored hash equals the hash of ray_core.h + synthpy_b200.cu, and reports its DRAM bytes as
+    `traffic` only for a launch of the same number of rays."""
+    import bench
+    prof = tmp_path / "profiles"
+    prof.mkdir()
+    cap = {"source_sha16": bench.source_sha16(), "rays_per_launch": 10000000, "dram__bytes_read.sum": ["2.5", "Gbyte"],
+           "dram__bytes_write.sum": ["120", "Mbyte"], "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active": ["53.1", "%"]}
+    (prof / "r2_c2_k_propagate_ncu_full.json").write_text(json.dumps(cap))
+    monkeypatch.setattr(bench, "ROOT", str(tmp_path))
+    monkeypatch.setattr(bench, "source_sha16", lambda: cap["source_sha16"])
+    a = bench.parse([])
+    roof = {"traffic": None}
+    bench.attach_ncu_static(roof, a, 10000000)
+    assert abs(roof["traffic"] - 2.62e9) < 1e3 and roof["ncu_static"]["fp64_pipe_pct"] == 53.1
+    roof = {"traffic": None}
+    bench.attach_ncu_static(roof, a, 2000000)                        # another launch size: evidence kept, traffic not claimed
+    assert roof["traffic"] is None and roof["ncu_static"]["rays_of_profiled_launch"] == 10000000
+    monkeypatch.setattr(bench, "source_sha16", lambda: "0" * 16)      # the kernel source changed
+    roof = {"traffic": None}
+    bench.attach_ncu_static(roof, a, 10000000)
+    assert roof["traffic"] is None and roof["ncu_static"] == {"stale": True, "source": os.path.join("profiles", "r2_c2_k_propagate_ncu_full.json")}
