@@ -400,6 +400,8 @@ def parity_check(a, dom, rays, odom, n, ray_offset=0, workers=None, conditioning
     from oracle import parallel as OP, synthpy_oracle as O
     from synthpy_b200 import propagator as P
     kw = solve_kw(a, dom)
+    if a.workload == "C4":
+        kw["early_exit"] = False       # solve_ivp integrates to t_end: keep the free-flight attempts so that step counts are comparable
     if hasattr(rays, "spec"):
         s0 = rays.materialise(n, ray_offset)
     else:

@@ -38,7 +38,7 @@ def shard(n_total, rank, world):
 def combine_images(images, root=None):
     """Sum detector images over ranks: to every rank (``root=None``, one all-reduce per image) or to ``root`` only (one
     reduce, the reference's ``comm.reduce(H, root=0, op=MPI.SUM)``).  uint64 counts (held as int64 tensors) are exact and
-    order-independent; interferogram planes are float64 sums (order-dependent at 1e-16, inside the 1e-3 L1 budget).
+    order-independent, and so are interferogram planes: int64 fixed-point sums (2^-40 units, include/synthpy_b200.h).
 
     The sum is taken OUT OF PLACE for ``engine.ImageBuffer``s: the per-rank accumulator that ``solve_and_image`` keeps
     adding to is left alone and the global image is attached with ``set_global`` (``ImageBuffer.result()`` then returns
