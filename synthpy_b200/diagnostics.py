@@ -228,7 +228,7 @@ class Refractometry(Diagnostic):
     def refractogram(self, bin_scale=1, pix_x=3448, pix_y=2574, clear_mem=False):   # diagnostics.py:526-527
         self.histogram_legacy(bin_scale=bin_scale, pix_x=pix_x, pix_y=pix_y, clear_mem=clear_mem)
 
-    def fresnel_solve(self, bin_scale=1, pix_x=3448, pix_y=2574, clear_mem=False):
+    def fresnel_solve(self, bin_scale=1, pix_x=3448, pix_y=2574, clear_mem=False, gridding="triangulation"):
         """diagnostics.py:529-552: the exit rays' amplitude and phase (constructor arguments ``amp``, ``phase``) are
         interpolated onto the grid ``x`` x ``y`` (lengths ``x_l``, ``y_l``) and carried over ``3L/4 - focal_plane`` by the
         Fresnel integral (``fresnel_integral.propagate``); ``self.Jf`` becomes that field, as upstream.  Upstream then
@@ -238,7 +238,7 @@ class Refractometry(Diagnostic):
         if any(v is None for v in (self.x, self.y, self.x_l, self.y_l, self.amp, self.phase)):
             raise ValueError("fresnel_solve needs x, y, x_l, y_l, amp and phase (constructor keyword arguments)")
         U = fresnel_integral.propagate(self.wavelength, self.x, self.y, self.x_l, self.y_l, m_to_mm(self._rf_m), self.amp,
-                                       self.phase, 3 * self.L / 4 - self.focal_plane)
+                                       self.phase, 3 * self.L / 4 - self.focal_plane, gridding=gridding)
         self._Jf = U
         self.H = self._view(U.abs())
         if clear_mem:

@@ -57,6 +57,37 @@ def scatter_to_grid(px, py, values, x, y, fill_value=0.0, simplices=None):
     return out
 
 
+def bin_to_grid(px, py, amplitudes, phases, x, y):
+    """Triangulation-free alternative to ``scatter_to_grid`` for dense ray bundles: U0 on the grid ``x`` x ``y`` as the
+    COHERENT MEAN of amp exp(-i phase) over the rays whose nearest node it is (empty nodes: 0).  The sums are taken by
+    the library's own detector-binning kernel (``sp_optics_image`` with interferogram accumulation: exact int64 fixed-
+    point sums, order-independent), so nothing leaves the GPU and no Qhull call is made -- the host triangulation is
+    1.3 s per 3e5 rays against 11 ms for the whole device step.  This is a different estimator
+    from upstream's piecewise-linear interpolation (it converges to the same field as the ray density grows; see
+    tests/test_gpu_parity.py::test_fresnel_binned_gridding); it is offered as ``propagate(..., gridding='binned')`` and
+    is not what parity with the reference is claimed for.  ``x`` and ``y`` must be uniformly spaced.
+    Returns (U0 complex128 (len(y), len(x)), rays per node int64)."""
+    engine.require_cuda()
+    gx, gy = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    dx, dy = (gx[-1] - gx[0]) / (len(gx) - 1), (gy[-1] - gy[0]) / (len(gy) - 1)
+    if not (np.allclose(np.diff(gx), dx, rtol=1e-6) and np.allclose(np.diff(gy), dy, rtol=1e-6)):
+        raise ValueError("gridding='binned' needs uniformly spaced x and y")
+    px_d, py_d = engine.to_device(px), engine.to_device(py)
+    amp, ph = engine.to_device(amplitudes), engine.to_device(phases)
+    n = int(px_d.numel())
+    rf = torch.zeros((4, n), dtype=torch.float64, device="cuda")
+    rf[0], rf[2] = px_d, py_d
+    jf = torch.empty((2, n), dtype=torch.complex128, device="cuda")
+    jf[0] = torch.polar(amp, -ph)                       # amp exp(-i phase): the integrand of U0 (fresnel_integral.py:79)
+    jf[1] = 1.0                                         # its sum is the number of rays in the bin
+    img = engine.ImageBuffer("interferogram", len(gx), len(gy), (gx[0] - dx / 2, gx[-1] + dx / 2), (gy[0] - dy / 2, gy[-1] + dy / 2))
+    engine.optics_image(rf, [], jf=jf, image=img, input_mm=True, want_rays=False)
+    planes = img.planes.to(torch.float64) * (2.0 ** -L.PLANE_FRAC_BITS)
+    count = planes[2].round()
+    u0 = torch.complex(planes[0], planes[1]) / count.clamp(min=1.0)
+    return u0, count.to(torch.int64)
+
+
 def _prepare(a, b, mode, n0, n1, pad_factor, alpha):
     out = torch.empty(((2 * pad_factor + 1) * n0, (2 * pad_factor + 1) * n1), dtype=torch.complex128, device="cuda")
     L.check(L.lib.sp_fresnel_prepare(_ptr(a), _ptr(b), mode, n0, n1, int(pad_factor), float(alpha),
@@ -95,11 +126,25 @@ def fresnel_propagate(U0_prepared, L_, wavelength, z, original_shape, pad_factor
     return out.cpu().numpy() if as_numpy else out
 
 
-def propagate(lwl, x, y, x_length, y_length, jones_vector, amplitudes, phases, z, pad_factor=2, *, return_grids=False):
+def propagate(lwl, x, y, x_length, y_length, jones_vector, amplitudes, phases, z, pad_factor=2, *, return_grids=False,
+              gridding="triangulation"):
     """fresnel_integral.py:61-93.  ``jones_vector`` is what upstream passes under that name: the (4, N) ray array
-    whose rows 0 and 2 are the sample positions.  Returns the complex field (len(y), len(x)) at distance ``z``."""
+    whose rows 0 and 2 are the sample positions.  Returns the complex field (len(y), len(x)) at distance ``z``.
+    ``gridding='triangulation'`` is upstream's LinearNDInterpolator (Qhull on the host, interpolation on the device);
+    ``'binned'`` the device-only coherent mean per node (``bin_to_grid``)."""
     as_numpy = not isinstance(jones_vector, torch.Tensor)
     r = engine.to_device(jones_vector)
+    if gridding == "binned":
+        ok = torch.isfinite(r[0]) & torch.isfinite(r[2])
+        u0, _ = bin_to_grid(r[0][ok], r[2][ok], engine.to_device(amplitudes)[ok], engine.to_device(phases)[ok], x, y)
+        ny, nx = int(u0.shape[0]), int(u0.shape[1])
+        prepared = _prepare(torch.view_as_real(u0.contiguous()), None, 0, ny, nx, pad_factor, 0.4)
+        out = fresnel_propagate(prepared, (x_length, y_length), lwl, z, (ny, nx), pad_factor=pad_factor)
+        if as_numpy:
+            out = out.cpu().numpy()
+        return (out, torch.angle(u0).neg(), u0.abs()) if return_grids else out
+    if gridding != "triangulation":
+        raise ValueError("gridding must be 'triangulation' or 'binned'")
     grids = scatter_to_grid(r[0], r[2], [phases, amplitudes], x, y, fill_value=0.0)
     ny, nx = int(grids.shape[1]), int(grids.shape[2])
     prepared = _prepare(grids[1], grids[0], 1, ny, nx, pad_factor, 0.4)        # U0 = amp exp(-i phase), padded, windowed
