@@ -159,3 +159,27 @@ def test_bench_ncu_evidence_is_tied_to_the_kernel_source(tmp_path, monkeypatch):
     roof = {"traffic": None}
     bench.attach_ncu_static(roof, a, 10000000)
     assert roof["traffic"] is None and roof["ncu_static"] == {"stale": True, "source": os.path.join("profiles", "r2_c2_k_propagate_ncu_full.json")}
+
+
+def test_bench_parity_helpers_and_lattice():
+    """bench.parity_check's ingredients that can be checked without a GPU: the per-row scale of the relative error, NaN
+    pattern handling, and -- the point of the parity block -- that the oracle is stepped on the SAME fixed-step lattice
+    (h, n_steps) that propagator._params hands to the kernel for every workload."""
+    import bench
+    from synthpy_b200 import domain as Dm, propagator as P
+    a = np.array([[1e-3, -2e-3, 1e-12], [0.02, 1e-9, -0.03]])
+    b = a * (1 + 1e-10)
+    s = bench._row_scale(a)
+    assert np.allclose(s, np.sqrt((a ** 2).mean(axis=1)))
+    assert abs(bench._rel(b, a, s) - 1e-10) < 1e-13                       # tiny entries are measured against the row scale
+    assert bench._rel(b, a, 1e-30) > 9e-11
+    c = a.copy(); c[0, 1] = np.nan
+    assert bench._rel(c, a, s) == float("inf")                            # NaN patterns must coincide
+    for w in ("C1", "C2", "C3", "C5"):
+        args = bench.parse(["--workload", w])
+        dom = Dm.ScalarDomain(bench.LENGTHS, 16)                          # cell size only depends on lengths / dims
+        dom.dims = np.array([args.grid] * 3)
+        prm = P._params(dom, bench.EXTENT, bench.LWL, "rk4", None, args.ds_frac * dom.cell_size(), None, None, "fp64", True, False,
+                        False, True, "current", None)
+        h, n = bench.rk4_lattice(args)
+        assert prm.h == h and prm.n_steps == n, w
