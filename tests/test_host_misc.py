@@ -183,3 +183,16 @@ def test_bench_parity_helpers_and_lattice():
                         False, True, "current", None)
         h, n = bench.rk4_lattice(args)
         assert prm.h == h and prm.n_steps == n, w
+
+
+def test_numa_binding_is_best_effort():
+    """distributed.bind_to_local_numa never raises: without a GPU (or without sysfs NUMA information, as inside the GPU
+    pool's containers: numa_node = -1) it reports that nothing was bound and the run proceeds unbound."""
+    from synthpy_b200 import distributed as D
+    before = os.sched_getaffinity(0)
+    r = D.bind_to_local_numa(0)
+    assert isinstance(r, dict) and r.get("bound") in (False, True)
+    if not r["bound"]:
+        assert os.sched_getaffinity(0) == before
+    else:
+        os.sched_setaffinity(0, before)
