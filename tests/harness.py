@@ -168,6 +168,13 @@ class HField:
                           C.c_int(int(self.f64 if aux64 is None else aux64)))
         return out
 
+    def rhs_direct(self, s):
+        s = np.ascontiguousarray(s, dtype=np.float64)
+        out = np.empty_like(s)
+        self.H.lib.hh_rhs_direct(self.h, _p(s), C.c_uint64(s.shape[1]), _p(out), C.c_double(self.omega), C.c_int(int(self.phase)),
+                                 C.c_int(int(self.f64)))
+        return out
+
     def rhs_walk(self, s, near):
         s = np.ascontiguousarray(s, dtype=np.float64)
         out = np.empty_like(s)

@@ -129,6 +129,25 @@ extern "C" void hh_rhs(void* h, const double* s, uint64_t n, double* out, double
     else rhs_t<true, true>(f, s, n, out, omega);
 }
 
+// The cache-free evaluation of the adaptive integrators (rhs_direct): same interface as hh_rhs.
+template <bool PH, bool A64>
+static void rhs_direct_t(const HostField* f, const double* s, uint64_t n, double* out, double omega) {
+    FieldView<double> F = f->view64();
+    for (uint64_t i = 0; i < n; ++i) {
+        Ray<double> r; load(f, s, n, i, r);
+        Deriv<double> d;
+        deriv_direct<double, PH, A64>(F, omega, r.p, r.v, d);
+        for (int k = 0; k < 3; ++k) { out[(uint64_t)f->perm[k] * n + i] = d.dp[k]; out[(uint64_t)(3 + f->perm[k]) * n + i] = d.dv[k]; }
+        out[6 * n + i] = 0; out[7 * n + i] = d.dph; out[8 * n + i] = 0;
+    }
+}
+extern "C" void hh_rhs_direct(void* h, const double* s, uint64_t n, double* out, double omega, int phase, int aux64) {
+    const HostField* f = (const HostField*)h;
+    if (!phase) rhs_direct_t<false, false>(f, s, n, out, omega);
+    else if (!aux64) rhs_direct_t<true, false>(f, s, n, out, omega);
+    else rhs_direct_t<true, true>(f, s, n, out, omega);
+}
+
 // One persistent cell cache walked through the points in order (near = the fixed-step neighbour relocation, else the
 // direct search of the adaptive steppers): must give what a fresh cache gives at every point.
 template <bool NEARP>

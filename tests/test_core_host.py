@@ -479,3 +479,46 @@ def test_tsit5_pid_flavour(H, golden):
     assert abs(b @ A @ c - 1 / 6) < 1e-15 and abs(b @ A @ A @ c - 1 / 24) < 1e-15 and abs(b @ A @ A @ A @ c - 1 / 120) < 1e-15
     assert abs((b * c) @ A @ c - 1 / 8) < 1e-15 and abs(b @ A @ c ** 3 - 1 / 20) < 1e-15 and abs(b @ ((A @ c) ** 2) - 1 / 20) < 1e-15
     assert abs(bt.sum()) < 1e-15 and all(abs(bt @ c ** k) < 1e-15 for k in (1, 2, 3)) and abs(bt @ c ** 4) > 1e-4
+
+
+def test_rhs_direct_matches_reference_and_cached_path(H, golden):
+    """The cache-free evaluation the adaptive integrators use (rhs_direct: guessed cell, table entries and corners in one
+    round trip, verified, reference's sum over corners of value x weight product): (a) against the reference's own dsdt
+    (golden g1: identical in/out-of-bounds pattern incl. points exactly on the rounded end nodes, <= 1e-11; phase lane to the
+    oracle's own rounding floor); (b) against the cell-cached evaluation of the fixed-step kernel to rounding; (c) on
+    non-uniform axes, on nodes, one ulp either side of nodes, outside the grid, and NaN in -> NaN out."""
+    g = golden("g1_rhs")
+    for ph in (False, True):
+        f = H.field(g["ne"], g["x"], g["y"], g["z"], omega_of(float(g["lwl"])), phase=ph, f64=ph)
+        out, ref = f.rhs_direct(g["s"]), g["dsdt_phase%d" % ph]
+        assert np.array_equal(out[:3], ref[:3])
+        assert np.array_equal(out[3:6] == 0, ref[3:6] == 0)
+        assert rel_err(out[3:6], ref[3:6], floor=1e3) < 1e-11
+        cached = f.rhs(g["s"])
+        assert np.max(np.abs(out[3:6] - cached[3:6])) < 1e-13 * np.abs(cached[3:6]).max()
+        if ph:
+            assert np.all(np.abs(out[7] - ref[7]) <= 1e-15 * f.omega + 1e-12 * np.abs(ref[7]))
+    rng = np.random.default_rng(8)
+    x = np.cumsum(rng.uniform(0.5, 2.0, 19)); x = (x - x.mean()) * 1e-3 / 3
+    y = np.sort(rng.uniform(-4e-3, 4e-3, 15)); z = np.linspace(-1, 1, 23) ** 3 * 8e-3
+    ne = 1e25 * (1 + 0.5 * rng.random((19, 15, 23)))
+    d = O.Domain(x, y, z, 8e-3)
+    d.external_ne(ne)
+    d.calc_dndr(1064e-9)
+    f = H.field(ne, x, y, z, omega_of(1064e-9))
+    ax = [np.float64(np.float32(a)) for a in (x, y, z)]
+    n = 6000
+    s = np.zeros((9, n))
+    s[0], s[1], s[2] = rng.uniform(x[0] * 1.1, x[-1] * 1.1, n), rng.uniform(-4.4e-3, 4.4e-3, n), rng.uniform(-8.5e-3, 8.5e-3, n)
+    for k in range(3):                                             # nodes, and one ulp either side of them
+        m = len(ax[k])
+        s[k, 100 * k:100 * k + m] = ax[k]
+        s[k, 1000 + 100 * k:1000 + 100 * k + m] = np.nextafter(ax[k], np.inf)
+        s[k, 2000 + 100 * k:2000 + 100 * k + m] = np.nextafter(ax[k], -np.inf)
+    s[3:6] = 1e8
+    ref = d.dsdt(0.0, s.ravel().copy()).reshape(9, -1)
+    out = f.rhs_direct(s)
+    assert np.array_equal(out[3:6] == 0, ref[3:6] == 0)
+    assert np.max(np.abs(out[3:6] - ref[3:6])) < 1e-11 * np.abs(ref[3:6]).max()
+    s[0, 5] = np.nan
+    assert np.all(np.isnan(f.rhs_direct(s)[3:6, 5]))
