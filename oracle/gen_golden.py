@@ -149,6 +149,123 @@ def minimal_fixture():
     np.savez_compressed(os.path.join(OUT, "g8_minimal.npz"), **g)
 
 
+def jnp_shim():
+    """A ``jax.numpy`` stand-in made of NumPy, for running src/simulator/diagnostics.py UNMODIFIED where jax cannot be
+    installed.  That file uses jax.numpy purely as an array library (no jit / vmap / lax / random in any code path
+    exercised): 18 NumPy-named functions plus the functional update ``a.at[idx].set(v)``.  The stand-in maps the
+    functions to NumPy's float64 ones (== jax with ``jax_enable_x64``, config.py:129-131; elementary functions may differ
+    from XLA's in the last ulp) and gives arrays an ``at`` that returns an updated COPY.  ``array == None`` is False, as it
+    is for a jax array (diagnostics.py:569 relies on it)."""
+    class _Idx:
+        def __init__(self, a, idx):
+            self.a, self.idx = a, idx
+
+        def set(self, v):
+            out = np.array(self.a, copy=True).view(JArray)
+            out[self.idx] = v
+            return out
+
+    class _At:
+        def __init__(self, a):
+            self.a = a
+
+        def __getitem__(self, idx):
+            return _Idx(self.a, idx)
+
+    class JArray(np.ndarray):
+        @property
+        def at(self):
+            return _At(self)
+
+        def __eq__(self, other):
+            return False if other is None else np.ndarray.__eq__(self, other)
+
+        __hash__ = None
+
+    def wrap(v):
+        if isinstance(v, tuple):
+            return tuple(wrap(u) for u in v)
+        return v.view(JArray) if isinstance(v, np.ndarray) else v
+
+    mod = types.ModuleType("jax.numpy")
+    for name in ("abs", "arctan", "array", "asarray", "copy", "diag", "digitize", "exp", "histogram2d", "isnan", "linspace",
+                 "matmul", "real", "rot90", "sqrt", "tanh", "zeros"):
+        setattr(mod, name, (lambda f: lambda *a, **k: wrap(f(*a, **k)))(getattr(np, name)))
+    mod.nan, mod.pi = np.nan, np.pi
+    return mod
+
+
+def import_diagnostics():
+    """src/simulator/diagnostics.py, source untouched, with ``jax.numpy`` -> ``jnp_shim()``, empty matplotlib modules, the
+    real fresnel_integral.py next to it, and an empty ``propagator`` (only ``Interferometry.bkg``, not exercised, uses it)."""
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    jax = types.ModuleType("jax")
+    jax.numpy = jnp_shim()
+    prop = types.ModuleType("propagator")
+    prop.ray_to_Jonesvector = None
+    saved = {k: sys.modules.get(k) for k in ("jax", "jax.numpy", "propagator")}
+    sys.modules.update({"jax": jax, "jax.numpy": jax.numpy, "propagator": prop})
+    sys.path.insert(0, os.path.join(REF, "simulator"))
+    try:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location("ref_diagnostics", os.path.join(REF, "simulator", "diagnostics.py"))
+        dg = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(dg)
+    finally:
+        sys.path.pop(0)
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return dg
+
+
+def diagnostics_fixture():
+    """G9: the CURRENT generation's optics and detector code (src/simulator/diagnostics.py:122-640) executed from its own
+    source through ``import_diagnostics``: every ``*_solve`` layout, ``propagate_E``, the reference beam
+    (``interfere_ref_beam`` on exit rays in metres), ``histogram`` and the per-ray ``histogram_legacy`` loop."""
+    dg = import_diagnostics()
+    rng = np.random.default_rng(9)
+    N, lwl = 3000, 1064e-9
+    rf = np.zeros((4, N))
+    rf[0], rf[2] = rng.uniform(-8e-3, 8e-3, (2, N))                   # exit plane, metres
+    rf[1], rf[3] = rng.normal(0, 4e-3, (2, N))
+    wide = rng.choice(N, 400, replace=False)                          # rays the lens apertures / stops reject
+    rf[1, wide], rf[3, wide] = rng.normal(0, 5e-2, (2, 400))
+    rf[1, :40], rf[3, :40] = rng.normal(0, 2e-6, (2, 40))             # rays the dark-field stop rejects
+    rf[:, 40:44] = np.nan                                             # rays lost before the exit plane
+    Jf = (rng.normal(size=(2, N)) + 1j * rng.normal(size=(2, N))) / np.sqrt(2)
+    g = dict(rf=rf, Jf=Jf, lwl=lwl, L=400.0, R=25.0, focal_plane=3.0, bin_scale=24)
+    kw = dict(focal_plane=3.0, L=400, R=25)
+
+    def image(d, which, **k):
+        quiet(getattr(d, which), bin_scale=24, **k)
+        return np.asarray(d.H)
+
+    for cls, meth, args in (("Shadowgraphy", "single_lens_solve", {}), ("Shadowgraphy", "two_lens_solve", {}),
+                            ("Schlieren", "DF_solve", {"R": 1}), ("Schlieren", "LF_solve", {"R": 1}),
+                            ("Refractometry", "incoherent_solve", {})):
+        d = getattr(dg, cls)(lwl, rf.copy(), **kw)
+        getattr(d, meth)(**args)
+        g[meth + "_rf"], g[meth + "_H"] = np.asarray(d.rf), image(d, "histogram")
+    d = dg.Refractometry(lwl, rf.copy(), Jf.copy(), **kw)
+    d.coherent_solve()
+    g["coherent_solve_rf"], g["coherent_solve_Jf"], g["coherent_solve_H"] = np.asarray(d.rf), np.asarray(d.Jf), image(d, "refractogram")
+    d = dg.Refractometry(lwl, rf.copy(), Jf.copy(), focal_plane=0, L=300, R=6)      # the aperture on r0 rejects rays
+    d.coherent_solve()
+    g["coherent_R6_rf"], g["coherent_R6_Jf"], g["coherent_R6_H"] = np.asarray(d.rf), np.asarray(d.Jf), image(d, "refractogram")
+    d = dg.Interferometry(lwl, rf.copy(), Jf.copy(), **kw)
+    d.interfere_ref_beam(7, 60)                                       # deg >= 45 branch
+    g["ref_beam_7_60_Jf"] = np.asarray(d.Jf)
+    d = dg.Interferometry(lwl, rf.copy(), Jf.copy(), **kw)
+    d.two_lens_solve()
+    g["interf_rf"], g["interf_Jf"], g["interf_H"] = np.asarray(d.rf), np.asarray(d.Jf), image(d, "interferogram")
+    np.savez_compressed(os.path.join(OUT, "g9_diagnostics.npz"), **g)
+
+
 def reference_fixture():
     """The one binary fixture the reference itself holds: evaluation/sergio_testing/integratedPy.npy = ne.sum(axis=2) of
     test_linear_cos(s1=-1, s2=1, n_e0=1e26, Ly=5e-3) on the 100 x 1000 x 100 grid of sergio_testing/notebook.ipynb cells
@@ -355,6 +472,7 @@ def main():
     minimal_fixture()
     reference_fixture()
     fresnel_fixture()
+    diagnostics_fixture()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)) // 1024, "KiB")
 
@@ -362,6 +480,8 @@ def main():
 if __name__ == "__main__":
     if sys.argv[1:] == ["fresnel"]:
         fresnel_fixture()
+    elif sys.argv[1:] == ["diagnostics"]:
+        diagnostics_fixture()
     elif sys.argv[1:] == ["minimal"]:
         minimal_fixture()
         reference_fixture()

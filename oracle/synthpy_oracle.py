@@ -10,7 +10,9 @@ Parity status: **pinned**.  ``oracle/gen_golden.py`` imports the real reference
 seeded inputs and commits the outputs under ``tests/golden/``;  ``tests/test_oracle_golden.py`` holds this
 restatement to those vectors (bit-exact for the RHS / joint RK45 / optics / histograms).  The reference has
 no test-suite of its own; its two docstring known-answer cases (NULL and SLAB test,
-full_solver.py:12-82) are covered in the same test file.
+full_solver.py:12-82) are covered in the same test file.  The optics / detector code of the current generation
+(src/simulator/diagnostics.py) is pinned the same way (g9: its source run with NumPy standing in for jax.numpy);
+the one restatement without a fixture, the diffrax Tsit5 + PID solve, says PARITY UNPINNED where it is defined.
 
 Third-party arithmetic the reference calls and which is therefore called here at the same call sites:
 ``scipy.interpolate.RegularGridInterpolator`` (full_solver.py:232-234,289,344) and
@@ -456,6 +458,35 @@ def run_chain(rf_m, ops, E=None, wl=None):
     return (r, E) if E is not None else r
 
 
+def coherent_solve_current(rf_m, E, wl, L=400, R=25, focal_plane=0):
+    """``Refractometry.coherent_solve`` of the CURRENT generation (src/simulator/diagnostics.py:505-524), which differs
+    from the legacy one (rtm_solver.py:288-331 == chain("refracto_coherent")): the first aperture is applied to ``r0``,
+    not to the rays carried to the first lens, so the positions never make the ``3L/4 - focal_plane`` leg; the field is
+    advanced by the length of that leg all the same (``propagate_E(r2, r1)``) and, this time, across the middle travel.
+    Pinned by tests/golden/g9_diagnostics.npz (the reference's own source run on NumPy arrays)."""
+    k = 2 * np.pi / wl
+    E = np.array(E, dtype=complex, copy=True)
+
+    def advance(E, a, b):                                                # diagnostics.py:315-321
+        return E * np.exp(1.0j * k * np.sqrt((a[0] - b[0]) ** 2 + (a[2] - b[2]) ** 2))
+
+    r0 = m_to_mm(rf_m)
+    r1 = apply_op(r0, ("travel", 3 * L / 4 - focal_plane))
+    r2 = apply_op(r0, ("circ_ap", R))
+    E[:, np.isnan(r2[0])] = np.nan
+    E = advance(E, r2, r1)
+    r3 = apply_op(r2, ("lens", L / 2, L / 2))
+    E = advance(E, r3, r2)
+    r4 = apply_op(r3, ("travel", 3 * L / 2))
+    E = advance(E, r4, r3)
+    r5 = apply_op(r4, ("circ_ap", R))
+    E[:, np.isnan(r5[0])] = np.nan
+    r6 = apply_op(r5, ("lens", L / 3, L / 2))
+    E = advance(E, r6, r5)
+    r7 = apply_op(r6, ("travel", L))
+    return r7, advance(E, r7, r6)
+
+
 def histogram(r, bin_scale=10, pix_x=3448, pix_y=2574, Lx=18, Ly=13.5):
     """rtm_solver.py:156-174: drop NaN rays, np.histogram2d on the detector rectangle, transpose."""
     x, y = r[0], r[2]
@@ -488,7 +519,8 @@ def interferogram(r, E, bin_scale=1, pix_x=3448, pix_y=2574, Lx=18, Ly=13.5, ret
 
 def interfere_ref_beam(rf_m, E, n_fringes=10, deg=20):
     """Reference-beam term of the *JAX-generation* API (/root/reference/src/simulator/diagnostics.py:
-    559-581).  That generation cannot run here (jax absent): this restatement is PARITY UNPINNED.
+    559-581).  Pinned by tests/golden/g9_diagnostics.npz: that file's own source executed with a NumPy stand-in for
+    jax.numpy (oracle/gen_golden.py::import_diagnostics).
     Note the reference evaluates it on ``self.rf`` i.e. exit positions in METRES (diagnostics.py:579)."""
     if deg >= 45:
         deg = -abs(deg - 90)

@@ -220,10 +220,24 @@ class Refractometry(Diagnostic):
     def incoherent_solve(self):                      # diagnostics.py:469-484
         self._run("refracto_incoherent")
 
-    def coherent_solve(self, wl=None):
-        """Legacy semantics (rtm_solver.py:288-331).  The current upstream version (diagnostics.py:505-524)
-        apertures ``self.r0`` instead of ``r1`` and cannot be run for parity (JAX absent): not reproduced."""
-        self._run("refracto_coherent", coherent=True, wl=wl)
+    def coherent_solve(self, wl=None, generation="current"):
+        """``generation='current'``: diagnostics.py:505-524 as upstream ships it -- the first aperture is applied to ``r0``
+        (the rays never make the ``3L/4 - focal_plane`` leg to the first lens) while the field is advanced by the length of
+        that leg (``propagate_E(r2, r1)``) and across every later element.  Two passes of the optics kernel: one whose
+        only output is the advanced field, then the rest of the train on the unmoved rays.
+        ``generation='legacy'``: rtm_solver.py:288-331 (rays carried to the lens; no field advance across the middle
+        travel).  Both are pinned against the reference's own output (tests/golden g9 / g4)."""
+        if generation == "legacy":
+            return self._run("refracto_coherent", coherent=True, wl=wl)
+        if generation != "current":
+            raise ValueError("generation must be 'current' or 'legacy'")
+        if self._Jf is None:
+            raise ValueError("This diagnostic requires a calculated Jf matrix.")
+        L_, wl = self.L, wl or self.wavelength
+        _, jf = engine.optics_image(self._rf_m, [("travel", 3 * L_ / 4 - self.focal_plane)], jf=self._Jf, wavelength=wl)
+        self._ops = [("circ_ap", self.R), ("lens", L_ / 2, L_ / 2), ("travel", 3 * L_ / 2), ("circ_ap", self.R),
+                     ("lens", L_ / 3, L_ / 2), ("travel", L_)]
+        self._rf_det, self._Jf = engine.optics_image(self._rf_m, self._ops, jf=jf, wavelength=wl)
 
     def refractogram(self, bin_scale=1, pix_x=3448, pix_y=2574, clear_mem=False):   # diagnostics.py:526-527
         self.histogram_legacy(bin_scale=bin_scale, pix_x=pix_x, pix_y=pix_y, clear_mem=clear_mem)

@@ -239,7 +239,7 @@ class Schlieren(_Rays, _diag.Schlieren):
 
 class Refractometry(_Rays, _diag.Refractometry):
     def coherent_solve(self, wl=1064e-9):
-        super().coherent_solve(wl=wl)
+        super().coherent_solve(wl=wl, generation="legacy")
 
 
 class Interferometry(_Rays, _diag.Interferometry):

@@ -270,6 +270,70 @@ def test_optics_elements_and_chains(H, golden):
         assert np.max(np.abs(E[m] - g[key + "_rE"][m])) < 1e-6            # k*r ~ 1e8 rad: 1 ulp of the argument ~ 1e-8
 
 
+
+def _host_engine(H, monkeypatch):
+    """Route the diagnostics classes' three engine calls to the host build of the SAME optics code (csrc/ray_core.h::
+    run_optics through tests/host_harness.cpp), so that the Python composition above the C ABI is testable without a GPU."""
+    import torch
+    from synthpy_b200 import engine
+
+    def to_device(a, dtype=torch.float64):
+        return torch.as_tensor(np.ascontiguousarray(a.numpy() if isinstance(a, torch.Tensor) else a)).to(dtype)
+
+    def optics_image(rf, ops, *, jf=None, image=None, wavelength=0.0, input_mm=False, want_rays=True):
+        assert image is None
+        out = H.optics(rf.numpy(), ops, jf=None if jf is None else jf.numpy(), wavelength=wavelength or 0.0, input_mm=input_mm)
+        if jf is None:
+            return torch.from_numpy(out), None
+        return torch.from_numpy(out[0]), torch.from_numpy(out[1])
+
+    monkeypatch.setattr(engine, "to_device", to_device)
+    monkeypatch.setattr(engine, "optics_image", optics_image)
+    monkeypatch.setattr(engine, "require_cuda", lambda: None)
+
+
+def test_current_generation_diagnostics_host(H, golden, monkeypatch):
+    """g9 (src/simulator/diagnostics.py run from its own source): the product's optics math on every layout of the current
+    API, the reference beam, and the two-pass composition behind ``Refractometry.coherent_solve(generation='current')``."""
+    from synthpy_b200 import diagnostics as D
+    g = golden("g9_diagnostics")
+    rf, Jf, lwl = g["rf"], g["Jf"], float(g["lwl"])
+    kw = dict(L=float(g["L"]), R=float(g["R"]), focal_plane=float(g["focal_plane"]))
+
+    def same_field(E, ref):
+        assert np.array_equal(np.isnan(E.real), np.isnan(ref.real))
+        m = ~np.isnan(ref.real)
+        assert m.sum() > 100 and np.max(np.abs(E[m] - ref[m])) < 1e-6         # k * path ~ 1e9 rad: an ulp of the argument ~ 1e-7
+
+    for meth, name in (("single_lens_solve", "shadow_single"), ("two_lens_solve", "shadow_two"), ("DF_solve", "schlieren_DF"),
+                       ("LF_solve", "schlieren_LF"), ("incoherent_solve", "refracto_incoherent")):
+        assert rel_err(H.optics(rf, D.chain_ops(name, **kw)), g[meth + "_rf"], floor=1e-3) < 1e-11, meth
+    _, E = H.optics(rf, [("ref_beam", 7, 60)], jf=Jf)
+    assert rel_err(E.view(np.float64), g["ref_beam_7_60_Jf"].view(np.float64), floor=1e-3) < 1e-12
+    r, E = H.optics(rf, [("ref_beam", 10, 20)] + D.chain_ops("interf_two", **kw), jf=Jf, wavelength=lwl)
+    assert rel_err(r, g["interf_rf"], floor=1e-3) < 1e-11
+    same_field(E, g["interf_Jf"])
+
+    _host_engine(H, monkeypatch)
+    for tag, k in (("coherent_solve", kw), ("coherent_R6", dict(L=300, R=6, focal_plane=0))):
+        d = D.Refractometry(lwl, rf.copy(), Jf.copy(), **k)
+        d.coherent_solve()
+        assert rel_err(d.rf, g[tag + "_rf"], floor=1e-3) < 1e-11, tag
+        same_field(d.Jf, g[tag + "_Jf"])
+    d = D.Refractometry(lwl, rf.copy(), Jf.copy(), **kw)                     # the legacy layout is still there, and different
+    d.coherent_solve(generation="legacy")
+    ro, Eo = O.run_chain(rf, O.chain("refracto_coherent", **kw), E=Jf, wl=lwl)
+    assert rel_err(d.rf, ro, floor=1e-3) < 1e-11 and np.nanmax(np.abs(d.rf - g["coherent_solve_rf"])) > 1.0
+    with pytest.raises(ValueError):
+        d.coherent_solve(generation="jax")
+    with pytest.raises(ValueError):
+        D.Refractometry(lwl, rf.copy(), **kw).coherent_solve()
+    it = D.Interferometry(lwl, rf.copy(), Jf.copy(), **kw)
+    it.two_lens_solve()
+    assert rel_err(it.rf, g["interf_rf"], floor=1e-3) < 1e-11
+    same_field(it.Jf, g["interf_Jf"])
+
+
 def test_bin_search_matches_numpy(H):
     rng = np.random.default_rng(3)
     for lo, hi, nb in [(-9.0, 9.0, 3448), (-6.75, 6.75, 2574), (-9.0, 9.0, 137), (-7.0, 6.0, 63)]:

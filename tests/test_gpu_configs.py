@@ -86,7 +86,7 @@ def test_C3_interferometry_phase(mods):
     ph_o = sf_o[7]
     dphi = np.angle(Jf2[1] * np.exp(-1j * ph_o))
     assert np.max(np.abs(dphi)) < 2e-6 * np.abs(ph_o).max() + 1e-9
-    # reference-beam variant of the current API (parity unpinned upstream): against the oracle's restatement
+    # reference-beam variant of the current API (pinned by golden g9, test_gpu_parity::test_current_generation_diagnostics)
     it2 = D.Interferometry(LWL, rf, Jf)
     it2.two_lens_solve()
     it2.interferogram(bin_scale=40)

@@ -374,6 +374,51 @@ def test_coherent_chains_and_interferogram(sp, golden):
     assert np.max(np.abs(rc.rE[m] - g["refr_coh_rE"][m])) < 1e-6
 
 
+
+def test_current_generation_diagnostics(sp, golden):
+    """g9: the classes of the CURRENT API (src/simulator/diagnostics.py:269-640, executed from its own source by
+    oracle/gen_golden.py::import_diagnostics) -- every ``*_solve`` layout with ``histogram``, the reference beam,
+    ``Interferometry.two_lens_solve`` + ``interferogram``, and both radii of ``Refractometry.coherent_solve`` with its
+    aperture on r0 + ``refractogram``."""
+    from synthpy_b200 import diagnostics as D
+    g = golden("g9_diagnostics")
+    rf, Jf, lwl, bs = g["rf"], g["Jf"], float(g["lwl"]), int(g["bin_scale"])
+    kw = dict(L=float(g["L"]), R=float(g["R"]), focal_plane=float(g["focal_plane"]))
+
+    def same_field(E, ref):
+        assert np.array_equal(np.isnan(E.real), np.isnan(ref.real))
+        m = ~np.isnan(ref.real)
+        assert np.max(np.abs(E[m] - ref[m])) < 1e-6                            # k * path ~ 1e9 rad: an ulp of the argument ~ 1e-7
+
+    def same_image(H, ref):
+        assert H.shape == ref.shape and np.abs(H - ref).sum() <= 1e-3 * ref.sum() and np.max(np.abs(H - ref)) < 1e-4
+
+    for cls, meth, a in ((D.Shadowgraphy, "single_lens_solve", {}), (D.Shadowgraphy, "two_lens_solve", {}),
+                         (D.Schlieren, "DF_solve", {"R": 1}), (D.Schlieren, "LF_solve", {"R": 1}),
+                         (D.Refractometry, "incoherent_solve", {})):
+        d = cls(lwl, rf.copy(), **kw)
+        getattr(d, meth)(**a)
+        assert rel_err(d.rf, g[meth + "_rf"], floor=1e-3) < 1e-11, meth
+        d.histogram(bin_scale=bs)
+        assert np.array_equal(d.H, g[meth + "_H"]), meth
+    it = D.Interferometry(lwl, rf.copy(), Jf.copy(), **kw)
+    it.interfere_ref_beam(7, 60)
+    assert rel_err(it.Jf.view(np.float64), g["ref_beam_7_60_Jf"].view(np.float64), floor=1e-3) < 1e-12
+    it = D.Interferometry(lwl, rf.copy(), Jf.copy(), **kw)
+    it.two_lens_solve()
+    assert rel_err(it.rf, g["interf_rf"], floor=1e-3) < 1e-11
+    same_field(it.Jf, g["interf_Jf"])
+    it.interferogram(bin_scale=bs)
+    same_image(it.H, g["interf_H"])
+    for tag, k in (("coherent_solve", kw), ("coherent_R6", dict(L=300, R=6, focal_plane=0))):
+        d = D.Refractometry(lwl, rf.copy(), Jf.copy(), **k)
+        d.coherent_solve()
+        assert rel_err(d.rf, g[tag + "_rf"], floor=1e-3) < 1e-11, tag
+        same_field(d.Jf, g[tag + "_Jf"])
+        d.refractogram(bin_scale=bs)
+        same_image(d.H, g[tag + "_H"])
+
+
 def test_interferogram_planes_are_order_independent(sp, golden):
     """The complex sums of an interferogram are kept in int64 fixed point (2^-40): identical planes from run to run,
     sorted or unsorted, in one launch or in three uneven shards (what the multi-GPU all-reduce sums), at a fine image

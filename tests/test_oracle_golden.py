@@ -205,3 +205,30 @@ def test_reference_held_fixture_linear_cos():
     d = O.Domain(ax[0], ax[1], ax[2], (dims[2] - 1) * spcs[2] / 2)
     d.test_linear_cos(s1=-1, s2=1, n_e0=1e26, Ly=5e-3)
     assert ref.shape == (100, 1000) and np.array_equal(d.ne.sum(axis=2), ref)
+
+
+def test_current_generation_diagnostics(golden):
+    """g9: src/simulator/diagnostics.py run from its own source on NumPy arrays (oracle/gen_golden.py::import_diagnostics).
+    Pins the op lists of the current API, the reference beam (diagnostics.py:559-581), the field advance
+    (diagnostics.py:315-321), ``coherent_solve`` with its aperture on r0 (diagnostics.py:505-524), ``histogram`` and the
+    per-ray ``histogram_legacy`` loop."""
+    g = golden("g9_diagnostics")
+    rf, Jf, lwl = g["rf"], g["Jf"], float(g["lwl"])
+    kw = dict(L=float(g["L"]), R=float(g["R"]), focal_plane=float(g["focal_plane"]))
+    bs = int(g["bin_scale"])
+    for meth, name in (("single_lens_solve", "shadow_single"), ("two_lens_solve", "shadow_two"), ("DF_solve", "schlieren_DF"),
+                       ("LF_solve", "schlieren_LF"), ("incoherent_solve", "refracto_incoherent")):
+        r = O.run_chain(rf, O.chain(name, **kw))
+        assert np.array_equal(r, g[meth + "_rf"], equal_nan=True), meth
+        assert np.array_equal(O.histogram(r, bin_scale=bs), g[meth + "_H"]) and g[meth + "_H"].sum() > 300, meth
+    assert np.array_equal(O.interfere_ref_beam(rf, Jf, 7, 60), g["ref_beam_7_60_Jf"], equal_nan=True)
+    r, E = O.run_chain(rf, O.chain("interf_two", **kw), E=O.interfere_ref_beam(rf, Jf, 10, 20), wl=lwl)
+    assert np.array_equal(r, g["interf_rf"], equal_nan=True) and np.array_equal(E, g["interf_Jf"], equal_nan=True)
+    assert np.array_equal(O.interferogram(r, E, bin_scale=bs), g["interf_H"])
+    for tag, k in (("coherent_solve", kw), ("coherent_R6", dict(L=300, R=6, focal_plane=0))):
+        r, E = O.coherent_solve_current(rf, Jf, lwl, **k)
+        assert np.array_equal(r, g[tag + "_rf"], equal_nan=True) and np.array_equal(E, g[tag + "_Jf"], equal_nan=True), tag
+        assert np.array_equal(O.interferogram(r, E, bin_scale=bs), g[tag + "_H"]), tag
+    # the two generations of coherent_solve really are different computations
+    r_old = O.run_chain(rf, O.chain("refracto_coherent", **kw))
+    assert np.nanmax(np.abs(r_old - g["coherent_solve_rf"])) > 1.0
