@@ -1,6 +1,13 @@
-"""Generate tests/golden/*.npz by running the REAL reference (legacy generation) in the build container.
+"""Generate tests/golden/*.npz by running the REAL reference in the build container.
 
     python oracle/gen_golden.py            # needs /root/reference; writes tests/golden/
+    python oracle/gen_golden.py diagnostics   # only g9-g12 (current generation, below)
+
+g1-g8: the legacy generation (NumPy/SciPy), imported as it is.  g9-g12: the current generation's files
+(src/simulator/{diagnostics,beam,utils,domain,propagator}.py), whose sources are executed UNMODIFIED with a NumPy stand-in
+registered as ``jax.numpy`` (``jnp_shim`` / ``simulator_stubs`` below): those files use jax.numpy as an array library on the
+paths exercised (no jit / vmap / lax), so what is pinned is their arithmetic in float64 (= ``jax_enable_x64``); XLA's
+elementary functions may differ from NumPy's in the last ulp.  ``propagator.solve`` (diffrax) cannot be run this way.
 
 The reference (/root/reference/src/solvers-legacy/{full_solver,rtm_solver}.py and
 /root/reference/src/field_generator/gaussian3D.py) is imported unmodified with the two zero-source-change
@@ -180,6 +187,12 @@ def jnp_shim():
         def __eq__(self, other):
             return False if other is None else np.ndarray.__eq__(self, other)
 
+        def __iadd__(self, other):                          # jax arrays are immutable: ``a += b`` rebinds, and may broadcast a up
+            return self + other
+
+        def __imul__(self, other):
+            return self * other
+
         __hash__ = None
 
     def wrap(v):
@@ -189,38 +202,139 @@ def jnp_shim():
 
     mod = types.ModuleType("jax.numpy")
     for name in ("abs", "arctan", "array", "asarray", "copy", "diag", "digitize", "exp", "histogram2d", "isnan", "linspace",
-                 "matmul", "real", "rot90", "sqrt", "tanh", "zeros"):
+                 "matmul", "real", "rot90", "sqrt", "tanh", "zeros", "cos", "sin", "shape", "max", "meshgrid", "pad", "stack", "zeros_like",
+                 "sum", "round", "maximum", "expand_dims", "concatenate", "append", "floor", "log10", "gradient", "log", "ones", "power",
+                 "ravel", "reshape", "where", "broadcast_arrays", "empty", "searchsorted"):
         setattr(mod, name, (lambda f: lambda *a, **k: wrap(f(*a, **k)))(getattr(np, name)))
-    mod.nan, mod.pi = np.nan, np.pi
+    mod.nan, mod.pi, mod.int32, mod.float32 = np.nan, np.pi, np.int32, np.float32
     return mod
 
 
-def import_diagnostics():
-    """src/simulator/diagnostics.py, source untouched, with ``jax.numpy`` -> ``jnp_shim()``, empty matplotlib modules, the
-    real fresnel_integral.py next to it, and an empty ``propagator`` (only ``Interferometry.bkg``, not exercised, uses it)."""
+@contextlib.contextmanager
+def simulator_stubs():
+    """What src/simulator/*.py needs to be importable where jax is absent, registered in sys.modules for the duration:
+    ``jax.numpy`` -> ``jnp_shim()``, empty matplotlib modules, ``equinox.Module`` as a plain base class, ``jax.Array``,
+    ``jax.lib.xla_bridge.get_backend().platform == 'cpu'`` (domain.py:141-142), name-only placeholders for the jax internals
+    utils.py:115-118 imports for its own interpolator (not exercised), and an empty ``propagator`` (only
+    ``Interferometry.bkg``, not exercised, uses it).  The sibling modules (utils, printing, fresnel_integral) are the real ones."""
     for name in ("matplotlib", "matplotlib.pyplot"):
         sys.modules.setdefault(name, types.ModuleType(name))
     sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
     jax = types.ModuleType("jax")
+    jax.__path__ = []
     jax.numpy = jnp_shim()
+    jax.Array = np.ndarray
     prop = types.ModuleType("propagator")
     prop.ray_to_Jonesvector = None
-    saved = {k: sys.modules.get(k) for k in ("jax", "jax.numpy", "propagator")}
-    sys.modules.update({"jax": jax, "jax.numpy": jax.numpy, "propagator": prop})
+    eqx = types.ModuleType("equinox")
+    eqx.Module = type("Module", (), {})
+    bridge = types.ModuleType("jax.lib.xla_bridge")
+    bridge.get_backend = lambda: types.SimpleNamespace(platform="cpu")
+    lib = types.ModuleType("jax.lib")
+    lib.__path__, lib.xla_bridge = [], bridge
+    stubs = {"jax": jax, "jax.numpy": jax.numpy, "propagator": prop, "equinox": eqx, "jax.lib": lib, "jax.lib.xla_bridge": bridge}
+    # utils.py:115-118 takes these from jax internals for its own RegularGridInterpolator: the same NumPy stand-ins
+    internals = {"jax._src": {}, "jax._src.dtypes": {"can_cast": np.can_cast}, "jax._src.tree_util": {"register_pytree_node": None},
+                 "jax._src.numpy": {k: getattr(jax.numpy, k) for k in ("asarray", "broadcast_arrays", "empty", "searchsorted", "where", "zeros")},
+                 "jax._src.numpy.util": {"check_arraylike": lambda *a, **k: None,
+                                         "promote_dtypes_inexact": lambda *a: [jax.numpy.asarray(v, dtype=np.result_type(v, np.float32)) for v in a]}}
+    for name, attrs in internals.items():
+        m = types.ModuleType(name)
+        m.__path__ = []
+        for a, v in attrs.items():
+            setattr(m, a, v)
+        stubs[name] = m
+    stubs["jax._src"].dtypes = stubs["jax._src.dtypes"]
+    names = tuple(stubs) + ("utils", "fresnel_integral", "printing")
+    saved = {k: sys.modules.pop(k, None) for k in names}
+    sys.modules.update(stubs)
     sys.path.insert(0, os.path.join(REF, "simulator"))
     try:
-        import importlib.util
-        spec = importlib.util.spec_from_file_location("ref_diagnostics", os.path.join(REF, "simulator", "diagnostics.py"))
-        dg = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(dg)
+        yield
     finally:
         sys.path.pop(0)
-        for k, v in saved.items():
-            if v is None:
-                sys.modules.pop(k, None)
-            else:
-                sys.modules[k] = v
-    return dg
+        for k in names:
+            sys.modules.pop(k, None)
+            if saved[k] is not None:
+                sys.modules[k] = saved[k]
+
+
+def import_simulator(module):
+    """``src/simulator/<module>.py`` executed from its own source under ``simulator_stubs()``."""
+    import importlib.util
+    with simulator_stubs():
+        spec = importlib.util.spec_from_file_location("ref_" + module, os.path.join(REF, "simulator", module + ".py"))
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+    return mod
+
+
+def import_diagnostics():
+    return import_simulator("diagnostics")
+
+
+def domain_fixture():
+    """G11: ``ScalarDomain`` of the current generation (src/simulator/domain.py:11-451) executed from its own source: the
+    float32 axes of a non-cubic grid and the four named profiles, evaluated upstream on the float32-rounded mesh."""
+    dm = import_simulator("domain")
+    lengths, dims = (8e-3, 6e-3, 10e-3), (14, 11, 9)
+    g = dict(lengths=np.array(lengths), dims=np.array(dims))
+    with simulator_stubs():                                        # the constructor imports jax.lib when it is called
+        for name in ("test_null", "test_slab", "test_linear_cos", "test_exponential_cos"):
+            d = quiet(dm.ScalarDomain, lengths, dims, ne_type=name)
+            g[name] = np.asarray(d.ne)
+        g["x"], g["y"], g["z"] = (np.asarray(v) for v in (d.x, d.y, d.z))
+        d = quiet(dm.ScalarDomain, 5e-3, 7)                        # scalar arguments; the mesh is kept for the caller
+        g["cube_x"], g["cube_XX"] = np.asarray(d.x), np.asarray(d.XX)
+    np.savez_compressed(os.path.join(OUT, "g11_domain.npz"), **g)
+
+
+def propagator_fixture():
+    """G12: the array-level functions of the current generation's propagator.py executed from their own source -- the RHS
+    ``dsdt`` (:94-175; gradient of ne / (3.142e-4 omega^2) taken at every call, utils.RegularGridInterpolator :124-214),
+    ``ray_to_Jonesvector`` (:178-298) and ``back_propogate`` (:300-349) -- on the grid and probe states of G1 with the
+    float32 axes a current-generation ScalarDomain holds.  (``solve`` itself is diffrax / jit code and cannot run here.)"""
+    pr = import_simulator("propagator")
+    g1 = np.load(os.path.join(OUT, "g1_rhs.npz"))
+    x, y, z = (np.float32(g1[k]) for k in "xyz")
+    lwl = float(g1["lwl"])
+    omega = 2 * np.pi * pr.c / lwl                                           # propagator.py: omega = 2 pi c / lwl
+    s = g1["s"]
+    g = dict(omega=omega)
+    with simulator_stubs():
+        g["dsdt"] = np.asarray(pr.dsdt(0.0, s.ravel().copy(), False, False, False, False, g1["ne"], None, None, None, x, y, z,
+                                       omega, None, None, None)).reshape(9, -1)
+        rng = np.random.default_rng(5)
+        sf = np.zeros((9, 257))
+        sf[:3] = rng.uniform(-4e-3, 4e-3, (3, 257))
+        sf[3:6] = rng.normal(0, 2e6, (3, 257))
+        sf[6], sf[7], sf[8] = rng.uniform(0.2, 1, 257), rng.uniform(0, 300, 257), rng.uniform(-0.3, 0.3, 257)
+        g["sf"] = sf
+        for pd, col in (("x", 3), ("y", 4), ("z", 5)):
+            st = sf.copy()
+            st[col] = pr.c * (1 - rng.uniform(0, 1e-4, 257))
+            g["sf_" + pd] = st
+            for keep in (False, True):
+                rp, rj = pr.ray_to_Jonesvector(st.copy(), 5e-3, probing_direction=pd, keep_current_plane=keep, return_E=True)
+                g["rtj_%s_%d_p" % (pd, keep)], g["rtj_%s_%d_J" % (pd, keep)] = np.asarray(rp), np.asarray(rj)
+            g["bp_" + pd] = np.asarray(pr.back_propogate(st.copy().view(type(pr.jnp.zeros(1))), 5e-3, pd))
+    np.savez_compressed(os.path.join(OUT, "g12_propagator.npz"), **g)
+
+
+def beam_fixture():
+    """G10: ``Beam`` of the current generation (src/simulator/beam.py:7-303 + utils.py:8-24, NumPy's global RNG) executed from
+    its own source: every beam type that upstream can construct x probing direction, unseeded (np.random.seed set by the
+    caller) and ``seeded=True`` (utils re-seeds with 0 before every draw, so t, u and chi share one stream start)."""
+    bm = import_simulator("beam")
+    g = {}
+    # ('linear' and 'even' cannot be constructed upstream: beam.py:291 deletes a name 'linear' never binds, :222 ranges over a float)
+    for bt, size in (("circular", 4e-3), ("square", 3e-3), ("rectangular", (1e-3, 2.5e-3)), ("rect_trackers", (2e-3, 0.5e-3))):
+        for pd in ("x", "y", "z"):
+            for seeded in (False, True):
+                np.random.seed(17)
+                b = quiet(bm.Beam, 96, size, 2e-4, 6e-3, probing_direction=pd, beam_type=bt, seeded=seeded)
+                g["%s_%s_%d" % (bt, pd, seeded)] = np.asarray(b.s0)
+    np.savez_compressed(os.path.join(OUT, "g10_beam.npz"), **g)
 
 
 def diagnostics_fixture():
@@ -473,6 +587,9 @@ def main():
     reference_fixture()
     fresnel_fixture()
     diagnostics_fixture()
+    beam_fixture()
+    domain_fixture()
+    propagator_fixture()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)) // 1024, "KiB")
 
@@ -482,6 +599,9 @@ if __name__ == "__main__":
         fresnel_fixture()
     elif sys.argv[1:] == ["diagnostics"]:
         diagnostics_fixture()
+        beam_fixture()
+        domain_fixture()
+        propagator_fixture()
     elif sys.argv[1:] == ["minimal"]:
         minimal_fixture()
         reference_fixture()

@@ -334,6 +334,40 @@ def test_current_generation_diagnostics_host(H, golden, monkeypatch):
     same_field(it.Jf, g["interf_Jf"])
 
 
+
+def test_current_generation_propagator_functions(H, golden):
+    """g12: src/simulator/propagator.py's array-level functions executed from their own source (oracle/gen_golden.py::
+    import_simulator): the RHS as the current generation evaluates it (gradient of ne / (3.142e-4 omega^2) in float64 at every
+    call, its own interpolator), ``ray_to_Jonesvector`` with the current output-axis convention and ``back_propogate``."""
+    from synthpy_b200 import propagator as P
+    g, g1 = golden("g12_propagator"), golden("g1_rhs")
+    assert abs(float(g["omega"]) / omega_of(float(g1["lwl"])) - 1) < 1e-12
+    # RHS: same velocities, same in/out-of-grid decisions; accelerations equal to the float32 rounding of the gradient table
+    # that the legacy generation (and the packed field here) keeps -- 1.7e-7 of the largest one, the same distance as
+    # between the two upstream generations themselves
+    f = H.field(g1["ne"], g1["x"], g1["y"], g1["z"], float(g["omega"]))
+    out, ref = f.rhs(g1["s"]), g["dsdt"]
+    assert np.array_equal(out[:3], ref[:3]) and np.array_equal(out[3:6] == 0, ref[3:6] == 0) and not ref[6:].any()
+    scale = np.abs(ref[3:6]).max()
+    assert np.abs(out[3:6] - ref[3:6]).max() < 3e-7 * scale
+    assert np.abs(g1["dsdt_phase0"][3:6] - ref[3:6]).max() < 3e-7 * scale
+    # exit plane, the product's projection code with the axis maps the Python layer passes
+    for pd, p in (("x", 0), ("y", 1), ("z", 2)):
+        st = g["sf_" + pd]
+        a, b = P._out_axes(pd, "current")
+        rf = f.exit(st, p, a, b, 5e-3)
+        assert rel_err(rf, g["rtj_%s_0_p" % pd], floor=1e-7) < 1e-13, pd
+        rj = O.ray_to_jones(st, 5e-3)[1]                                    # the field does not depend on the direction
+        assert np.max(np.abs(rj - g["rtj_%s_0_J" % pd])) < 1e-12 and np.array_equal(g["rtj_%s_0_J" % pd], g["rtj_%s_1_J" % pd])
+        keep = g["rtj_%s_1_p" % pd]
+        assert np.array_equal(keep[0], st[a]) and np.array_equal(keep[2], st[b]) and np.array_equal(keep[[1, 3]], g["rtj_%s_0_p" % pd][[1, 3]])
+        # back_propogate: rows 0..2 hold (a, b) on the exit plane; upstream stores them in ray_p order for 'y' (z, plane, x)
+        bp = g["bp_" + pd]
+        order = {"x": (1, 2), "y": (0, 2), "z": (0, 1)}[pd]
+        assert np.all(bp[p] == 5e-3) and np.array_equal(bp[3:], st[3:])
+        assert rel_err(bp[order[0]], g["rtj_%s_0_p" % pd][0], floor=1e-7) < 1e-13 and rel_err(bp[order[1]], g["rtj_%s_0_p" % pd][2], floor=1e-7) < 1e-13
+
+
 def test_bin_search_matches_numpy(H):
     rng = np.random.default_rng(3)
     for lo, hi, nb in [(-9.0, 9.0, 3448), (-6.75, 6.75, 2574), (-9.0, 9.0, 137), (-7.0, 6.0, 63)]:

@@ -590,6 +590,24 @@ def test_ray_to_jonesvector_and_back_propogate(sp, golden):
     for pd in ("x", "y"):
         rf, _ = P.ray_to_Jonesvector(g3[pd + "_sf"], float(g3["extent"]), probing_direction=pd, axis_convention="legacy")
         assert rel_err(rf, g3[pd + "_rf"], floor=1e-7) < 1e-13
+    # the current generation's own functions (g12: src/simulator/propagator.py:94-349 executed from source)
+    from synthpy_b200 import domain as Dm
+    g12, g1 = golden("g12_propagator"), golden("g1_rhs")
+    for pd, p in (("x", 0), ("y", 1), ("z", 2)):
+        st = g12["sf_" + pd]
+        for keep in (0, 1):
+            rf, Jf = P.ray_to_Jonesvector(st, 5e-3, probing_direction=pd, keep_current_plane=bool(keep), return_E=True)
+            assert rel_err(rf, g12["rtj_%s_%d_p" % (pd, keep)], floor=1e-7) < 1e-13, (pd, keep)
+            assert np.max(np.abs(Jf - g12["rtj_%s_%d_J" % (pd, keep)])) < 1e-12
+        sb, bp = P.back_propogate(st, 5e-3, pd), g12["bp_" + pd]
+        if pd == "y":                                   # upstream stores (z, plane, x) for 'y'; rows keep their meaning here
+            bp = bp[[2, 1, 0, 3, 4, 5, 6, 7, 8]]
+        assert rel_err(sb, bp, floor=1e-7) < 1e-13, pd
+    d = Dm.ScalarDomain((10e-3, 8e-3, 20e-3), (24, 20, 28))
+    d.external_ne(g1["ne"])
+    out, ref = P.rhs(g1["s"], d, lwl=float(g1["lwl"])), g12["dsdt"]
+    assert np.array_equal(out[:3], ref[:3]) and np.array_equal(out[3:6] == 0, ref[3:6] == 0)
+    assert np.abs(out[3:6] - ref[3:6]).max() < 3e-7 * np.abs(ref[3:6]).max()      # float32 gradient table (as the legacy generation)
 
 
 def test_edge_cases(sp, golden):

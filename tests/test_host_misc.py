@@ -136,6 +136,41 @@ def test_beam_types_rect_trackers_and_even():
     assert all((rings == i).sum() == 6 * i for i in range(1, n_c + 1))
 
 
+
+def test_beam_matches_current_generation_source(golden):
+    """g10: src/simulator/beam.py + utils.py executed from their own source (oracle/gen_golden.py::import_simulator, NumPy
+    standing in for jax.numpy; the draws are NumPy's global RNG upstream too).  Every beam type upstream can construct x
+    probing direction x seeded / unseeded: bit for bit.  ('linear' and 'even' raise upstream -- beam.py:291, :222 -- and
+    are this package's reading of the intent: test_beam_types_rect_trackers_and_even.)"""
+    from synthpy_b200 import beam as B
+    g = golden("g10_beam")
+    sizes = {"circular": 4e-3, "square": 3e-3, "rectangular": (1e-3, 2.5e-3), "rect_trackers": (2e-3, 0.5e-3)}
+    assert len(g) == 24
+    for key, ref in g.items():
+        bt, pd, seeded = key.rsplit("_", 2)
+        np.random.seed(17)
+        b = B.Beam(96, sizes[bt], 2e-4, 6e-3, probing_direction=pd, beam_type=bt, seeded=bool(int(seeded)))
+        assert np.array_equal(b.s0, ref), key
+
+
+
+def test_domain_matches_current_generation_source(golden):
+    """g11: src/simulator/domain.py executed from its own source (oracle/gen_golden.py::import_simulator).  The float32
+    axes are identical; the named profiles, which upstream evaluates in float32 on the float32-rounded mesh
+    (domain.py:392-451) and this package in float64 (domain.py docstring here), agree to float32 rounding."""
+    from synthpy_b200 import domain as Dm
+    g = golden("g11_domain")
+    for name in ("test_null", "test_slab", "test_linear_cos", "test_exponential_cos"):
+        d = Dm.ScalarDomain(tuple(g["lengths"]), tuple(g["dims"]), ne_type=name)
+        ref = g[name]
+        assert ref.dtype == np.float32 and np.asarray(d.ne).shape == ref.shape
+        assert np.max(np.abs(np.asarray(d.ne) - ref)) <= 1e-6 * np.abs(ref).max(), name
+        assert all(getattr(d, k).dtype == np.float32 and np.array_equal(getattr(d, k), g[k]) for k in "xyz")
+    assert np.abs(g["test_exponential_cos"]).max() > 1e26 and np.ptp(g["test_slab"]) > 1e23      # the fixture is not trivial
+    d = Dm.ScalarDomain(5e-3, 7)                                             # scalar lengths / dims
+    assert np.array_equal(d.x, g["cube_x"]) and tuple(d.dims) == g["cube_XX"].shape
+
+
 def test_bench_ncu_evidence_is_tied_to_the_kernel_source(tmp_path, monkeypatch):
     """static ncu numbers in the bench line must not survive a kernel change.  attach_ncu_static accepts a
     capture only while its stored hash equals the hash of ray_core.h + synthpy_b200.cu, and reports its DRAM bytes as
