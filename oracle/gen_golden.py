@@ -318,6 +318,14 @@ def propagator_fixture():
                 rp, rj = pr.ray_to_Jonesvector(st.copy(), 5e-3, probing_direction=pd, keep_current_plane=keep, return_E=True)
                 g["rtj_%s_%d_p" % (pd, keep)], g["rtj_%s_%d_J" % (pd, keep)] = np.asarray(rp), np.asarray(rj)
             g["bp_" + pd] = np.asarray(pr.back_propogate(st.copy().view(type(pr.jnp.zeros(1))), 5e-3, pd))
+        # NRL inverse-bremsstrahlung rate and refractive index as the current generation codes them (:23-64)
+        ne3 = 10.0 ** rng.uniform(22, 27.2, (6, 5, 4))                       # up to above the critical density (omega_pe > omega branch)
+        Te3, Z3 = 10.0 ** rng.uniform(0, 3.5, (6, 5, 4)), rng.uniform(1, 30, (6, 5, 4))
+        as_j = lambda a: a.view(type(pr.jnp.zeros(1)))
+        g["k_ne"], g["k_Te"], g["k_Z"] = ne3, Te3, Z3
+        g["kappa"] = np.asarray(pr.kappa(as_j(ne3.copy()), as_j(Te3.copy()), as_j(Z3.copy()), omega))
+        with np.errstate(invalid="ignore"):
+            g["n_refrac"] = np.asarray(pr.n_refrac(as_j(ne3.copy()), omega))
     np.savez_compressed(os.path.join(OUT, "g12_propagator.npz"), **g)
 
 

@@ -351,6 +351,11 @@ def test_current_generation_propagator_functions(H, golden):
     scale = np.abs(ref[3:6]).max()
     assert np.abs(out[3:6] - ref[3:6]).max() < 3e-7 * scale
     assert np.abs(g1["dsdt_phase0"][3:6] - ref[3:6]).max() < 3e-7 * scale
+    # NRL inverse-bremsstrahlung rate (propagator.py:30-61), densities up to above critical: the host field preparation is identical
+    from synthpy_b200 import engine
+    assert np.array_equal(engine.kappa_grid(g["k_ne"], g["k_Te"], g["k_Z"], float(g["omega"])), g["kappa"]) and (g["kappa"] > 0).all()
+    with np.errstate(invalid="ignore"):
+        assert np.array_equal(np.sqrt(1.0 - (5.64e4 * np.sqrt(g["k_ne"] * 1e-6) / float(g["omega"])) ** 2), g["n_refrac"], equal_nan=True)
     # exit plane, the product's projection code with the axis maps the Python layer passes
     for pd, p in (("x", 0), ("y", 1), ("z", 2)):
         st = g["sf_" + pd]
