@@ -11,6 +11,6 @@ Same call shape as the reference's ``src/simulator`` package::
 The compute is hand-written sm_100a CUDA behind a C ABI (include/synthpy_b200.h); there is no CPU fallback.
 """
 from . import _lib  # noqa: F401  (raises ImportError if the CUDA library is not built)
-from . import beam, diagnostics, domain, engine, propagator  # noqa: F401
+from . import beam, diagnostics, domain, engine, out_of_core, propagator  # noqa: F401
 
-__all__ = ["beam", "diagnostics", "domain", "engine", "propagator"]
+__all__ = ["beam", "diagnostics", "domain", "engine", "out_of_core", "propagator"]

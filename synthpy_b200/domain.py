@@ -13,7 +13,8 @@ from . import engine
 class ScalarDomain:
     """Deviations from upstream's container that a caller should know:
       * ``region_count`` / ``auto_batching`` (domain.py:137-243, WIP upstream) are accepted and ignored -- one region, always
-        (a warning is raised for region_count > 1);
+        (a warning is raised for region_count > 1); grids that do not fit in HBM are traced slab by slab with
+        ``out_of_core.solve_out_of_core``, with results identical to one region;
       * the ``test_*`` profiles are evaluated on the float64 mesh and rounded once when the device field is packed (the
         legacy generation's arithmetic, full_solver.py:120,130-167); upstream's current generation evaluates them on the
         float32-rounded mesh (domain.py:392-451), a 1e-7 relative difference in ``ne``;
@@ -43,7 +44,8 @@ class ScalarDomain:
         if region_count not in (None, 1):
             import warnings
             warnings.warn("synthpy_b200.ScalarDomain keeps the whole grid on one GPU (a 1024^3 packed field is 17 GB of 180 GB): "
-                          f"region_count={region_count} is ignored and the domain is traced as one region", stacklevel=2)
+                          f"region_count={region_count} is ignored and the domain is traced as one region "
+                          "(grids beyond HBM: synthpy_b200.out_of_core.solve_out_of_core)", stacklevel=2)
         self.region_count = 1                       # no domain batching needed on a 180 GB part
         self.coord_backup = self.future_dims = None
         # domain.py:230-232: float32-rounded linspace axes

@@ -373,6 +373,94 @@ def test_current_generation_propagator_functions(H, golden):
         assert rel_err(bp[order[0]], g["rtj_%s_0_p" % pd][0], floor=1e-7) < 1e-13 and rel_err(bp[order[1]], g["rtj_%s_0_p" % pd][2], floor=1e-7) < 1e-13
 
 
+
+class _HostSlabBackend:
+    """``out_of_core.trace_slabs`` on the host build of the ray code (tests/host_harness.cpp): same planner and driver as
+    the device path, the arithmetic of csrc/ray_core.h + field_prep.h compiled for the CPU."""
+
+    def __init__(self, H, omega, p, out_axes, extent, phase=False):
+        self.H, self.omega, self.p, self.out_axes, self.extent, self.phase = H, omega, p, out_axes, extent, phase
+        self.launches, self.vscale = [], 1.0
+
+    def to_state(self, s0):
+        return np.array(s0, dtype=np.float64)
+
+    def live_range(self, s, lo, hi):
+        pos, vel = s[:3], s[3:6]
+        lo, hi = np.array(lo)[:, None], np.array(hi)[:, None]
+        gone = (((pos > hi) & (vel >= 0)) | ((pos < lo) & (vel <= 0))).any(0)
+        live = ~gone & np.isfinite(s[:6]).all(0)
+        if not live.any():
+            return None
+        z, vz = pos[self.p][live], vel[self.p][live]
+        return float(z.min()), float(z.max()), float(np.abs(vz).max()) * self.vscale
+
+    def field(self, ne_slab, axes):
+        return self.H.field(np.ascontiguousarray(ne_slab), axes[0], axes[1], axes[2], self.omega, march_axis=self.p,
+                            phase=self.phase, f64=self.phase)
+
+    def steps(self, field, s, m, h, last, want_jf, channels):
+        self.launches.append(m)
+        sf, st = field.rk4(s, m, h, early=True)
+        rf = field.exit(sf, self.p, self.out_axes[0], self.out_axes[1], self.extent) if last else None
+        return sf, st.astype(np.int64), rf, None, None
+
+    def exit(self, s, want_jf):
+        raise AssertionError("not reached in these tests")
+
+    def release(self, field):
+        pass
+
+
+def test_out_of_core_planner_and_driver(H, golden):
+    """Slab-wise tracing (synthpy_b200/out_of_core.py) gives the one-region result BIT FOR BIT: states, steps per ray, exit
+    rays -- turbulent field, probing along z and along x, with the phase lane, slabs of 9 .. 14 of 32 planes."""
+    from synthpy_b200 import out_of_core as OC
+    g = golden("g3_turb")
+    omega, ext = omega_of(float(g["lwl"])), float(g["extent"])
+    for pd, p, pre, out_axes, planes, phase in (("z", 2, "", (0, 1), 9, False), ("z", 2, "", (0, 1), 14, True), ("x", 0, "x_", (1, 2), 11, False)):
+        axes = [g[pre + k] for k in "xyz"]
+        s0 = g[pre + "s0"]
+        cell = np.diff(axes[p]).min()
+        h = 0.5 * cell / C_LIGHT
+        n = int(np.ceil(np.sqrt(8.0) * ext / C_LIGHT / h))
+        whole = H.field(g["ne"], *axes, omega, march_axis=p, phase=phase, f64=phase)
+        sf, steps = whole.rk4(s0, n, h, early=True)
+        rf = whole.exit(sf, p, out_axes[0], out_axes[1], ext)
+        be = _HostSlabBackend(H, omega, p, out_axes, ext, phase)
+        s_sl, st_sl, rf_sl, _, log, _ = OC.trace_slabs(be, s0, OC.array_source(g["ne"], pd), axes, pd, n, h, planes)
+        assert len(log) >= 3 and log[0]["planes"][0] == 0 and log[-1]["planes"][1] == len(axes[p]) - 1, log
+        assert all(b - a + 1 <= planes + 1 for a, b in (e["planes"] for e in log))
+        assert np.array_equal(s_sl, sf, equal_nan=True) and np.array_equal(st_sl, steps) and np.array_equal(rf_sl, rf, equal_nan=True), pd
+        assert steps.max() < n and sum(e["steps"] for e in log) == n              # early exit at work; every step accounted for
+        if phase:
+            assert np.abs(sf[7]).max() > 1.0
+        assert len(be.launches) == len(log)                                        # no slab had to be redone
+    # a planner that under-estimates the speed over-plans the steps: the check on the actual positions catches it, the slab is
+    # redone with fewer steps, and the result is still the one-region result
+    be = _HostSlabBackend(H, omega, p, out_axes, ext, phase)
+    be.vscale = 0.45
+    s_sl, st_sl, rf_sl, _, log, _ = OC.trace_slabs(be, s0, OC.array_source(g["ne"], pd), axes, pd, n, h, planes)
+    assert len(be.launches) > len(log)
+    assert np.array_equal(s_sl, sf, equal_nan=True) and np.array_equal(st_sl, steps) and np.array_equal(rf_sl, rf, equal_nan=True)
+    # the planner alone
+    zc = np.float64(np.float32(np.linspace(-1e-2, 1e-2, 64)))
+    a, b, m, z_stop = OC.plan_slab(zc, -1e-2, -1e-2, C_LIGHT, 1e-13, 500, 16)
+    assert (a, b) == (0, 15) and z_stop == zc[13] and m == int((zc[13] + 1e-2) / (1e-13 * C_LIGHT * 1.02))
+    a, b, m, z_stop = OC.plan_slab(zc, zc[40] + 1e-6, zc[41], C_LIGHT, 1e-13, 500, 16)
+    assert (a, b) == (38, 53) and zc[a + 2] <= zc[40] + 1e-6
+    a, b, m, z_stop = OC.plan_slab(zc, zc[55], zc[56], C_LIGHT, 1e-13, 77, 16)
+    assert b == 63 and m == 77 and z_stop == np.inf
+    with pytest.raises(ValueError):
+        OC.plan_slab(zc, zc[10], zc[30], C_LIGHT, 1e-13, 500, 16)                  # rays spread over more planes than a slab holds
+    # an axis whose float32 spacings are NOT all equal while those of a short window are: the window grows until its stencil
+    # choice (np.gradient's uniform / non-uniform formula) is the full axis's
+    zz = np.concatenate([np.arange(40) * 2.0 ** -10, 40 * 2.0 ** -10 + np.arange(1, 25) * 2.0 ** -10 * (1 + 2.0 ** -20)])
+    assert not OC.axis_is_uniform(zz) and OC.axis_is_uniform(zz[:16])
+    a, b, m, _ = OC.plan_slab(zz, 0.0, 0.0, C_LIGHT, 1e-13, 500, 16)
+    assert a == 0 and b == 40 and not OC.axis_is_uniform(zz[a:b + 1]) and OC.axis_is_uniform(zz[a:b])
+
+
 def test_bin_search_matches_numpy(H):
     rng = np.random.default_rng(3)
     for lo, hi, nb in [(-9.0, 9.0, 3448), (-6.75, 6.75, 2574), (-9.0, 9.0, 137), (-7.0, 6.0, 63)]:

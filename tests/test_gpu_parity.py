@@ -419,6 +419,53 @@ def test_current_generation_diagnostics(sp, golden):
         same_image(d.H, g[tag + "_H"])
 
 
+
+def test_out_of_core_equals_in_core(sp, golden, tmp_path):
+    """Slab-wise tracing of a grid streamed through HBM (synthpy_b200/out_of_core.py; the reference's region batching,
+    domain.py:137-243 + propagator.py:366-450) against the one-region solve: exit rays, Jones vectors, full states, steps
+    per ray and the fused detector image BIT FOR BIT -- slabs of 10 of 32 planes, phase lane on, from an array, from a
+    memory-mapped file and along x."""
+    from synthpy_b200 import diagnostics as D, domain as Dm, out_of_core as OC, propagator as P
+    g = golden("g3_turb")
+    lwl, ext, ne = float(g["lwl"]), float(g["extent"]), g["ne"]
+    lengths, dims = (10e-3, 10e-3, 20e-3), (32, 32, 32)
+    np.random.seed(8)
+    s0 = sp.init_beam(6000, 3e-3, 2e-3, ext, "circular", "z")
+    s0[0, 5] = np.nan                                                       # a lost ray and one that leaves sideways
+    s0[3, 6] = 0.5 * C_LIGHT
+    dom = Dm.ScalarDomain(lengths, dims, phaseshift=True)
+    dom.external_ne(ne)
+    n = 150
+    rf, Jf, _, ex = P.solve(s0, dom, ext, lwl=lwl, return_E=True, method="rk4", n_steps=n, return_state=True)
+    mm = np.memmap(str(tmp_path / "ne.raw"), dtype=np.float64, mode="w+", shape=ne.shape)
+    mm[:] = ne
+    mm.flush()
+    for src in (OC.array_source(ne), OC.array_source(np.memmap(str(tmp_path / "ne.raw"), dtype=np.float64, mode="r", shape=ne.shape))):
+        rf2, Jf2, _, ex2 = OC.solve_out_of_core(s0, src, lengths, dims, ext, slab_planes=10, lwl=lwl, return_E=True, phaseshift=True,
+                                                n_steps=n, return_state=True)
+        assert len(ex2["slabs"]) >= 3 and sum(e["steps"] for e in ex2["slabs"]) == n
+        assert np.array_equal(rf2, rf, equal_nan=True) and np.array_equal(Jf2, Jf, equal_nan=True)
+        assert np.array_equal(ex2["sf"], ex["sf"], equal_nan=True) and np.array_equal(ex2["steps"], ex["steps"])
+        assert ex2["stats"]["ray_steps"] == ex["stats"]["ray_steps"]
+    assert 0 < ex["steps"][100] < n and np.nanmax(np.abs(ex["sf"][7])) > 1.0    # early exit and phase at work
+    # fused detector image from the last slab's launch
+    a, b = D.spec("shadow_two", bin_scale=16), D.spec("shadow_two", bin_scale=16)
+    P.solve_and_image(dom, s0, ext, [a], lwl=lwl, method="rk4", n_steps=n)
+    OC.solve_out_of_core(s0, OC.array_source(ne), lengths, dims, ext, slab_planes=12, lwl=lwl, phaseshift=True, n_steps=n,
+                         diagnostics=[b])
+    assert a.image.result().sum() > 1000 and torch.equal(a.image.result(), b.image.result())
+    # along x, default step (half a cell of the probing axis)
+    domx = Dm.ScalarDomain(lengths, dims, probing_direction="x")
+    domx.external_ne(ne)
+    np.random.seed(9)
+    sx = sp.init_beam(2000, 3e-3, 1e-3, 5e-3, "circular", "x")
+    rfx, _, _, exx = P.solve(sx, domx, 5e-3, lwl=lwl, method="rk4", return_state=True)
+    rfx2, _, _, exx2 = OC.solve_out_of_core(sx, OC.array_source(ne, "x"), lengths, dims, 5e-3, slab_planes=11, lwl=lwl,
+                                            probing_direction="x", return_state=True)
+    assert np.array_equal(rfx2, rfx, equal_nan=True) and np.array_equal(exx2["sf"], exx["sf"], equal_nan=True)
+    assert np.array_equal(exx2["steps"], exx["steps"]) and len(exx2["slabs"]) >= 3
+
+
 def test_interferogram_planes_are_order_independent(sp, golden):
     """The complex sums of an interferogram are kept in int64 fixed point (2^-40): identical planes from run to run,
     sorted or unsorted, in one launch or in three uneven shards (what the multi-GPU all-reduce sums), at a fine image
