@@ -329,6 +329,41 @@ def propagator_fixture():
     np.savez_compressed(os.path.join(OUT, "g12_propagator.npz"), **g)
 
 
+def louis_fixture():
+    """G13: src/solvers-legacy/rtm_solver-louis.py (sympy-lambdified composite matrices; the one place upstream uses a knife
+    edge inside a diagnostic, SchlierenRays.solve :375-391), imported unmodified by path (its file name is not a module
+    name).  Rays are given in mm, as that file expects."""
+    import importlib.util
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    spec = importlib.util.spec_from_file_location("rtm_solver_louis", os.path.join(REF, "solvers-legacy", "rtm_solver-louis.py"))
+    lo = importlib.util.module_from_spec(spec)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")                     # "is" with a literal (:133)
+        spec.loader.exec_module(lo)
+    rng = np.random.default_rng(13)
+    N = 4000
+    r0 = np.zeros((4, N))
+    r0[0], r0[2] = rng.uniform(-6, 6, (2, N))                                # mm
+    r0[1], r0[3] = rng.normal(0, 3e-3, (2, N))
+    r0[1, :300], r0[3, :300] = rng.normal(0, 6e-2, (2, 300))                 # rays the lens apertures reject
+    E = (rng.normal(size=(2, N)) + 1j * rng.normal(size=(2, N))) / np.sqrt(2)
+    g = dict(r0=r0, E=E, L=400.0, R=25.0, displacement=7.5, wl=532e-9)
+    for cls, tag, kw in ((lo.RefractometerRays, "refractometer", {}), (lo.ShadowgraphyRays, "shadowgraphy", {"displacement": 7.5}),
+                         (lo.SchlierenRays, "schlieren", {})):
+        d = cls(r0.copy(), L=400, R=25)
+        d.solve(**kw)
+        g[tag + "_rf"] = d.rf
+        d.histogram(bin_scale=24)
+        g[tag + "_H"] = d.H
+    d = lo.InterferometerRays(r0.copy(), E=E.copy(), L=400, R=25)
+    d.solve(wl=532e-9)
+    g["interferometer_rf"], g["interferometer_rE"] = d.rf, d.rE
+    np.savez_compressed(os.path.join(OUT, "g13_louis.npz"), **g)
+
+
 def beam_fixture():
     """G10: ``Beam`` of the current generation (src/simulator/beam.py:7-303 + utils.py:8-24, NumPy's global RNG) executed from
     its own source: every beam type that upstream can construct x probing direction, unseeded (np.random.seed set by the
@@ -598,6 +633,7 @@ def main():
     beam_fixture()
     domain_fixture()
     propagator_fixture()
+    louis_fixture()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)) // 1024, "KiB")
 
@@ -610,6 +646,8 @@ if __name__ == "__main__":
         beam_fixture()
         domain_fixture()
         propagator_fixture()
+    elif sys.argv[1:] == ["louis"]:
+        louis_fixture()
     elif sys.argv[1:] == ["minimal"]:
         minimal_fixture()
         reference_fixture()

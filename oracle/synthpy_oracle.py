@@ -434,7 +434,8 @@ def chain(name, L=400, R=25, focal_plane=0, **kw):
         # r5 - r4 *after* the in-place aperture, i.e. zero) -> "travel_noE"
         return [("travel", 3 * L / 4 - focal_plane), ("circ_ap", R), ("lens", L / 2, L / 2), ("travel_noE", 3 * L / 2),
                 ("circ_ap", R), ("lens", L / 3, L / 2), ("travel", L)]
-    if name == "schlieren_knife":       # layout of rtm_solver-louis.py:375-391 (SchlierenRays.solve)
+    if name == "schlieren_knife":       # SURVEY.md 8d-C4 (knife edge as the dark-field stop; upstream's own knife-edge train,
+        # rtm_solver-louis.py:375-391, is pinned as an explicit op list in tests: golden g13)
         return [("travel", L), ("circ_ap", R), ("lens", L, L), ("travel", L),
                 ("knife", kw.get("offset", 0.0), kw.get("axis", 2), kw.get("direction", 1)),
                 ("travel", L), ("circ_ap", R), ("lens", L, L), ("travel", L)]

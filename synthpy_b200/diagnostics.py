@@ -109,10 +109,23 @@ def chain_ops(name, L=400, R=25, focal_plane=0, **kw):
     if name == "refracto_coherent":          # field not advanced across the middle travel (rtm_solver.py:308-314)
         return [("travel", 3 * L / 4 - focal_plane), ("circ_ap", R), ("lens", L / 2, L / 2), ("travel_noE", 3 * L / 2),
                 ("circ_ap", R), ("lens", L / 3, L / 2), ("travel", L)]
-    if name == "schlieren_knife":            # layout of rtm_solver-louis.py:375-391
+    if name == "schlieren_knife":            # the dark-field layout with diagnostics.py:226-245's knife edge as the stop
         return [("travel", L), ("circ_ap", R), ("lens", L, L), ("travel", L),
                 ("knife", kw.get("offset", 0.0), kw.get("axis", 2), kw.get("direction", 1)),
                 ("travel", L), ("circ_ap", R), ("lens", L, L), ("travel", L)]
+    # rtm_solver-louis.py:185-438 -- the older sympy-lambdified trains (lens * distance composites, apertures after the lenses;
+    # the only diagnostic upstream that has a knife edge in it: fixed 0.1 mm threshold in the Fourier plane, :128-139,375-391)
+    if name == "louis_refractometer":
+        return [("travel", L), ("lens", L / 2, L / 2), ("circ_ap", R), ("travel", 3 * L / 2), ("lens", L / 3, L / 2),
+                ("circ_ap", R), ("travel", L)]
+    if name == "louis_shadowgraphy":
+        return [("travel", kw.get("displacement", 0)), ("travel", L), ("lens", L / 2, L / 2), ("circ_ap", R), ("travel", 3 * L / 2),
+                ("lens", L / 3, L / 3), ("circ_ap", R), ("travel", L)]
+    if name == "louis_schlieren":
+        return [("travel", L), ("lens", L / 2, L / 2), ("circ_ap", R), ("travel", L / 2), ("knife", 1e-1, 2, -1), ("travel", L),
+                ("lens", L / 3, L / 3), ("circ_ap", R), ("travel", L)]
+    if name == "louis_interferometer":       # no apertures; the field advances across every composite (:397-438)
+        return [("travel", L), ("lens", L / 2, L / 2), ("travel", 3 * L / 2), ("lens", L / 3, L / 3), ("travel", L)]
     raise ValueError(name)
 
 
@@ -212,7 +225,7 @@ class Schlieren(Diagnostic):
     def LF_solve(self, R=1):                         # diagnostics.py:446-460
         self._run("schlieren_LF", R_stop=R)
 
-    def knife_solve(self, offset=0.0, axis="y", direction=1):    # rtm_solver-louis.py:375-391
+    def knife_solve(self, offset=0.0, axis="y", direction=1):    # SURVEY.md 8d-C4 (upstream's own: chain_ops('louis_schlieren'))
         self._run("schlieren_knife", offset=offset, axis={"x": 0, "y": 2}[axis], direction=direction)
 
 

@@ -461,6 +461,27 @@ def test_out_of_core_planner_and_driver(H, golden):
     assert a == 0 and b == 40 and not OC.axis_is_uniform(zz[a:b + 1]) and OC.axis_is_uniform(zz[a:b])
 
 
+
+def test_louis_layouts(H, golden):
+    """g13: src/solvers-legacy/rtm_solver-louis.py run as it is (sympy-lambdified composite matrices).  Its four trains as
+    op lists (``diagnostics.chain_ops('louis_*')``), the knife edge in the Fourier plane included."""
+    from synthpy_b200 import diagnostics as D
+    g = golden("g13_louis")
+    kw = dict(L=float(g["L"]), R=float(g["R"]))
+    for tag, extra in (("refractometer", {}), ("shadowgraphy", {"displacement": float(g["displacement"])}), ("schlieren", {})):
+        r = H.optics(g["r0"], D.chain_ops("louis_" + tag, **kw, **extra), input_mm=True)
+        assert rel_err(r, g[tag + "_rf"], floor=1e-3) < 1e-11, tag
+        nx, ny = 3448 // 24, 2574 // 24
+        ix, iy = H.bins(r[0], -9.0, 9.0, nx, True), H.bins(r[2], -6.75, 6.75, ny, True)
+        ok = (ix >= 0) & (iy >= 0)
+        Hh = np.zeros((ny, nx))
+        np.add.at(Hh, (iy[ok], ix[ok]), 1.0)
+        assert np.array_equal(Hh, g[tag + "_H"]) and Hh.sum() > 500, tag
+    assert np.isnan(g["schlieren_rf"][0]).sum() > np.isnan(g["shadowgraphy_rf"][0]).sum() + 1000      # the knife edge cuts
+    r, E = H.optics(g["r0"], D.chain_ops("louis_interferometer", **kw), jf=g["E"], wavelength=float(g["wl"]), input_mm=True)
+    assert rel_err(r, g["interferometer_rf"], floor=1e-3) < 1e-11 and np.max(np.abs(E - g["interferometer_rE"])) < 1e-5
+
+
 def test_bin_search_matches_numpy(H):
     rng = np.random.default_rng(3)
     for lo, hi, nb in [(-9.0, 9.0, 3448), (-6.75, 6.75, 2574), (-9.0, 9.0, 137), (-7.0, 6.0, 63)]:

@@ -420,6 +420,25 @@ def test_current_generation_diagnostics(sp, golden):
 
 
 
+
+def test_louis_layouts(sp, golden):
+    """g13: the four optical trains of src/solvers-legacy/rtm_solver-louis.py (run as it is) through ``chain_ops('louis_*')``
+    and the optics / binning kernels: detector rays, identical histograms, the field of its interferometer."""
+    from synthpy_b200 import diagnostics as D, engine
+    g = golden("g13_louis")
+    kw = dict(L=float(g["L"]), R=float(g["R"]))
+    r0 = engine.to_device(g["r0"])
+    for tag, extra in (("refractometer", {}), ("shadowgraphy", {"displacement": float(g["displacement"])}), ("schlieren", {})):
+        img = engine.ImageBuffer.for_histogram(24, 3448, 2574, 18, 13.5)
+        r, _ = engine.optics_image(r0, D.chain_ops("louis_" + tag, **kw, **extra), image=img, input_mm=True)
+        assert rel_err(r.cpu().numpy(), g[tag + "_rf"], floor=1e-3) < 1e-11, tag
+        assert np.array_equal(img.result().cpu().numpy(), g[tag + "_H"]), tag
+    r, E = engine.optics_image(r0, D.chain_ops("louis_interferometer", **kw), jf=engine.to_device(g["E"], torch.complex128),
+                               wavelength=float(g["wl"]), input_mm=True)
+    assert rel_err(r.cpu().numpy(), g["interferometer_rf"], floor=1e-3) < 1e-11
+    assert np.max(np.abs(E.cpu().numpy() - g["interferometer_rE"])) < 1e-5
+
+
 def test_out_of_core_equals_in_core(sp, golden, tmp_path):
     """Slab-wise tracing of a grid streamed through HBM (synthpy_b200/out_of_core.py; the reference's region batching,
     domain.py:137-243 + propagator.py:366-450) against the one-region solve: exit rays, Jones vectors, full states, steps
