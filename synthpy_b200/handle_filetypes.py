@@ -257,6 +257,79 @@ def pvti_readin(filename, *, array=0, device=None):
 vti_readin = pvti_readin
 
 
+def pvti_slab_source(filename, *, probing_direction="z", array=0, device=None, scale=1.0):
+    """Out-of-core access to the first cell array of a ``.pvti`` / ``.vti`` dump: returns ``(source, dims, spacing)`` where
+    ``source(k0, k1)`` is the sub-grid of planes [k0, k1) of the probing axis, shaped like ``ne[..., k0:k1]`` (or the
+    corresponding slice for 'x' / 'y') -- what ``out_of_core.solve_out_of_core`` asks for, slab by slab.
+
+    The file stores x fastest and z slowest, so for 'z' a slab of a raw, uncompressed piece is one contiguous byte range of
+    the memory-mapped file: only those pages are read.  Other encodings decode the piece once and keep it.  With ``device``
+    the planes are uploaded in file order and transposed to (x, y, z) on the device; without it a NumPy array is returned."""
+    pieces, whole, spacing = _pieces_of(filename)
+    if not pieces:
+        raise ValueError(f"{filename}: no pieces")
+    p = {"x": 0, "y": 1, "z": 2}[probing_direction]
+    dims = _cells(whole)
+    lo = [whole[0], whole[2], whole[4]]
+    cache = {}
+
+    def flat_of(i):
+        if i not in cache:
+            vti, piece = pieces[i]
+            arrs = piece["cell"]
+            if not arrs:
+                raise ValueError(f"{vti.path}: no cell data")
+            elem = arrs[array] if not isinstance(array, str) else next(e for e in arrs if e.get("Name") == array)
+            if int(elem.get("NumberOfComponents", "1")) != 1:
+                raise ValueError("pvti_slab_source reads scalar cell arrays")
+            cache[i] = vti.array(elem)
+        return cache[i]
+
+    first = pieces[0][1]["cell"]
+    if not first:
+        raise ValueError(f"{pieces[0][0].path}: no cell data")
+    dtype = np.dtype(_VTK_TYPES[(first[array] if not isinstance(array, str) else next(e for e in first if e.get("Name") == array)).get("type")])
+
+    def source(k0, k1):
+        k0, k1 = int(k0), int(k1)
+        if not 0 <= k0 < k1 <= dims[p]:
+            raise IndexError(f"planes [{k0}, {k1}) outside the grid's {dims[p]}")
+        shape = list(dims)
+        shape[p] = k1 - k0
+        if device is None:
+            out = np.empty(shape, dtype)
+        else:
+            import torch
+            out = torch.empty(shape, dtype=torch.from_numpy(np.empty(0, dtype)).dtype, device=device)
+        for i, (vti, piece) in enumerate(pieces):
+            e = piece["extent"]
+            e_lo, e_hi = e[2 * p] - lo[p], e[2 * p + 1] - lo[p]
+            a, b = max(k0, e_lo), min(k1, e_hi)
+            if a >= b:
+                continue
+            c = _cells(e)
+            blk = np.asarray(flat_of(i)).reshape(c[::-1])                  # (z, y, x) of this piece, a view
+            idx = [slice(None)] * 3
+            idx[2 - p] = slice(a - e_lo, b - e_lo)
+            sub = blk[tuple(idx)]
+            dst = [slice(e[0] - lo[0], e[1] - lo[0]), slice(e[2] - lo[1], e[3] - lo[1]), slice(e[4] - lo[2], e[5] - lo[2])]
+            dst[p] = slice(a - k0, b - k0)
+            if device is None:
+                out[tuple(dst)] = sub.transpose(2, 1, 0)
+            else:
+                import torch
+                import warnings
+                with warnings.catch_warnings():              # a mapped file range is read-only; it is only read from
+                    warnings.simplefilter("ignore", UserWarning)
+                    host = torch.from_numpy(np.ascontiguousarray(sub).astype(dtype.newbyteorder("="), copy=False))
+                out[tuple(dst)] = host.to(device).permute(2, 1, 0)
+        if scale != 1.0:
+            out = out * scale
+        return out
+
+    return source, dims, spacing
+
+
 # ------------------------------------------------------------------------------------------------ writing
 def _write_vti(path, arr_f, cells, spacing, name, encoding, compress, block=1 << 15):
     """One-piece ImageData file with ``arr_f`` (flat, x fastest) as cell data in an appended section."""

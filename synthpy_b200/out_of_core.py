@@ -211,3 +211,16 @@ def solve_out_of_core(s0_import, source, lengths, dims, probing_depth, *, slab_p
                      stats=engine.stats_dict(stats))
         return rf, jf, duration, extra
     return rf, jf, duration
+
+
+def solve_from_pvti(s0_import, filename, probing_depth, *, slab_planes, probing_direction="z", scale=1.0, **kw):
+    """``solve_out_of_core`` on a ``.pvti`` / ``.vti`` dump that is never loaded whole: the box is the one the reference's
+    drivers build from the file (half-lengths ``dim * spacing / 2``, pvti_trace_multiprocess.py:45-65 ==
+    ``handle_filetypes.domain_from_pvti``), the slabs come from ``handle_filetypes.pvti_slab_source`` (a contiguous byte
+    range of the mapped file per slab when probing along z)."""
+    from . import handle_filetypes as hf
+    source, dims, spacing = hf.pvti_slab_source(filename, probing_direction=probing_direction, device="cuda", scale=scale)
+    lengths = [float(dims[a] * spacing[a]) for a in range(3)]
+    return solve_out_of_core(s0_import, source, lengths, list(dims), probing_depth, slab_planes=slab_planes,
+                             probing_direction=probing_direction, **kw)
+

@@ -172,6 +172,50 @@ def test_multi_piece_pvti(tmp_path):
     assert dim == (5, 4, 6) and t.is_contiguous() and np.array_equal(t.numpy(), a)
 
 
+
+@pytest.mark.parametrize("encoding,compress", [("raw", False), ("base64", True)])
+def test_slab_source_for_out_of_core_tracing(tmp_path, encoding, compress):
+    """``pvti_slab_source``: planes [k0, k1) of the probing axis straight from the dump (what out_of_core.solve_out_of_core
+    consumes) -- every direction, single- and multi-piece files, NumPy and tensor (host here) paths, and only the mapped
+    byte range for a raw z-slab."""
+    a = _arr((6, 8, 10), "f8", 3) * 1e24
+    hf.export_pvti(a, fname=str(tmp_path / "ne"), encoding=encoding, compress=compress)
+    for pd, ax in (("x", 0), ("y", 1), ("z", 2)):
+        for dev in (None, "cpu"):
+            src, dims, spacing = hf.pvti_slab_source(str(tmp_path / "ne.pvti"), probing_direction=pd, device=dev)
+            assert dims == a.shape
+            for k0, k1 in ((0, a.shape[ax]), (2, 5), (a.shape[ax] - 1, a.shape[ax])):
+                idx = [slice(None)] * 3
+                idx[ax] = slice(k0, k1)
+                got = src(k0, k1)
+                got = got if dev is None else got.numpy()
+                assert got.dtype == a.dtype and np.array_equal(got, a[tuple(idx)]), (pd, dev, k0, k1)
+            with pytest.raises(IndexError):
+                src(3, a.shape[ax] + 1)
+    src, _, _ = hf.pvti_slab_source(str(tmp_path / "ne.pvti"), scale=1e-6)
+    assert np.array_equal(src(1, 4), a[:, :, 1:4] * 1e-6)
+    # multi-piece dump (pieces cut in x and z): slabs that straddle the cuts
+    b = _arr((5, 4, 6), "f4", 5)
+    cuts = [((0, 2), (0, 4), (0, 6)), ((2, 5), (0, 4), (0, 3)), ((2, 5), (0, 4), (3, 6))]
+    pieces = ""
+    for k, ((x0, x1), (y0, y1), (z0, z1)) in enumerate(cuts):
+        raw = b[x0:x1, y0:y1, z0:z1].flatten(order="F").tobytes()
+        ext = f"{x0} {x1} {y0} {y1} {z0} {z1}"
+        _vti(tmp_path / f"part{k}.vti", '<DataArray type="Float32" Name="rnec" format="appended" offset="0"/>', extent=ext,
+             appended=np.array([len(raw)], "<u4").tobytes() + raw)
+        pieces += f'<Piece Extent="{ext}" Source="part{k}.vti"/>\n'
+    with open(tmp_path / "whole.pvti", "w") as fh:
+        fh.write('<?xml version="1.0"?>\n<VTKFile type="PImageData" version="0.1" byte_order="LittleEndian">\n'
+                 '<PImageData WholeExtent="0 5 0 4 0 6" GhostLevel="0" Origin="0 0 0" Spacing="0.5 0.25 2">\n'
+                 '<PCellData Scalars="rnec"><PDataArray type="Float32" Name="rnec"/></PCellData>\n' + pieces + "</PImageData>\n</VTKFile>\n")
+    for pd, ax in (("x", 0), ("z", 2)):
+        src, dims, _ = hf.pvti_slab_source(str(tmp_path / "whole.pvti"), probing_direction=pd)
+        for k0, k1 in ((1, 4), (0, b.shape[ax]), (2, 3)):
+            idx = [slice(None)] * 3
+            idx[ax] = slice(k0, k1)
+            assert np.array_equal(src(k0, k1), b[tuple(idx)]), (pd, k0, k1)
+
+
 def test_tensor_path_equals_numpy_path_and_domain_loader(tmp_path):
     a = np.abs(_arr((8, 6, 10), "f8", 6)) * 1e24
     hf.export_pvti(a, fname=str(tmp_path / "ne"), extent_x=2e-3, extent_y=1.5e-3, extent_z=5e-3)

@@ -483,6 +483,15 @@ def test_out_of_core_equals_in_core(sp, golden, tmp_path):
                                             probing_direction="x", return_state=True)
     assert np.array_equal(rfx2, rfx, equal_nan=True) and np.array_equal(exx2["sf"], exx["sf"], equal_nan=True)
     assert np.array_equal(exx2["steps"], exx["steps"]) and len(exx2["slabs"]) >= 3
+    # straight from a dump on disk: slabs are byte ranges of the mapped .vti; the in-core side loads the same file whole
+    from synthpy_b200 import handle_filetypes as hf
+    hf.export_pvti(ne, fname=str(tmp_path / "dump"), extent_x=5e-3, extent_y=5e-3, extent_z=10e-3)
+    domf, _ = hf.domain_from_pvti(str(tmp_path / "dump.pvti"), phaseshift=True)
+    rff, Jff, _, exf = P.solve(s0, domf, ext, lwl=lwl, return_E=True, method="rk4", n_steps=n, return_state=True)
+    rff2, Jff2, _, exf2 = OC.solve_from_pvti(s0, str(tmp_path / "dump.pvti"), ext, slab_planes=10, lwl=lwl, return_E=True,
+                                             phaseshift=True, n_steps=n, return_state=True)
+    assert np.array_equal(rff2, rff, equal_nan=True) and np.array_equal(Jff2, Jff, equal_nan=True)
+    assert np.array_equal(exf2["sf"], exf["sf"], equal_nan=True) and np.array_equal(exf2["steps"], exf["steps"]) and len(exf2["slabs"]) >= 3
 
 
 def test_interferogram_planes_are_order_independent(sp, golden):
