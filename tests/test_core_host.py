@@ -414,11 +414,12 @@ class _HostSlabBackend:
 
 def test_out_of_core_planner_and_driver(H, golden):
     """Slab-wise tracing (synthpy_b200/out_of_core.py) gives the one-region result BIT FOR BIT: states, steps per ray, exit
-    rays -- turbulent field, probing along z and along x, with the phase lane, slabs of 9 .. 14 of 32 planes."""
+    rays -- turbulent field, probing along z, x and y, with the phase lane, slabs of 9 .. 14 of 32 planes."""
     from synthpy_b200 import out_of_core as OC
     g = golden("g3_turb")
     omega, ext = omega_of(float(g["lwl"])), float(g["extent"])
-    for pd, p, pre, out_axes, planes, phase in (("z", 2, "", (0, 1), 9, False), ("z", 2, "", (0, 1), 14, True), ("x", 0, "x_", (1, 2), 11, False)):
+    for pd, p, pre, out_axes, planes, phase in (("z", 2, "", (0, 1), 9, False), ("z", 2, "", (0, 1), 14, True), ("x", 0, "x_", (1, 2), 11, False),
+                                                  ("y", 1, "y_", (2, 0), 12, True)):
         axes = [g[pre + k] for k in "xyz"]
         s0 = g[pre + "s0"]
         cell = np.diff(axes[p]).min()
