@@ -21,7 +21,8 @@ that nothing about the result depends on it:
 
 The slab source is a callable ``source(k0, k1) -> ne[..., k0:k1 along the probing axis]`` (NumPy array, ``np.memmap`` of a
 raw dump, or CUDA tensor): ``array_source`` wraps an array-like.  One slab is resident at a time; the next is packed after
-the rays have left the current one (no overlap of upload and tracing yet).
+the rays have left the current one.  ``PrefetchingSource`` overlaps the host-side read of the next slab with the tracing;
+upload and packing are not overlapped yet.
 """
 from time import time
 
@@ -42,6 +43,63 @@ def array_source(ne, probing_direction="z"):
         idx[axis] = slice(k0, k1)
         return ne[tuple(idx)]
     return source
+
+
+class PrefetchingSource:
+    """Wraps a HOST slab source so that the next slab is read (page faults, decoding, strided copy) on a worker thread while
+    the GPU traces the current one.  After serving planes [k0, k1) it starts fetching the window the planner is expected to
+    ask for next -- it begins ``back`` planes before k1 (the planner restarts MARGIN planes behind the slowest live ray, so
+    consecutive slabs overlap by a few planes) -- and serves any later request that lies inside a window it holds by
+    slicing it; anything else falls through to the wrapped source.  Pure data plumbing: what is returned is what the wrapped
+    source would return.  Only for sources that return NumPy arrays (a worker thread must not touch the CUDA stream)."""
+
+    def __init__(self, source, n_planes, axis, back=16):
+        import threading
+        self._source, self._n, self._axis, self._back = source, int(n_planes), int(axis), int(back)
+        self._threading = threading
+        self._job = None                    # (k0, k1, thread, result holder)
+        self.hits = self.misses = 0
+
+    def _start(self, k0, k1):
+        box = {}
+
+        def work():
+            try:
+                box["data"] = np.ascontiguousarray(self._source(k0, k1))
+            except Exception as e:          # surfaced on the main thread when (if) the window is asked for
+                box["error"] = e
+        t = self._threading.Thread(target=work, daemon=True)
+        t.start()
+        self._job = (k0, k1, t, box)
+
+    def __call__(self, k0, k1):
+        k0, k1 = int(k0), int(k1)
+        out = None
+        if self._job is not None:
+            j0, j1, t, box = self._job
+            if j0 <= k0 and k1 <= j1:
+                t.join()
+                if "error" in box:
+                    raise box["error"]
+                idx = [slice(None)] * 3
+                idx[self._axis] = slice(k0 - j0, k1 - j0)
+                out = box["data"][tuple(idx)]
+                self.hits += 1
+            else:
+                t.join()                    # a window nobody wants: let the read finish, then drop it
+            self._job = None
+        if out is None:
+            out = self._source(k0, k1)
+            self.misses += 1
+        if k1 < self._n:
+            n0 = max(0, k1 - self._back)
+            self._start(n0, min(self._n, n0 + (k1 - k0) + self._back))
+        return out
+
+    def close(self):
+        if self._job is not None:
+            self._job[2].join()
+            self._job = None
 
 
 def axis_is_uniform(a32):
@@ -168,12 +226,13 @@ def trace_slabs(backend, s0, source, axes, probing_direction, n_steps, h, slab_p
 
 def solve_out_of_core(s0_import, source, lengths, dims, probing_depth, *, slab_planes, probing_direction="z", lwl=1064e-9,
                       return_E=False, phaseshift=False, phase_f64=False, n_steps=None, ds=None, sort=True,
-                      axis_convention="current", diagnostics=(), return_state=False):
+                      axis_convention="current", diagnostics=(), return_state=False, prefetch=False):
     """``propagator.solve(..., method='rk4')`` for a grid delivered in slabs of ``slab_planes`` planes of the probing axis
     by ``source(k0, k1)``.  ``lengths`` / ``dims`` describe the whole grid as ``ScalarDomain`` takes them (axes
     ``linspace(-L/2, L/2, n)`` rounded to float32).  Same outputs as ``solve``: ``(rf, Jf, duration)`` (+ a dict with
     'sf', 'steps', 'slabs', 'stats' when ``return_state``); ``diagnostics`` (``DiagnosticSpec`` list) are binned by the
-    last slab's launch, fused as in ``solve_and_image``."""
+    last slab's launch, fused as in ``solve_and_image``.  ``prefetch=True`` (host sources only) reads the next slab on a
+    worker thread while the current one is traced (``PrefetchingSource``)."""
     import torch
     from . import propagator
     engine.require_cuda()
@@ -198,10 +257,17 @@ def solve_out_of_core(s0_import, source, lengths, dims, probing_depth, *, slab_p
                              extent, sort)
     chans = [(d.ops, d.image, d.wavelength if d.wavelength else lwl) for d in diagnostics]
     as_numpy = not isinstance(s0_import, torch.Tensor)
+    if prefetch:
+        pa = engine.AXIS[probing_direction]
+        source = PrefetchingSource(source, int(dims[pa]), pa)
     torch.cuda.synchronize()
     start = time()
-    sf, steps, rf, jf, log, stats = trace_slabs(backend, s0_import, source, axes, probing_direction, n_steps, h, slab_planes,
-                                                want_jf=return_E, channels=chans)
+    try:
+        sf, steps, rf, jf, log, stats = trace_slabs(backend, s0_import, source, axes, probing_direction, n_steps, h, slab_planes,
+                                                    want_jf=return_E, channels=chans)
+    finally:
+        if prefetch:
+            source.close()
     torch.cuda.synchronize()
     duration = time() - start
     if as_numpy:

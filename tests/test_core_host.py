@@ -444,6 +444,33 @@ def test_out_of_core_planner_and_driver(H, golden):
     s_sl, st_sl, rf_sl, _, log, _ = OC.trace_slabs(be, s0, OC.array_source(g["ne"], pd), axes, pd, n, h, planes)
     assert len(be.launches) > len(log)
     assert np.array_equal(s_sl, sf, equal_nan=True) and np.array_equal(st_sl, steps) and np.array_equal(rf_sl, rf, equal_nan=True)
+    # the same trace with the next slab read on a worker thread: identical result, every slab after the first served from the
+    # prefetched window; a request outside the window falls through to the wrapped source; errors surface on the caller
+    be = _HostSlabBackend(H, omega, p, out_axes, ext, phase)
+    calls = []
+
+    def slow_source(k0, k1, inner=OC.array_source(g["ne"], pd)):
+        calls.append((k0, k1))
+        return inner(k0, k1)
+    pf = OC.PrefetchingSource(slow_source, len(axes[p]), p)
+    s_pf, st_pf, rf_pf, _, log_pf, _ = OC.trace_slabs(be, s0, pf, axes, pd, n, h, planes)
+    pf.close()
+    assert np.array_equal(s_pf, sf, equal_nan=True) and np.array_equal(st_pf, steps) and np.array_equal(rf_pf, rf, equal_nan=True)
+    assert pf.misses == 1 and pf.hits == len(log_pf) - 1 >= 2
+    pf = OC.PrefetchingSource(slow_source, len(axes[p]), p, back=4)
+    idx = [slice(None)] * 3
+    idx[p] = slice(20, 26)
+    assert np.array_equal(pf(0, 8), slow_source(0, 8)) and np.array_equal(pf(20, 26), g["ne"][tuple(idx)]) and pf.misses == 2
+    pf.close()
+
+    def broken(k0, k1):
+        if k0 > 0:
+            raise OSError("disk")
+        return slow_source(k0, k1)
+    pf = OC.PrefetchingSource(broken, len(axes[p]), p, back=4)
+    pf(0, 8)
+    with pytest.raises(OSError):
+        pf(6, 12)
     # the planner alone
     zc = np.float64(np.float32(np.linspace(-1e-2, 1e-2, 64)))
     a, b, m, z_stop = OC.plan_slab(zc, -1e-2, -1e-2, C_LIGHT, 1e-13, 500, 16)
