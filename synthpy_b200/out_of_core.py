@@ -183,7 +183,8 @@ class _DeviceBackend:
 
 def trace_slabs(backend, s0, source, axes, probing_direction, n_steps, h, slab_planes, *, want_jf=False, channels=()):
     """The slab loop, independent of where the arithmetic runs (``backend``: the device, or the host build of the same ray
-    code in the tests).  Returns (state, steps per ray, rf, jf, log) with ``log`` one dict per slab."""
+    code in the tests).  Returns (state, steps per ray, rf, jf, log, stats) with ``log`` one dict per slab (planes, steps taken,
+    range of the live rays before it) and ``stats`` the launch counters summed over the slabs (None on the host build)."""
     p = engine.AXIS[probing_direction]
     ax64 = [np.asarray(np.float32(a), dtype=np.float64) for a in axes]
     zc = ax64[p]
