@@ -329,6 +329,25 @@ def propagator_fixture():
     np.savez_compressed(os.path.join(OUT, "g12_propagator.npz"), **g)
 
 
+def current_solve_fixture():
+    """G14: the current generation end to end on its SciPy path -- ``domain.ScalarDomain(ne_type=...)`` ->
+    ``beam.Beam`` -> ``propagator.solve(..., parallelise=False)`` (``solve_ivp`` RK45 over all rays jointly with the
+    current ``dsdt``, propagator.py:466-474) -> ``ray_to_Jonesvector`` -- every file executed from its own source."""
+    dm, bm, pr = import_simulator("domain"), import_simulator("beam"), import_simulator("propagator")
+    lengths, dims = (6e-3, 6e-3, 8e-3), (28, 24, 36)
+    g = dict(lengths=np.array(lengths), dims=np.array(dims), lwl=1064e-9)
+    with simulator_stubs():
+        for tag, pd, ext in (("z", "z", 4e-3), ("x", "x", 3e-3)):
+            dom = quiet(dm.ScalarDomain, lengths, dims, ne_type="test_exponential_cos", probing_direction=pd)
+            np.random.seed(21)
+            beam = quiet(bm.Beam, 160, 1.5e-3, 1e-4, ext, probing_direction=pd)
+            s0 = np.asarray(beam.s0).copy()
+            rf, Jf, _ = quiet(pr.solve, beam.s0, dom, ext, return_E=True, parallelise=False, lwl=1064e-9)
+            g[tag + "_s0"], g[tag + "_rf"], g[tag + "_Jf"], g[tag + "_extent"] = s0, np.asarray(rf), np.asarray(Jf), ext
+        g["ne"] = np.asarray(dom.ne)
+    np.savez_compressed(os.path.join(OUT, "g14_current_solve.npz"), **g)
+
+
 def louis_fixture():
     """G13: src/solvers-legacy/rtm_solver-louis.py (sympy-lambdified composite matrices; the one place upstream uses a knife
     edge inside a diagnostic, SchlierenRays.solve :375-391), imported unmodified by path (its file name is not a module
@@ -633,6 +652,7 @@ def main():
     beam_fixture()
     domain_fixture()
     propagator_fixture()
+    current_solve_fixture()
     louis_fixture()
     for fn in sorted(os.listdir(OUT)):
         print(fn, os.path.getsize(os.path.join(OUT, fn)) // 1024, "KiB")
@@ -646,6 +666,7 @@ if __name__ == "__main__":
         beam_fixture()
         domain_fixture()
         propagator_fixture()
+        current_solve_fixture()
     elif sys.argv[1:] == ["louis"]:
         louis_fixture()
     elif sys.argv[1:] == ["minimal"]:

@@ -232,3 +232,26 @@ def test_current_generation_diagnostics(golden):
     # the two generations of coherent_solve really are different computations
     r_old = O.run_chain(rf, O.chain("refracto_coherent", **kw))
     assert np.nanmax(np.abs(r_old - g["coherent_solve_rf"])) > 1.0
+
+
+def test_current_generation_solve_end_to_end(golden):
+    """g14: the CURRENT generation from domain to exit rays on its SciPy path (``ScalarDomain(ne_type=...)`` -> ``Beam`` ->
+    ``propagator.solve(parallelise=False)`` = solve_ivp RK45 over all rays jointly with the current ``dsdt``,
+    propagator.py:466-474 -> ``ray_to_Jonesvector``), every file run from its own source.  The legacy-generation algorithm
+    this oracle restates (and the CUDA path is held to at 1e-9, test_gpu_parity::test_rk45_joint_is_the_shipped_solver) lands
+    on the same rays: the two upstream generations differ only in where float32 rounding enters the gradient table
+    (float32(ne / nc) vs float32(ne) / float32(nc)), amplified by a strongly refracting field."""
+    g = golden("g14_current_solve")
+    axes = [np.linspace(-L / 2, L / 2, int(n)) for L, n in zip(g["lengths"], g["dims"])]
+    assert g["ne"].dtype == np.float32 and g["ne"].max() > 5e25
+    for tag in ("z", "x"):
+        ext = float(g[tag + "_extent"])
+        d = O.Domain(*axes, ext, phaseshift=False, probing_direction=tag)
+        d.external_ne(np.float64(g["ne"]))
+        d.calc_dndr(float(g["lwl"]))
+        rf, Jf = O.ray_to_jones(d.solve_joint(g[tag + "_s0"]), ext, probing_direction=tag)
+        ref = g[tag + "_rf"]
+        rms = np.sqrt((ref ** 2).mean(axis=1))
+        assert not np.isnan(ref).any() and rms[1] > 5e-3                       # milliradian deflections: the field does something
+        assert np.all(np.abs(rf - ref).max(axis=1) < 2e-4 * rms), (tag, np.abs(rf - ref).max(axis=1) / rms)
+        assert np.array_equal(Jf, g[tag + "_Jf"])
